@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""Benchmark of the cytopath sampler hot path on B200 (contract: see the task statement / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c4|c3|c2|c1]
+    torchrun --nproc-per-node N bench.py --gpus N ...        (one rank per GPU, NCCL)
+
+A "step" is one pass of the hot path over one batch: every rank advances its share of a
+sampling round (walkers_per_gpu walkers x (max_steps-1) transitions) through the step kernel K2
+with the graph resident in HBM.  `value` = walker-steps/s over all ranks (CUDA events, max over
+ranks).  `e2e` = the same metric through the C ABI with HOST buffers: upload of the CSR from
+pinned host memory + K1 + K2 + K3 + read-back of the kept index and a sample of kept rows.
+`--impl reference` times the reference's CPU algorithm (faithful joblib port, all host cores).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+os.environ.setdefault("TQDM_DISABLE", "1")
+
+WORKLOADS = {
+    # name: (cells, k, branches, root stems, walkers per GPU, max_steps)  -- BASELINE.json configs
+    "c1": dict(n=3_696, k=30, branches=4, stems=1, walkers=444_000, max_steps=108, desc="configs[0] graph: 3,696 cells k=30"),
+    "c2": dict(n=5_780, k=30, branches=5, stems=2, walkers=710_000, max_steps=200, desc="configs[1] graph: 5,780 cells k=30, 200 steps"),
+    "c3": dict(n=100_000, k=30, branches=8, stems=1, walkers=1_000_000, max_steps=200, desc="configs[2]: 100k cells k=30, 1M walkers x 200 steps (L2-resident)"),
+    "c4": dict(n=1_000_000, k=50, branches=16, stems=1, walkers=1_250_000, max_steps=500,
+               desc="configs[3]: 1M cells k=50 (51M nnz), 10M walkers x 500 steps / 8 GPUs = 1.25M walkers per GPU (HBM-bound)"),
+    "tiny": dict(n=20_000, k=30, branches=4, stems=1, walkers=100_000, max_steps=100, desc="developer smoke size"),
+}
+
+
+def env_world():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def make_graph(w, world):
+    from cytopath_b200 import synth
+    from cytopath_b200.sampler import _canonical_csr
+    g = synth.branching_graph(n=w["n"], k=w["k"], n_branches=w["branches"], n_root_stems=w["stems"], seed=0,
+                              workers=max(1, host_cores() // world))
+    C = _canonical_csr(g.T)
+    roots = np.where(np.isin(g.clusters, g.root_clusters))[0].astype(np.int32)
+    return g, C, roots
+
+
+class ClockSampler:
+    """nvidia-smi clocks line of B200_PROFILING.md, sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.proc = gpu, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons, power = [], [], set(), []
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": float(max(power))}
+
+
+def mean_visited_row_len(C, seq_sample):
+    lens = np.diff(C.indptr)
+    return float(lens[seq_sample[:, :-1].ravel()].mean())
+
+
+def cpu_baseline_sample(C, g, roots, max_steps, cdf_mode, budget_s=12.0):
+    """Bounded sample of the same workload on the host cores: faithful joblib port (kind 'port')."""
+    from joblib import Parallel
+    from oracle import cpu_baseline as cb
+    cores = host_cores()
+    prep = cb.prepare(C, cdf_mode)
+    sample_roots = roots[: max(4 * cores, 8)]
+    if len(sample_roots) < 4 * cores:
+        sample_roots = np.resize(roots, 4 * cores)
+    with Parallel(n_jobs=cores) as pool:
+        cb.joblib_port_rate(prep, sample_roots[:cores], g.clusters, min(max_steps, 20), 1, cores, pool)      # warm the pool
+        rate, dt, _ = cb.joblib_port_rate(prep, sample_roots, g.clusters, max_steps, 1, cores, pool)          # calibrate
+        sims = int(max(1, min(4096, budget_s / max(dt, 1e-3))))
+        if sims > 1:
+            rate, dt, _ = cb.joblib_port_rate(prep, sample_roots, g.clusters, max_steps, sims, cores, pool)
+    c_rate, c_dt, c_thr = cb.c_port_rate(prep, np.resize(roots, 4096), max_steps, max(1, int(2e8 / (4096 * max_steps))))
+    sample = "%d root cells x %d walkers x %d steps, joblib(n_jobs=%d) over root cells, %.1f s" % (
+        len(sample_roots), sims, max_steps, cores, dt)
+    return ({"value": rate, "unit": "walker-steps/s", "cores": cores, "kind": "port", "sample": sample},
+            {"value": c_rate, "unit": "walker-steps/s", "cores": c_thr, "kind": "port-c-openmp",
+             "sample": "oracle/walk.c, %.2f s" % c_dt})
+
+
+def run_reference(args, w):
+    """Reference arm: the reference's CPU algorithm for this path (joblib fan-out of the
+    pure-Python step loop, markov_chain_sampler.py:35-52,:306-308) on all host cores."""
+    rank, _, world = env_world()
+    if rank != 0:
+        return
+    from joblib import Parallel
+    from oracle import cpu_baseline as cb
+    g, C, roots = make_graph(w, 1)
+    cores = host_cores()
+    mode = 1 if args.cdf_mode == "exact" else 0
+    prep = cb.prepare(C, mode)
+    sample_roots = np.resize(roots, 4 * cores)
+    max_steps = w["max_steps"]
+    times = []
+    with Parallel(n_jobs=cores) as pool:
+        cb.joblib_port_rate(prep, sample_roots[:cores], g.clusters, min(max_steps, 20), 1, cores, pool)
+        _, dt1, _ = cb.joblib_port_rate(prep, sample_roots, g.clusters, max_steps, 1, cores, pool)
+        sims = int(max(1, min(4096, 6.0 / max(dt1, 1e-3))))            # ~6 s per step
+        for i in range(args.warmup + args.steps):
+            rate, dt, _ = cb.joblib_port_rate(prep, sample_roots, g.clusters, max_steps, sims, cores, pool)
+            if i >= args.warmup:
+                times.append(dt)
+    steps_per = len(sample_roots) * sims * (max_steps - 1)
+    value = steps_per * len(times) / sum(times)
+    sample = "%d root cells x %d walkers x %d steps per step, joblib(n_jobs=%d)" % (len(sample_roots), sims, max_steps, cores)
+    line = {
+        "impl": "reference", "metric": "walker_steps_per_sec", "value": value, "unit": "walker-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if mode else "f32", "data": "synthetic",
+        "config": {"workload": w["desc"], "cells": w["n"], "k": w["k"], "max_steps": max_steps, "cdf_mode": args.cdf_mode},
+        "cpu_baseline": {"value": value, "unit": "walker-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "walker-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args, w):
+    import torch
+    import torch.distributed as dist
+    from cytopath_b200 import _lib
+
+    rank, local_rank, world = env_world()
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    _lib.require_device(local_rank)
+    L = _lib.load()
+    mode = _lib.CDF_EXACT if args.cdf_mode == "exact" else _lib.CDF_REFERENCE
+
+    g, C, roots = make_graph(w, world)
+    max_steps, nt = w["max_steps"], w["max_steps"] - 1
+    W = args.walkers or w["walkers"]
+    total = W * world
+    n_roots = len(roots)
+    sims_per_root = -(-total // n_roots)
+    w0 = rank * W
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    # ---- resident state: graph (K1), roots, trajectory buffer
+    graph = _lib.Graph(C, mode, local_rank)
+    info = graph.info()
+    kernel_name = graph.variant_name(args.variant)
+    d_roots = torch.tensor(roots, dtype=torch.int32, device=dev)
+    d_seq = torch.empty((W, max_steps), dtype=torch.int32, device=dev)
+    d_miss = torch.zeros(1, dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream()
+    sptr = ctypes.c_void_p(stream.cuda_stream)
+
+    def step(i):
+        _lib.check(L.cyp_walk_device(graph.handle, d_roots.data_ptr(), n_roots, sims_per_root, w0, W, nt, args.seed, i,
+                                     None, d_seq.data_ptr(), d_miss.data_ptr(), args.variant, sptr))
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = total * nt * args.steps / (ms_max * 1e-3)
+    sample = d_seq[:: max(1, W // 2000)].cpu().numpy()
+    kbar = mean_visited_row_len(C, sample)
+    elem = 8 if mode == _lib.CDF_EXACT else 4
+    bytes_per_step = elem * kbar + 16.0
+    ms_launch = ms / args.steps                                  # this rank's kernel: one launch per step
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    else:
+        peak, peak_src = 6650.0, "fallback of B200_PROFILING.md"
+    achieved = W * nt * bytes_per_step / (ms_launch * 1e-3) / 1e9
+    assert int(d_miss.item()) == 0, "walkers hit rows without a CDF crossing"
+
+    # ---- e2e through the C ABI with host buffers (pinned), every step: upload CSR + K1 + round (K2+K3) + read-back
+    row_ptr = torch.from_numpy(np.ascontiguousarray(C.indptr, dtype=np.int64)).pin_memory()
+    col = torch.from_numpy(np.ascontiguousarray(C.indices, dtype=np.int32)).pin_memory()
+    val = torch.from_numpy(np.ascontiguousarray(C.data, dtype=np.float64)).pin_memory()
+    trunc = np.array([c[:8] for c in g.clusters], dtype="U8")
+    code_names, cell_code = np.unique(trunc, return_inverse=True)
+    cell_code = np.ascontiguousarray(cell_code, dtype=np.int32)
+    end_cells = np.where(np.isin(g.clusters, g.end_clusters))[0]
+    end_slot = np.full(C.shape[0], -1, dtype=np.int32)
+    end_slot[end_cells] = np.arange(len(end_cells), dtype=np.int32)
+    n_fetch = 2000
+    graph.close()
+    del d_seq
+    torch.cuda.empty_cache()
+
+    def e2e_step(i):
+        gh, sh = ctypes.c_void_p(), ctypes.c_void_p()
+        _lib.check(L.cyp_graph_create(local_rank, C.shape[0], C.nnz, ctypes.c_void_p(row_ptr.data_ptr()),
+                                      ctypes.c_void_p(col.data_ptr()), ctypes.c_void_p(val.data_ptr()), mode, ctypes.byref(gh)))
+        _lib.check(L.cyp_session_create(gh, _lib.ptr(roots), n_roots, _lib.ptr(cell_code), len(code_names), 2,
+                                        _lib.ptr(end_slot), len(end_cells), max_steps, 1, args.seed, ctypes.byref(sh)))
+        st = _lib.RoundStats()
+        _lib.check(L.cyp_session_round(sh, i, sims_per_root, w0, w0 + W, None, ctypes.byref(st)))
+        kept = st.n_kept
+        slot = np.empty(kept, dtype=np.int32)
+        walker = np.empty(kept, dtype=np.int64)
+        if kept:
+            _lib.check(L.cyp_session_fetch_index(sh, 0, kept, None, _lib.ptr(walker), _lib.ptr(slot)))
+        m = min(n_fetch, kept)
+        rows = np.ascontiguousarray(np.linspace(0, max(kept - 1, 0), m).astype(np.int64))
+        out = np.empty((m, max_steps), dtype=np.int32)
+        if m:
+            _lib.check(L.cyp_session_fetch_rows(sh, _lib.ptr(rows), m, _lib.ptr(out)))
+        L.cyp_session_destroy(sh)
+        L.cyp_graph_destroy(gh)
+        return st, kept * 12 + m * max_steps * 4
+
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    st, d2h = e2e_step(0)                                          # warm-up
+    torch.cuda.synchronize(); barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        st, d2h = e2e_step(1 + i)
+    torch.cuda.synchronize(); barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = total * nt * e2e_steps / float(t.item())
+    h2d = row_ptr.numel() * 8 + col.numel() * 4 + val.numel() * 8 + roots.nbytes + cell_code.nbytes + end_slot.nbytes
+
+    line = {
+        "metric": "walker_steps_per_sec", "value": value, "unit": "walker-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64" if mode == _lib.CDF_EXACT else "f32", "data": "synthetic",
+        "config": {"workload": w["desc"], "cells": w["n"], "k": w["k"], "nnz": int(C.nnz), "walkers_per_gpu": W,
+                   "global_walkers": total, "max_steps": max_steps, "cdf_mode": args.cdf_mode, "seed": args.seed,
+                   "kernel": kernel_name,
+                   "parallelism": "walkers sharded by id over %d GPU(s), graph replicated" % world,
+                   "l2": "no flush: graph %.2f GB + %.2f GB of trajectories per step exceed the 126 MB L2" % (
+                       info["device_bytes"] / 1e9, W * max_steps * 4 / 1e9)},
+        "clocks": clk,
+        "e2e": {"value": e2e_value, "unit": "walker-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "steps": e2e_steps, "kept_rows_last_step": int(st.n_kept), "ms_walk": st.ms_walk, "ms_filter": st.ms_filter,
+                "what": "cyp_graph_create(pinned host CSR)+K1, cyp_session_round (K2+K3), fetch kept index + %d rows" % n_fetch},
+        "gpu_launches": args.steps,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "bytes_per_walker_step": bytes_per_step,
+                     "mean_visited_row_nnz": kbar, "ms_per_launch": ms_launch},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu, cpu_c = cpu_baseline_sample(C, g, roots, max_steps, 1 if mode == _lib.CDF_EXACT else 0)
+        line["cpu_baseline"] = cpu
+        line["cpu_baseline_c"] = cpu_c
+    elif rank == 0:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--cdf-mode", default="exact", choices=["exact", "reference"])
+    ap.add_argument("--walkers", type=int, default=0, help="walkers per GPU (default: the workload's)")
+    ap.add_argument("--variant", type=int, default=0, help="step-kernel variant lanes*100+unroll (0 = auto)")
+    ap.add_argument("--seed", type=int, default=1234)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        print("note: fewer than 3 warm-up steps requested", file=sys.stderr)
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+        return
+    _, _, world = env_world()
+    if args.gpus != world:
+        print("note: --gpus %d but WORLD_SIZE=%d; using WORLD_SIZE" % (args.gpus, world), file=sys.stderr)
+    run_b200(args, w)
+
+
+if __name__ == "__main__":
+    main()

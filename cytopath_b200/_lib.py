@@ -1,0 +1,278 @@
+"""ctypes binding of libcytopath_b200.so (include/cytopath_b200.h).
+
+There is no CPU implementation behind this module.  If the library is missing, or no
+CUDA device is present when a compute entry point is called, it raises: the product
+never silently falls back to numpy or to the test oracle.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libcytopath_b200.so")
+
+CDF_REFERENCE = 0
+CDF_EXACT = 1
+E_NOCROSSING = -4
+
+EXPORTS = [
+    "cyp_version", "cyp_last_error", "cyp_device_count",
+    "cyp_graph_create", "cyp_graph_destroy", "cyp_graph_info", "cyp_graph_fetch_cdf", "cyp_graph_build_ms",
+    "cyp_walk", "cyp_walk_device", "cyp_walk_variant_name", "cyp_transition_scores",
+    "cyp_session_create", "cyp_session_destroy", "cyp_session_round", "cyp_session_rows",
+    "cyp_session_fetch_index", "cyp_session_fetch_rows", "cyp_session_round_records",
+    "cyp_session_round_prune", "cyp_session_set_hash_bits",
+]
+
+
+class RoundStats(ctypes.Structure):
+    _fields_ = [
+        ("n_walkers", ctypes.c_int64), ("n_pass_clusters", ctypes.c_int64), ("n_terminal", ctypes.c_int64),
+        ("n_kept", ctypes.c_int64), ("n_nocrossing", ctypes.c_int64), ("store_rows", ctypes.c_int64),
+        ("dedup_passes", ctypes.c_int32), ("ms_walk", ctypes.c_float), ("ms_filter", ctypes.c_float),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class CytopathB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("cytopath_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (building nothing: run `python -m cytopath_b200.build` or
+    `__graft_entry__.build()` first).  Raises if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "cytopath_b200: %s not found. Build it with `python -m cytopath_b200.build` "
+            "(needs nvcc; sm_100a). There is no CPU fallback." % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    i32, i64, u32, u64 = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_uint64
+    vp, ci = ctypes.c_void_p, ctypes.c_int
+    P = ctypes.POINTER
+    L.cyp_version.restype = ci
+    L.cyp_last_error.restype = ctypes.c_char_p
+    L.cyp_device_count.argtypes = [P(ci)]
+    L.cyp_graph_create.argtypes = [ci, i64, i64, vp, vp, vp, ci, P(vp)]
+    L.cyp_graph_destroy.argtypes = [vp]
+    L.cyp_graph_info.argtypes = [vp, P(i64), P(i64), P(i32), P(ci), P(ci), P(i64)]
+    L.cyp_graph_fetch_cdf.argtypes = [vp, vp]
+    L.cyp_graph_build_ms.argtypes = [vp, P(ctypes.c_float)]
+    L.cyp_walk.argtypes = [vp, vp, i64, i64, i64, i64, i32, u64, u32, vp, vp, P(i64)]
+    L.cyp_walk_device.argtypes = [vp, vp, i64, i64, i64, i64, i32, u64, u32, vp, vp, vp, ci, vp]
+    L.cyp_walk_variant_name.argtypes = [vp, ci]
+    L.cyp_walk_variant_name.restype = ctypes.c_char_p
+    L.cyp_transition_scores.argtypes = [vp, vp, i64, i32, vp]
+    L.cyp_session_create.argtypes = [vp, vp, i64, vp, i32, i32, vp, i32, i32, ci, u64, P(vp)]
+    L.cyp_session_destroy.argtypes = [vp]
+    L.cyp_session_round.argtypes = [vp, u32, i64, i64, i64, vp, P(RoundStats)]
+    L.cyp_session_rows.argtypes = [vp, P(i64)]
+    L.cyp_session_fetch_index.argtypes = [vp, i64, i64, vp, vp, vp]
+    L.cyp_session_fetch_rows.argtypes = [vp, vp, i64, vp]
+    L.cyp_session_round_records.argtypes = [vp, P(vp), P(i64)]
+    L.cyp_session_round_prune.argtypes = [vp, vp, i64, P(i64)]
+    L.cyp_session_set_hash_bits.argtypes = [vp, ci]
+    for name in EXPORTS:
+        fn = getattr(L, name)
+        if name not in ("cyp_last_error", "cyp_walk_variant_name"):
+            fn.restype = ci
+    _lib = L
+    return L
+
+
+def check(rc: int):
+    if rc != 0:
+        raise CytopathB200Error(rc, load().cyp_last_error().decode("utf-8", "replace"))
+
+
+def device_count() -> int:
+    n = ctypes.c_int(0)
+    check(load().cyp_device_count(ctypes.byref(n)))
+    return n.value
+
+
+def require_device(device: int = 0):
+    """Fail loudly when there is no GPU: this package has no CPU path."""
+    L = load()
+    n = ctypes.c_int(0)
+    rc = L.cyp_device_count(ctypes.byref(n))
+    if rc != 0 or n.value <= device:
+        raise RuntimeError(
+            "cytopath_b200 needs CUDA device %d (found %d; %s). There is no CPU fallback."
+            % (device, n.value, L.cyp_last_error().decode("utf-8", "replace")))
+
+
+def ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data_as(ctypes.c_void_p)
+    return ctypes.c_void_p(int(a))          # raw address (e.g. torch.Tensor.data_ptr())
+
+
+class Graph:
+    """Device-resident transition graph: CSR + per-row CDF (K1).  Mirrors what
+    `matrix_prep` (markov_chain_sampler.py:11-31) returns, minus the ELL padding."""
+
+    def __init__(self, C, cdf_mode: int = CDF_REFERENCE, device: int = 0):
+        """C: canonical scipy CSR (sorted columns, no duplicates, no explicit zeros), float64."""
+        require_device(device)
+        self._h = ctypes.c_void_p()
+        self.indptr = np.ascontiguousarray(C.indptr, dtype=np.int64)
+        indices = np.ascontiguousarray(C.indices, dtype=np.int32)
+        data = np.ascontiguousarray(C.data, dtype=np.float64)
+        self.n, self.nnz, self.cdf_mode, self.device = int(C.shape[0]), int(data.shape[0]), cdf_mode, device
+        check(load().cyp_graph_create(device, self.n, self.nnz, ptr(self.indptr), ptr(indices), ptr(data),
+                                      cdf_mode, ctypes.byref(self._h)))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def info(self):
+        n, nnz, mx, mode, dev, b = (ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int32(), ctypes.c_int(),
+                                    ctypes.c_int(), ctypes.c_int64())
+        check(load().cyp_graph_info(self._h, n, nnz, mx, mode, dev, b))
+        return dict(n_cells=n.value, nnz=nnz.value, max_row_nnz=mx.value, cdf_mode=mode.value,
+                    device=dev.value, device_bytes=b.value)
+
+    def build_ms(self) -> float:
+        ms = ctypes.c_float()
+        check(load().cyp_graph_build_ms(self._h, ctypes.byref(ms)))
+        return ms.value
+
+    def cdf(self) -> np.ndarray:
+        out = np.empty(self.nnz, dtype=np.float64 if self.cdf_mode == CDF_EXACT else np.float32)
+        check(load().cyp_graph_fetch_cdf(self._h, ptr(out)))
+        return out
+
+    def variant_name(self, variant: int = 0) -> str:
+        return load().cyp_walk_variant_name(self._h, variant).decode()
+
+    def walk(self, root_cells, sims_per_root: int, n_transitions: int, seed: int = 0, round_idx: int = 0,
+             walker_begin: int = 0, n_walkers: int | None = None, uniforms=None, strict: bool = True):
+        """markov_sim for walkers [walker_begin, walker_begin + n_walkers): int32 [n_walkers, n_transitions + 1]."""
+        roots = np.ascontiguousarray(root_cells, dtype=np.int32)
+        if n_walkers is None:
+            n_walkers = roots.shape[0] * sims_per_root - walker_begin
+        out = np.empty((n_walkers, n_transitions + 1), dtype=np.int32)
+        if uniforms is not None:
+            uniforms = np.ascontiguousarray(uniforms, dtype=np.float64)
+            assert uniforms.shape == (n_walkers, n_transitions)
+        miss = ctypes.c_int64(0)
+        rc = load().cyp_walk(self._h, ptr(roots), roots.shape[0], sims_per_root, walker_begin, n_walkers,
+                             n_transitions, seed, round_idx, ptr(uniforms), ptr(out), ctypes.byref(miss))
+        if rc == E_NOCROSSING:
+            if strict:      # the reference's accidental failure mode (markov_chain_sampler.py:49)
+                raise IndexError("index 0 is out of bounds for axis 0 with size 0")
+            return out
+        check(rc)
+        return out
+
+    def transition_scores(self, seq) -> np.ndarray:
+        seq = np.ascontiguousarray(seq, dtype=np.int32)
+        out = np.empty(seq.shape[0], dtype=np.float32)
+        if seq.shape[0]:
+            check(load().cyp_transition_scores(self._h, ptr(seq), seq.shape[0], seq.shape[1], ptr(out)))
+        return out
+
+    def close(self):
+        if self._h:
+            load().cyp_graph_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Session:
+    """One `sampling()` run on one device: the per-run inputs of the round loop and the
+    device-resident store of kept sequences (markov_chain_sampler.py:281-354)."""
+
+    def __init__(self, graph: Graph, root_cells, cell_code, n_codes: int, min_clusters: int, end_slot_of_cell,
+                 n_end_slots: int, max_steps: int, unique: bool, seed: int):
+        self.graph = graph
+        self.max_steps = int(max_steps)
+        self._h = ctypes.c_void_p()
+        roots = np.ascontiguousarray(root_cells, dtype=np.int32)
+        code = np.ascontiguousarray(cell_code, dtype=np.int32)
+        slot = np.ascontiguousarray(end_slot_of_cell, dtype=np.int32)
+        assert code.shape[0] == graph.n and slot.shape[0] == graph.n
+        check(load().cyp_session_create(graph.handle, ptr(roots), roots.shape[0], ptr(code), n_codes, min_clusters,
+                                        ptr(slot), n_end_slots, max_steps, int(bool(unique)), seed,
+                                        ctypes.byref(self._h)))
+
+    def round(self, round_idx: int, sims_per_root: int, walker_begin: int, walker_end: int, uniforms=None) -> dict:
+        st = RoundStats()
+        if uniforms is not None:
+            uniforms = np.ascontiguousarray(uniforms, dtype=np.float64)
+            assert uniforms.shape == (walker_end - walker_begin, self.max_steps - 1)
+        rc = load().cyp_session_round(self._h, round_idx, sims_per_root, walker_begin, walker_end, ptr(uniforms),
+                                      ctypes.byref(st))
+        if rc == E_NOCROSSING:
+            raise IndexError("index 0 is out of bounds for axis 0 with size 0")
+        check(rc)
+        return st.as_dict()
+
+    def rows(self) -> int:
+        n = ctypes.c_int64()
+        check(load().cyp_session_rows(self._h, ctypes.byref(n)))
+        return n.value
+
+    def fetch_index(self, row_begin: int = 0, n_rows: int | None = None):
+        if n_rows is None:
+            n_rows = self.rows() - row_begin
+        rnd = np.empty(n_rows, dtype=np.int32)
+        walker = np.empty(n_rows, dtype=np.int64)
+        slot = np.empty(n_rows, dtype=np.int32)
+        if n_rows:
+            check(load().cyp_session_fetch_index(self._h, row_begin, n_rows, ptr(rnd), ptr(walker), ptr(slot)))
+        return rnd, walker, slot
+
+    def fetch_rows(self, rows) -> np.ndarray:
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        out = np.empty((rows.shape[0], self.max_steps), dtype=np.int32)
+        if rows.shape[0]:
+            check(load().cyp_session_fetch_rows(self._h, ptr(rows), rows.shape[0], ptr(out)))
+        return out
+
+    def round_records(self):
+        """(device pointer, count) of this round's (hash_lo, hash_hi, walker) uint64 triples."""
+        p, n = ctypes.c_void_p(), ctypes.c_int64()
+        check(load().cyp_session_round_records(self._h, ctypes.byref(p), ctypes.byref(n)))
+        return p.value or 0, n.value
+
+    def round_prune(self, d_all_records, n_all: int) -> int:
+        dropped = ctypes.c_int64()
+        check(load().cyp_session_round_prune(self._h, ptr(d_all_records), n_all, ctypes.byref(dropped)))
+        return dropped.value
+
+    def set_hash_bits(self, bits: int):
+        check(load().cyp_session_set_hash_bits(self._h, bits))
+
+    def close(self):
+        if self._h:
+            load().cyp_session_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

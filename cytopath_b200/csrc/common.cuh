@@ -1,0 +1,100 @@
+// Shared declarations for the cytopath_b200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/cytopath_b200.h"
+
+namespace cyp {
+
+// ---- error plumbing ---------------------------------------------------------------
+void set_error(const std::string &msg);
+int fail(int code, const std::string &msg);
+
+#define CYP_CUDA(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return ::cyp::fail(CYP_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+#define CYP_REQUIRE(cond, msg)                                   \
+    do {                                                         \
+        if (!(cond)) return ::cyp::fail(CYP_E_INVALID, (msg));   \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (cur != prev && prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// ---- Philox4x32-10 and the frozen walker uniform stream (include/cytopath_b200.h) ----
+constexpr uint32_t kPhiloxM0 = 0xD2511F53u, kPhiloxM1 = 0xCD9E8D57u;
+constexpr uint32_t kPhiloxW0 = 0x9E3779B9u, kPhiloxW1 = 0xBB67AE85u;
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(kPhiloxM0, c.x), lo0 = kPhiloxM0 * c.x;
+        uint32_t hi1 = __umulhi(kPhiloxM1, c.z), lo1 = kPhiloxM1 * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += kPhiloxW0;
+        k.y += kPhiloxW1;
+    }
+    return c;
+}
+
+__device__ __forceinline__ double bits_to_unit_double(uint32_t a, uint32_t b) {
+    // numpy's 53-bit construction: ((a >> 5) * 2^26 + (b >> 6)) / 2^53, exact in double
+    uint64_t mant = (static_cast<uint64_t>(a >> 5) << 26) + static_cast<uint64_t>(b >> 6);
+    return static_cast<double>(mant) * (1.0 / 9007199254740992.0);
+}
+
+// Both uniforms of Philox call `pair` (transitions 2*pair and 2*pair+1) of one walker.
+__device__ __forceinline__ void walker_uniform_pair(uint64_t seed, uint32_t round, uint64_t walker, uint32_t pair,
+                                                    double &u_even, double &u_odd) {
+    uint4 x = philox4x32_10(make_uint4(static_cast<uint32_t>(walker), static_cast<uint32_t>(walker >> 32), pair, round),
+                            make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+    u_even = bits_to_unit_double(x.x, x.y);
+    u_odd = bits_to_unit_double(x.z, x.w);
+}
+
+// ---- device-resident graph ----------------------------------------------------------
+// Rows are stored "sector aligned": every row starts on a 32-byte boundary of the CDF
+// array (4 doubles / 8 floats), so a row of k entries touches ceil(k*sizeof/32) sectors
+// and 16-byte vector loads are always legal.  col/val use the same element offsets.
+struct RowInfo {          // one 8-byte load per walker-step
+    uint32_t off_units;   // row start / align_elems
+    uint32_t len;         // entries in the row
+};
+
+}  // namespace cyp
+
+struct cyp_graph {
+    int device = 0;
+    int cdf_mode = 0;
+    int64_t n = 0;
+    int64_t nnz = 0;
+    int64_t padded = 0;        // elements in the padded arrays
+    int32_t max_len = 0;
+    double mean_len = 0.0;
+    int align_elems = 4;       // 4 (float64 CDF) or 8 (float32 CDF): 32 bytes
+    cyp::RowInfo *d_row = nullptr;   // [n]
+    void *d_cdf = nullptr;           // float or double [padded]
+    int32_t *d_col = nullptr;        // [padded]
+    double *d_val = nullptr;         // [padded] raw probabilities (transition scores)
+    int64_t *d_row_ptr = nullptr;    // [n+1] original CSR offsets (fetch_cdf un-pads with it)
+    int64_t device_bytes = 0;
+    float build_ms = 0.f;
+};

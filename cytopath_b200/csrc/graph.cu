@@ -1,0 +1,304 @@
+// a1: matrix_prep (reference cytopath/markov_chain_sampler.py:11-31) on the device.
+//
+// K1 `build_cdf_kernel`: segmented inclusive prefix sum over the CSR values.  The sum of a
+// row is taken strictly left to right in float64 (np.cumsum, :19), so the result is
+// bit-identical to numpy; a tree scan would re-associate the additions and is not used.
+// Reference mode then narrows to float32 (:23,:28) and rounds to 3 decimals with
+// rintf(c*1000)/1000 in float32 (np.round(decimals=3), :31).  Output goes to the
+// sector-aligned row layout described in common.cuh.
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace cyp {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string &msg) { g_last_error = msg; }
+int fail(int code, const std::string &msg) {
+    g_last_error = msg;
+    return code;
+}
+
+// One CTA handles kK1Threads consecutive rows.  The CTA's slice of the CSR value array is
+// contiguous in HBM, so it is staged through shared memory with coalesced loads; each
+// thread then walks its own row sequentially in shared memory (the serial float64 chain,
+// overwriting the values with their running sums); finally the CTA's slice of the padded
+// output, again contiguous, is written with coalesced stores.  Slices that do not fit the
+// staging buffer (very long rows) take the direct per-thread path.
+constexpr int kK1Threads = 128;
+
+template <typename CdfT>
+__device__ __forceinline__ CdfT finish_cdf(double acc) {
+    if constexpr (sizeof(CdfT) == 8) {
+        return acc;
+    } else {
+        const float c = __double2float_rn(acc);                               // :23/:28 float32 store
+        return __fdiv_rn(rintf(__fmul_rn(c, 1000.0f)), 1000.0f);             // :31 np.round(decimals=3)
+    }
+}
+
+template <typename CdfT>
+__global__ void __launch_bounds__(kK1Threads)
+build_cdf_kernel(int64_t n, const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ raw_col,
+                 const double *__restrict__ raw_val, const RowInfo *__restrict__ rows, int align_elems,
+                 int64_t total_units, CdfT *__restrict__ cdf, int32_t *__restrict__ col, double *__restrict__ val,
+                 int smem_elems) {
+    extern __shared__ double s_val[];                 // [smem_elems] raw values, then cumulative sums in place
+    __shared__ int64_t s_src[kK1Threads + 1];         // CSR offsets of the CTA's rows
+    __shared__ int64_t s_dst[kK1Threads + 1];         // padded offsets of the CTA's rows
+    const int64_t r0 = static_cast<int64_t>(blockIdx.x) * kK1Threads;
+    const int64_t r1 = min(r0 + kK1Threads, n);
+    const int nrows = static_cast<int>(r1 - r0);
+    if (threadIdx.x <= nrows) {
+        const int64_t r = r0 + threadIdx.x;
+        s_src[threadIdx.x] = row_ptr[r];
+        s_dst[threadIdx.x] = (r < n) ? static_cast<int64_t>(rows[r].off_units) * align_elems : total_units * align_elems;
+    }
+    __syncthreads();
+    const int64_t src0 = s_src[0], cnt = s_src[nrows] - src0;
+    const int64_t dst0 = s_dst[0], dcnt = s_dst[nrows] - dst0;
+    if (cnt <= smem_elems) {
+        for (int64_t i = threadIdx.x; i < cnt; i += kK1Threads) s_val[i] = raw_val[src0 + i];
+        __syncthreads();
+        if (threadIdx.x < nrows) {
+            const int64_t a = s_src[threadIdx.x] - src0, b = s_src[threadIdx.x + 1] - src0;
+            double acc = 0.0;
+            for (int64_t j = a; j < b; ++j) {
+                acc = __dadd_rn(acc, s_val[j]);        // sequential: no re-association, no FMA
+                s_val[j] = acc;
+            }
+        }
+        __syncthreads();
+        for (int64_t p = threadIdx.x; p < dcnt; p += kK1Threads) {
+            int lo = 0, hi = nrows;                    // last row with s_dst[row] <= dst0 + p
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (s_dst[mid] - dst0 <= p) lo = mid; else hi = mid;
+            }
+            const int64_t j = p - (s_dst[lo] - dst0);
+            const int64_t len = s_src[lo + 1] - s_src[lo];
+            if (j < len) {
+                const int64_t q = s_src[lo] + j;
+                cdf[dst0 + p] = finish_cdf<CdfT>(s_val[q - src0]);
+                col[dst0 + p] = raw_col[q];
+                val[dst0 + p] = raw_val[q];
+            } else {                                   // padding never matches: u >= 0 > -1
+                cdf[dst0 + p] = static_cast<CdfT>(-1);
+                col[dst0 + p] = -1;
+                val[dst0 + p] = 0.0;
+            }
+        }
+    } else if (threadIdx.x < nrows) {
+        const int64_t a = s_src[threadIdx.x], len = s_src[threadIdx.x + 1] - a;
+        const int64_t dst = s_dst[threadIdx.x];
+        const int64_t len_pad = (len + align_elems - 1) / align_elems * align_elems;
+        double acc = 0.0;
+        for (int64_t j = 0; j < len; ++j) {
+            const double v = raw_val[a + j];
+            acc = __dadd_rn(acc, v);
+            cdf[dst + j] = finish_cdf<CdfT>(acc);
+            col[dst + j] = raw_col[a + j];
+            val[dst + j] = v;
+        }
+        for (int64_t j = len; j < len_pad; ++j) {
+            cdf[dst + j] = static_cast<CdfT>(-1);
+            col[dst + j] = -1;
+            val[dst + j] = 0.0;
+        }
+    }
+}
+
+template <typename CdfT>
+__global__ void unpad_cdf_kernel(int64_t n, const int64_t *__restrict__ row_ptr, const RowInfo *__restrict__ rows,
+                                 int align_elems, const CdfT *__restrict__ cdf, CdfT *__restrict__ out) {
+    // one warp per row
+    const int64_t r = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= n) return;
+    const int64_t a = row_ptr[r], len = row_ptr[r + 1] - a;
+    const int64_t src = static_cast<int64_t>(rows[r].off_units) * align_elems;
+    for (int64_t j = lane; j < len; j += 32) out[a + j] = cdf[src + j];
+}
+
+}  // namespace cyp
+
+using namespace cyp;
+
+extern "C" int cyp_version(void) { return CYP_VERSION; }
+extern "C" const char *cyp_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int cyp_device_count(int *n) {
+    CYP_REQUIRE(n != nullptr, "cyp_device_count: n is NULL");
+    CYP_CUDA(cudaGetDeviceCount(n));
+    return CYP_OK;
+}
+
+static void graph_free(cyp_graph *g) {
+    if (!g) return;
+    DeviceGuard guard(g->device);
+    cudaFree(g->d_row);
+    cudaFree(g->d_cdf);
+    cudaFree(g->d_col);
+    cudaFree(g->d_val);
+    cudaFree(g->d_row_ptr);
+    delete g;
+}
+
+extern "C" int cyp_graph_create(int device, int64_t n_cells, int64_t nnz, const int64_t *h_row_ptr,
+                                const int32_t *h_col, const double *h_val, int cdf_mode, cyp_graph **out) {
+    CYP_REQUIRE(out != nullptr, "cyp_graph_create: out is NULL");
+    *out = nullptr;
+    CYP_REQUIRE(n_cells > 0 && nnz > 0, "cyp_graph_create: empty matrix");
+    CYP_REQUIRE(n_cells < (1ll << 31), "cyp_graph_create: cell ids must fit int32 (the reference stores int32, :38)");
+    CYP_REQUIRE(h_row_ptr && h_col && h_val, "cyp_graph_create: NULL CSR array");
+    CYP_REQUIRE(cdf_mode == CYP_CDF_REFERENCE || cdf_mode == CYP_CDF_EXACT, "cyp_graph_create: bad cdf_mode");
+    CYP_REQUIRE(h_row_ptr[0] == 0 && h_row_ptr[n_cells] == nnz, "cyp_graph_create: row_ptr does not span nnz");
+    int ndev = 0;
+    CYP_CUDA(cudaGetDeviceCount(&ndev));
+    CYP_REQUIRE(device >= 0 && device < ndev, "cyp_graph_create: no such CUDA device");
+    DeviceGuard guard(device);
+
+    cyp_graph *g = new cyp_graph();
+    g->device = device;
+    g->cdf_mode = cdf_mode;
+    g->n = n_cells;
+    g->nnz = nnz;
+    g->align_elems = (cdf_mode == CYP_CDF_EXACT) ? 4 : 8;
+    const int A = g->align_elems;
+
+    // host: padded row offsets (O(n))
+    std::vector<RowInfo> rows(static_cast<size_t>(n_cells));
+    int64_t units = 0;
+    int32_t max_len = 0;
+    for (int64_t r = 0; r < n_cells; ++r) {
+        const int64_t len = h_row_ptr[r + 1] - h_row_ptr[r];
+        if (len < 0 || len > (1ll << 30)) {
+            delete g;
+            return fail(CYP_E_INVALID, "cyp_graph_create: row_ptr not monotone");
+        }
+        rows[r].off_units = static_cast<uint32_t>(units);
+        rows[r].len = static_cast<uint32_t>(len);
+        units += (len + A - 1) / A;
+        if (len > max_len) max_len = static_cast<int32_t>(len);
+    }
+    if (units >= (1ll << 32)) {
+        delete g;
+        return fail(CYP_E_INVALID, "cyp_graph_create: matrix too large for 32-bit row units");
+    }
+    g->padded = units * A + 4 * A;                     // slack so vector loads of a last partial chunk stay in bounds
+    g->max_len = max_len;
+    g->mean_len = static_cast<double>(nnz) / static_cast<double>(n_cells);
+    const size_t cdf_elem = (cdf_mode == CYP_CDF_EXACT) ? 8 : 4;
+
+    int32_t *d_raw_col = nullptr;
+    double *d_raw_val = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    auto cleanup = [&](int code, const std::string &msg) {
+        cudaFree(d_raw_col);
+        cudaFree(d_raw_val);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        graph_free(g);
+        return fail(code, msg);
+    };
+#define G_CUDA(expr)                                                                                  \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess) return cleanup(_e == cudaErrorMemoryAllocation ? CYP_E_NOMEM : CYP_E_CUDA, \
+                                              std::string(#expr) + ": " + cudaGetErrorString(_e));    \
+    } while (0)
+
+    G_CUDA(cudaMalloc(&g->d_row, sizeof(RowInfo) * n_cells));
+    G_CUDA(cudaMalloc(&g->d_row_ptr, sizeof(int64_t) * (n_cells + 1)));
+    G_CUDA(cudaMalloc(&g->d_cdf, cdf_elem * g->padded));
+    G_CUDA(cudaMalloc(&g->d_col, sizeof(int32_t) * g->padded));
+    G_CUDA(cudaMalloc(&g->d_val, sizeof(double) * g->padded));
+    G_CUDA(cudaMalloc(&d_raw_col, sizeof(int32_t) * nnz));
+    G_CUDA(cudaMalloc(&d_raw_val, sizeof(double) * nnz));
+    g->device_bytes = sizeof(RowInfo) * n_cells + sizeof(int64_t) * (n_cells + 1) +
+                      (cdf_elem + sizeof(int32_t) + sizeof(double)) * g->padded;
+    G_CUDA(cudaMemcpy(g->d_row, rows.data(), sizeof(RowInfo) * n_cells, cudaMemcpyHostToDevice));
+    G_CUDA(cudaMemcpy(g->d_row_ptr, h_row_ptr, sizeof(int64_t) * (n_cells + 1), cudaMemcpyHostToDevice));
+    G_CUDA(cudaMemcpy(d_raw_col, h_col, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice));
+    G_CUDA(cudaMemcpy(d_raw_val, h_val, sizeof(double) * nnz, cudaMemcpyHostToDevice));
+    // slack region: never-matching padding
+    G_CUDA(cudaMemset(static_cast<char *>(g->d_cdf) + cdf_elem * units * A, 0xFF, cdf_elem * 4 * A));   // NaN: u <= NaN is false
+    G_CUDA(cudaMemset(g->d_col + units * A, 0xFF, sizeof(int32_t) * 4 * A));
+    G_CUDA(cudaMemset(g->d_val + units * A, 0, sizeof(double) * 4 * A));
+
+    G_CUDA(cudaEventCreate(&e0));
+    G_CUDA(cudaEventCreate(&e1));
+    const int smem_elems = 20 * 1024;                  // 160 KB of staged float64 values per CTA
+    const int smem_bytes = smem_elems * static_cast<int>(sizeof(double));
+    const unsigned grid = static_cast<unsigned>((n_cells + kK1Threads - 1) / kK1Threads);
+    G_CUDA(cudaEventRecord(e0));
+    if (cdf_mode == CYP_CDF_EXACT) {
+        G_CUDA(cudaFuncSetAttribute(build_cdf_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        build_cdf_kernel<double><<<grid, kK1Threads, smem_bytes>>>(n_cells, g->d_row_ptr, d_raw_col, d_raw_val, g->d_row, A,
+                                                                   units, static_cast<double *>(g->d_cdf), g->d_col,
+                                                                   g->d_val, smem_elems);
+    } else {
+        G_CUDA(cudaFuncSetAttribute(build_cdf_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        build_cdf_kernel<float><<<grid, kK1Threads, smem_bytes>>>(n_cells, g->d_row_ptr, d_raw_col, d_raw_val, g->d_row, A,
+                                                                  units, static_cast<float *>(g->d_cdf), g->d_col,
+                                                                  g->d_val, smem_elems);
+    }
+    G_CUDA(cudaGetLastError());
+    G_CUDA(cudaEventRecord(e1));
+    G_CUDA(cudaEventSynchronize(e1));
+    G_CUDA(cudaEventElapsedTime(&g->build_ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_raw_col);
+    cudaFree(d_raw_val);
+#undef G_CUDA
+    *out = g;
+    return CYP_OK;
+}
+
+extern "C" int cyp_graph_destroy(cyp_graph *g) {
+    graph_free(g);
+    return CYP_OK;
+}
+
+extern "C" int cyp_graph_info(const cyp_graph *g, int64_t *n_cells, int64_t *nnz, int32_t *max_row_nnz,
+                              int *cdf_mode, int *device, int64_t *device_bytes) {
+    CYP_REQUIRE(g != nullptr, "cyp_graph_info: NULL graph");
+    if (n_cells) *n_cells = g->n;
+    if (nnz) *nnz = g->nnz;
+    if (max_row_nnz) *max_row_nnz = g->max_len;
+    if (cdf_mode) *cdf_mode = g->cdf_mode;
+    if (device) *device = g->device;
+    if (device_bytes) *device_bytes = g->device_bytes;
+    return CYP_OK;
+}
+
+extern "C" int cyp_graph_build_ms(const cyp_graph *g, float *ms) {
+    CYP_REQUIRE(g != nullptr && ms != nullptr, "cyp_graph_build_ms: NULL argument");
+    *ms = g->build_ms;
+    return CYP_OK;
+}
+
+extern "C" int cyp_graph_fetch_cdf(const cyp_graph *g, void *h_cdf) {
+    CYP_REQUIRE(g != nullptr && h_cdf != nullptr, "cyp_graph_fetch_cdf: NULL argument");
+    DeviceGuard guard(g->device);
+    const size_t elem = (g->cdf_mode == CYP_CDF_EXACT) ? 8 : 4;
+    void *d_out = nullptr;
+    CYP_CUDA(cudaMalloc(&d_out, elem * g->nnz));
+    const int threads = 256;
+    const unsigned grid = static_cast<unsigned>((g->n * 32 + threads - 1) / threads);
+    if (g->cdf_mode == CYP_CDF_EXACT)
+        unpad_cdf_kernel<double><<<grid, threads>>>(g->n, g->d_row_ptr, g->d_row, g->align_elems,
+                                                   static_cast<const double *>(g->d_cdf), static_cast<double *>(d_out));
+    else
+        unpad_cdf_kernel<float><<<grid, threads>>>(g->n, g->d_row_ptr, g->d_row, g->align_elems,
+                                                  static_cast<const float *>(g->d_cdf), static_cast<float *>(d_out));
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy(h_cdf, d_out, elem * g->nnz, cudaMemcpyDeviceToHost);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(CYP_E_CUDA, std::string("cyp_graph_fetch_cdf: ") + cudaGetErrorString(e));
+    return CYP_OK;
+}

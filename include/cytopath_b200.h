@@ -1,0 +1,151 @@
+/* cytopath_b200 — C ABI of the B200-native Markov-chain trajectory sampler.
+ *
+ * This is the drop-in boundary for ONE path of aron0093/cytopath: `cytopath.sampling`
+ * (reference cytopath/markov_chain_sampler.py:89-414).  The reference has no FFI layer
+ * (it is pure Python); these entry points are what a ctypes binding inside the
+ * reference's `markov_chain_sampler.py` would call instead of its numpy loops.  Each
+ * declaration names the reference lines it replaces.  INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success or a negative CYP_E_* code;
+ *     `cyp_last_error()` returns a thread-local message for the last failure.
+ *   - handles (`cyp_graph`, `cyp_session`) own device memory; callers own host buffers.
+ *   - pointers named `h_*` are host memory, `d_*` device memory on the handle's device.
+ *   - calls are synchronous on return unless they take a `stream` (a cudaStream_t passed
+ *     as void*; NULL = the legacy default stream), in which case work is only enqueued.
+ *   - there is no CPU implementation behind any of these: without a CUDA device they fail.
+ *
+ * Uniform stream (frozen; restated in oracle/philox.py and oracle/walk.c)
+ *   key = (seed lo, seed hi); ctr = (walker lo, walker hi, t >> 1, round);
+ *   x = Philox4x32-10(ctr, key); (a, b) = t even ? (x0, x1) : (x2, x3);
+ *   u = ((a >> 5) * 2^26 + (b >> 6)) * 2^-53.
+ *   `walker` is the row of the round's sample matrix (root-major: walker / sims_per_root
+ *   is the index into root_cells, like markov_chain_sampler.py:314-317), `t` the 0-based
+ *   transition, `round` the 0-based sampling round.  Results are therefore independent of
+ *   how walkers are sharded over launches, chunks or GPUs.
+ */
+#ifndef CYTOPATH_B200_H
+#define CYTOPATH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CYP_VERSION 100              /* 0.1.0 */
+
+#define CYP_OK 0
+#define CYP_E_INVALID (-1)           /* bad argument */
+#define CYP_E_CUDA (-2)              /* CUDA runtime error (message has the detail) */
+#define CYP_E_NOMEM (-3)             /* device memory would be exceeded */
+#define CYP_E_NOCROSSING (-4)        /* some u exceeded its row's last CDF value: the reference
+                                        raises IndexError at markov_chain_sampler.py:49 */
+
+/* CDF recipes (markov_chain_sampler.py:18-19,:23,:28,:31) */
+#define CYP_CDF_REFERENCE 0          /* float32(cumsum_f64) rounded to 3 decimals: bit-exact with the reference */
+#define CYP_CDF_EXACT 1              /* float64 sequential cumsum (north-star mode) */
+
+typedef struct cyp_graph cyp_graph;
+typedef struct cyp_session cyp_session;
+
+int cyp_version(void);
+const char *cyp_last_error(void);
+int cyp_device_count(int *n);
+
+/* ---- a1: matrix_prep (markov_chain_sampler.py:11-31) -------------------------------
+ * Uploads a canonical CSR (columns ascending, no duplicates, no explicit zeros: what
+ * `sparse.csr_matrix(dense)` at :14 holds) and builds the per-row CDF on the device with
+ * a segmented prefix-sum kernel that adds strictly left to right in float64, like
+ * np.cumsum (:19).  The zero-padded ELL arrays of :22-28 are not reproduced: padding
+ * never changes the selection. */
+int cyp_graph_create(int device, int64_t n_cells, int64_t nnz, const int64_t *h_row_ptr,
+                     const int32_t *h_col, const double *h_val, int cdf_mode, cyp_graph **out);
+int cyp_graph_destroy(cyp_graph *g);
+int cyp_graph_info(const cyp_graph *g, int64_t *n_cells, int64_t *nnz, int32_t *max_row_nnz,
+                   int *cdf_mode, int *device, int64_t *device_bytes);
+/* CDF values in CSR order: float[nnz] (reference mode) or double[nnz] (exact mode). */
+int cyp_graph_fetch_cdf(const cyp_graph *g, void *h_cdf);
+/* Milliseconds the K1 prefix-sum kernel took when the graph was created (CUDA events). */
+int cyp_graph_build_ms(const cyp_graph *g, float *ms);
+
+/* ---- a2: markov_sim (markov_chain_sampler.py:35-52) --------------------------------
+ * Walkers [walker_begin, walker_begin + n_walkers) of one round, each starting at
+ * root_cells[walker / sims_per_root] and taking n_transitions = max_steps - 1 steps with
+ * next = col[first j with u <= cdf[j]] (:48-49, ties go to the bin).  `uniforms`, when not
+ * NULL, is double [n_walkers, n_transitions] and replaces the Philox stream (the hook the
+ * parity tests use to drive the reference's numpy rule with identical numbers).
+ * out_seq is int32 [n_walkers, n_transitions + 1], column 0 = root (:41).
+ * *n_nocrossing counts walker-steps with no bin (the reference raises IndexError there);
+ * the host variant returns CYP_E_NOCROSSING if it is non-zero but still fills out_seq. */
+int cyp_walk(const cyp_graph *g, const int32_t *h_root_cells, int64_t n_roots, int64_t sims_per_root,
+             int64_t walker_begin, int64_t n_walkers, int32_t n_transitions, uint64_t seed, uint32_t round,
+             const double *h_uniforms, int32_t *h_out_seq, int64_t *n_nocrossing);
+/* Same, everything resident in HBM, enqueued on `stream`.  d_nocrossing (may be NULL) is
+ * incremented atomically.  `variant` selects the step kernel (0 = auto). */
+int cyp_walk_device(const cyp_graph *g, const int32_t *d_root_cells, int64_t n_roots, int64_t sims_per_root,
+                    int64_t walker_begin, int64_t n_walkers, int32_t n_transitions, uint64_t seed,
+                    uint32_t round, const double *d_uniforms, int32_t *d_out_seq,
+                    unsigned long long *d_nocrossing, int variant, void *stream);
+/* Name of the kernel variant `cyp_walk_device` would pick / picked for this graph. */
+const char *cyp_walk_variant_name(const cyp_graph *g, int variant);
+
+/* score = sum_t -log(float32(T[c_t, c_t+1])) per row, float32 (markov_chain_sampler.py:50,:52),
+ * evaluated on the device for the rows given (numpy's pairwise summation order). */
+int cyp_transition_scores(const cyp_graph *g, const int32_t *h_seq, int64_t n_rows, int32_t n_steps,
+                          float *h_score);
+
+/* ---- a3: one sampling round + filters (markov_chain_sampler.py:299-354) -------------
+ * A session fixes the per-run inputs of the round loop: root cells, the per-cell code of
+ * the 8-character-truncated cluster label (:39,:51) with min_clusters (:322), the
+ * end-point slot of every cell (-1 = not an end point; :343-349), max_steps, `unique`
+ * (:329-333) and the seed.  Each round walks its share of the round's walkers, keeps those
+ * that (1) visit >= min_clusters distinct labels and (2) end on an end point, removes
+ * duplicates keeping the first occurrence (lowest walker id, = np.unique(..., return_index)
+ * + sorted at :330-331), and appends the survivors, in walker order, to a device-resident
+ * store.  Sequences that do not end on an end point can never be selected by :385-403 and
+ * are dropped on the device. */
+int cyp_session_create(const cyp_graph *g, const int32_t *h_root_cells, int64_t n_roots,
+                       const int32_t *h_cell_code, int32_t n_codes, int32_t min_clusters,
+                       const int32_t *h_end_slot_of_cell, int32_t n_end_slots,
+                       int32_t max_steps, int unique, uint64_t seed, cyp_session **out);
+int cyp_session_destroy(cyp_session *s);
+
+typedef struct cyp_round_stats {
+    int64_t n_walkers;        /* walkers simulated by this call */
+    int64_t n_pass_clusters;  /* of those, visiting >= min_clusters labels */
+    int64_t n_terminal;       /* of those, also ending on an end point */
+    int64_t n_kept;           /* after de-duplication: rows appended to the store */
+    int64_t n_nocrossing;     /* walker-steps with no CDF crossing */
+    int64_t store_rows;       /* total rows in the store after this call */
+    int32_t dedup_passes;     /* hash passes used (1 unless a 128-bit hash collided) */
+    float ms_walk;            /* step kernel, CUDA events */
+    float ms_filter;          /* filter + dedup + compaction kernels */
+} cyp_round_stats;
+
+/* Walkers [walker_begin, walker_end) of round `round` with sims_per_root walkers per root.
+ * h_uniforms as in cyp_walk (rows relative to walker_begin), or NULL. */
+int cyp_session_round(cyp_session *s, uint32_t round, int64_t sims_per_root, int64_t walker_begin,
+                      int64_t walker_end, const double *h_uniforms, cyp_round_stats *stats);
+/* Rows kept so far, then per kept row: round, walker id, end-point slot (store order =
+ * round-major, walker order within a round, i.e. the accumulation order of :335-340). */
+int cyp_session_rows(const cyp_session *s, int64_t *n_rows);
+int cyp_session_fetch_index(const cyp_session *s, int64_t row_begin, int64_t n_rows, int32_t *h_round,
+                            int64_t *h_walker, int32_t *h_end_slot);
+/* Gather store rows (by store row index) into int32 [n_rows, max_steps] on the host. */
+int cyp_session_fetch_rows(const cyp_session *s, const int64_t *h_rows, int64_t n_rows, int32_t *h_seq);
+
+/* Multi-GPU de-duplication support (walkers sharded by contiguous id blocks).  After a
+ * round, each rank exports the (hash_lo, hash_hi, walker) records of the rows it just
+ * appended; the ranks all-gather them (NCCL) and each rank drops the rows whose sequence
+ * was also produced by a lower walker id on another rank. */
+int cyp_session_round_records(const cyp_session *s, uint64_t **d_records, int64_t *n_records);
+int cyp_session_round_prune(cyp_session *s, const uint64_t *d_all_records, int64_t n_all, int64_t *n_dropped);
+
+/* test hook: keep only the low `bits` bits of the 128-bit sequence hash (forces collisions) */
+int cyp_session_set_hash_bits(cyp_session *s, int bits);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -67,11 +67,13 @@ def to_ell(C: sparse.csr_matrix, cdf: np.ndarray):
 
 
 # --------------------------------------------------------------------------- a2
-def markov_sim_port(j, sim_number, max_steps, root_cells, clusters, C, idx_ell, cdf_ell, uniforms=None):
+def markov_sim_port(j, sim_number, max_steps, root_cells, clusters, C, idx_ell, cdf_ell, uniforms=None, prob_ell=None):
     """Faithful restatement of markov_sim (:35-52): same loop nest (step outer, walker
     inner), same `np.where(u <= row)[0][0]` first-crossing rule on the padded arrays.
-    `C` (canonical CSR) replaces the dense matrix for the T[cur, nxt] lookup at :50.
-    This is the function the CPU baseline times."""
+    `C` (canonical CSR) replaces the dense matrix for the T[cur, nxt] lookup at :50; at
+    sizes where even that is too slow to be fair to the reference (its dense lookup is one
+    fancy index), `prob_ell` (raw probabilities in the same padded layout) gives the same
+    number with the same cost.  This is the function the CPU baseline times."""
     prob_state = np.empty((sim_number, max_steps - 1), dtype=np.float32)
     state = np.empty((sim_number, max_steps), dtype=np.int32)
     clust_state = np.empty((sim_number, max_steps), dtype="U8")
@@ -84,7 +86,7 @@ def markov_sim_port(j, sim_number, max_steps, root_cells, clusters, C, idx_ell, 
             pos = np.where(u[k, i - 1] <= cdf_ell[cur, :])[0][0]
             nxt = idx_ell[cur, pos]
             state[k, i] = nxt
-            prob_state[k, i - 1] = C[cur, nxt]
+            prob_state[k, i - 1] = C[cur, nxt] if prob_ell is None else prob_ell[cur, pos]
             clust_state[k, i] = clusters[nxt]
     return state, np.sum(-np.log(prob_state), axis=1), clust_state
 

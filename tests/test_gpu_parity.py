@@ -1,0 +1,316 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle and the golden
+vectors of the real reference.  Integer outputs must be bit-exact; transition scores are
+float32 and compared at rtol 2e-6 (numpy's SIMD log differs from log() in the last bit)."""
+import contextlib
+import io
+import warnings
+
+import numpy as np
+import pytest
+
+import cytopath_b200
+from cytopath_b200 import _lib, synth
+from oracle import cwalk, philox, sampler_port as sp
+from tests.helpers import SAMPLING_CASES, adata_from_case, csr_from, load
+from tests.test_sampling_host import check_against_golden, run_quiet
+
+pytestmark = pytest.mark.gpu
+
+MODES = [(_lib.CDF_REFERENCE, 0), (_lib.CDF_EXACT, 1)]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def need_gpu():
+    _lib.require_device(0)          # raises (fails the test) if the CUDA path cannot run
+
+
+# ---- K1 ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["f64", "f32"])
+def test_k1_cdf_matches_reference_matrix_prep(tag):
+    z = load("matrix_prep_messy_" + tag)
+    C = sp.canonical_csr(csr_from(z))
+    g = _lib.Graph(C, _lib.CDF_REFERENCE)
+    idx, ell = sp.to_ell(C, g.cdf())
+    np.testing.assert_array_equal(idx, z["idx"])
+    np.testing.assert_array_equal(ell, z["cdf"])
+    g.close()
+
+
+@pytest.mark.parametrize("n,k", [(2000, 30), (500, 200), (300, 1)])
+@pytest.mark.parametrize("mode,omode", MODES)
+def test_k1_cdf_bit_exact_vs_oracle(n, k, mode, omode):
+    if k == 1:
+        C = sp.canonical_csr(synth.random_sparse_rows(n=n, max_nnz=1, seed=1, messy=False))
+    else:
+        C = sp.canonical_csr(synth.branching_graph(n=n, k=k, n_branches=3, seed=n + k, workers=1).T)
+    g = _lib.Graph(C, mode)
+    got = g.cdf()
+    want = cwalk.build_cdf(C, omode)
+    assert got.dtype == want.dtype
+    np.testing.assert_array_equal(got, want)
+    info = g.info()
+    assert info["n_cells"] == n and info["nnz"] == C.nnz and info["max_row_nnz"] == int(np.diff(C.indptr).max())
+    g.close()
+
+
+def test_k1_ragged_rows_with_staging_overflow():
+    rng = np.random.default_rng(5)
+    n = 700
+    lens = rng.integers(1, 400, size=n)
+    lens[10] = 1; lens[11] = 399
+    rows = np.repeat(np.arange(n), lens)
+    cols = np.concatenate([np.sort(rng.choice(n, size=l, replace=False)) for l in lens])
+    vals = rng.random(len(cols)) + 1e-3
+    from scipy import sparse
+    M = sparse.csr_matrix((vals, (rows, cols)), shape=(n, n))
+    M = sparse.diags(1.0 / np.asarray(M.sum(axis=1)).ravel()) @ M
+    C = sp.canonical_csr(M)
+    for mode, omode in MODES:
+        g = _lib.Graph(C, mode)
+        np.testing.assert_array_equal(g.cdf(), cwalk.build_cdf(C, omode))
+        g.close()
+
+
+# ---- K2 ---------------------------------------------------------------------------------
+def test_k2_matches_reference_markov_sim_golden():
+    z = load("markov_sim_small")
+    C = sp.canonical_csr(csr_from(z))
+    g = _lib.Graph(C, _lib.CDF_REFERENCE)
+    sim, steps, seed = int(z["sim"]), int(z["steps"]), int(z["seed"])
+    got = g.walk(z["roots"], sim, steps - 1, seed=seed)
+    np.testing.assert_array_equal(got, z["seq"])                      # native Philox == the stream fed to the reference
+    u = philox.walker_uniforms(seed, 0, 0, 2 * sim, steps - 1)
+    np.testing.assert_array_equal(g.walk(z["roots"], sim, steps - 1, uniforms=u), z["seq"])    # injected uniforms
+    np.testing.assert_allclose(g.transition_scores(z["seq"]), z["score"], rtol=2e-6)
+    g.close()
+
+
+GRAPHS = {
+    "k4": lambda: synth.branching_graph(n=500, k=4, n_branches=2, seed=1, workers=1, scale=3.0, noise=0.03).T,
+    "k12": lambda: synth.branching_graph(n=1500, k=12, n_branches=3, seed=2, workers=1, scale=4.0).T,
+    "k30": lambda: synth.branching_graph(n=3696, k=30, n_branches=4, seed=0, workers=1).T,
+    "k50": lambda: synth.branching_graph(n=4000, k=50, n_branches=4, seed=3, workers=1).T,
+    "k200": lambda: synth.cycling_graph(n=3000, k=200, seed=4, workers=1).T,
+    "ragged": lambda: synth.random_sparse_rows(n=400, max_nnz=70, seed=9, messy=True),
+}
+
+
+@pytest.mark.parametrize("gname", list(GRAPHS))
+@pytest.mark.parametrize("mode,omode", MODES)
+def test_k2_bit_exact_vs_oracle_all_variants(gname, mode, omode):
+    C = sp.canonical_csr(GRAPHS[gname]())
+    g = _lib.Graph(C, mode)
+    cdf = cwalk.build_cdf(C, omode)
+    rng = np.random.default_rng(7)
+    roots = rng.choice(C.shape[0], size=13, replace=False)
+    sims, nt, seed, rnd = 37, 61, 0xDEADBEEFCAFE, 2
+    want = cwalk.walk(C, cdf, np.repeat(roots, sims), nt, seed=seed, round_idx=rnd, strict=False)
+    L = _lib.load()
+    import ctypes
+    import torch
+    d_roots = torch.tensor(roots, dtype=torch.int32, device="cuda")
+    for lanes in (1, 2, 4, 8, 16, 32):
+        for unroll in (2, 4):
+            out = torch.full((len(roots) * sims, nt + 1), -7, dtype=torch.int32, device="cuda")
+            miss = torch.zeros(1, dtype=torch.int64, device="cuda")
+            _lib.check(L.cyp_walk_device(g.handle, d_roots.data_ptr(), len(roots), sims, 0, len(roots) * sims, nt, seed, rnd,
+                                         None, out.data_ptr(), miss.data_ptr(), lanes * 100 + unroll,
+                                         ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            torch.cuda.synchronize()
+            np.testing.assert_array_equal(out.cpu().numpy(), want, err_msg="lanes=%d unroll=%d" % (lanes, unroll))
+    # auto variant through the host entry point, a shard in the middle of the round
+    got = g.walk(roots, sims, nt, seed=seed, round_idx=rnd, walker_begin=100, n_walkers=211, strict=False)
+    np.testing.assert_array_equal(got, want[100:311])
+    g.close()
+
+
+def test_k2_edge_cases_ties_zero_and_last_bin():
+    """u == cdf[j] picks bin j (`<=` at :49); u = 0 picks bin 0; u just below 1 picks the last bin."""
+    from scipy import sparse
+    P = np.array([[0.25, 0.25, 0.5, 0.0], [0.0, 1.0, 0.0, 0.0], [0.125, 0.125, 0.25, 0.5], [1.0, 0, 0, 0]])
+    C = sp.canonical_csr(sparse.csr_matrix(P))
+    for mode, omode in MODES:
+        g = _lib.Graph(C, mode)
+        cdf = cwalk.build_cdf(C, omode)
+        u = np.array([[0.0, 0.25, 0.5], [0.25, 0.0, 0.999999], [0.5, 0.125, 0.75], [np.nextafter(0.5, 1), 0.5, 1.0 - 2**-53]])
+        roots = np.array([0, 0, 2, 2])
+        want = sp.walk(C, cdf, roots, u)
+        got = g.walk(roots, 1, 3, uniforms=u)
+        np.testing.assert_array_equal(got, want)
+        np.testing.assert_array_equal(cwalk.walk(C, cdf, roots, 3, uniforms=u), want)
+        g.close()
+
+
+def test_k2_under_normalised_row_raises_like_the_reference():
+    from scipy import sparse
+    P = np.array([[0.4995, 0.4995], [0.5, 0.5]])          # row 0 sums to 0.999: passes the :184-185 check
+    C = sp.canonical_csr(sparse.csr_matrix(P))
+    g = _lib.Graph(C, _lib.CDF_REFERENCE)
+    u = np.array([[0.9995, 0.1]])
+    with pytest.raises(IndexError):
+        g.walk(np.array([0]), 1, 2, uniforms=u)
+    with pytest.raises(IndexError):
+        cwalk.walk(C, cwalk.build_cdf(C, 0), np.array([0]), 2, uniforms=u)
+    g.close()
+
+
+def test_k2_single_step_and_zero_transitions():
+    C = sp.canonical_csr(GRAPHS["k12"]())
+    g = _lib.Graph(C, _lib.CDF_EXACT)
+    roots = np.array([3, 9, 11])
+    np.testing.assert_array_equal(g.walk(roots, 2, 0), np.repeat(roots, 2)[:, None])
+    want = cwalk.walk(C, cwalk.build_cdf(C, 1), np.repeat(roots, 2), 1, seed=5)
+    np.testing.assert_array_equal(g.walk(roots, 2, 1, seed=5), want)
+    g.close()
+
+
+# ---- K3 + sampling() end to end --------------------------------------------------------
+@pytest.mark.parametrize("name", SAMPLING_CASES)
+def test_sampling_cuda_matches_reference_golden(name):
+    z = load(name)
+    ad, kw = adata_from_case(z)
+    np.random.seed(int(z["np_seed"]))
+    run_quiet(cytopath_b200.sampling, ad, **kw, seed=int(z["seed"]))
+    check_against_golden(ad, z)
+    assert "walk_kernel" in ad.uns["run_info"]["b200"]["kernel"]
+
+
+def make_session(C, g, roots, code, min_clusters, end_cells, max_steps, unique, seed):
+    n = C.shape[0]
+    slot = np.full(n, -1, dtype=np.int32)
+    slot[end_cells] = np.arange(len(end_cells), dtype=np.int32)
+    return _lib.Session(g, roots, code, int(code.max()) + 1, min_clusters, slot, len(end_cells), max_steps, unique, seed), slot
+
+
+def oracle_round(C, cdf, roots, sims, max_steps, seed, rnd, code, min_clusters, slot, unique, w0=0, w1=None):
+    starts = np.repeat(roots, sims)
+    w1 = len(starts) if w1 is None else w1
+    seq = cwalk.walk(C, cdf, starts[w0:w1], max_steps - 1, seed=seed, round_idx=rnd, walker_begin=w0)
+    cs = np.sort(code[seq], axis=1)
+    ok = (1 + (np.diff(cs, axis=1) != 0).sum(axis=1)) >= min_clusters
+    cand = np.flatnonzero(ok & (slot[seq[:, -1]] >= 0))
+    if unique and cand.size:
+        cand = cand[np.sort(np.unique(seq[cand], axis=0, return_index=True)[1])]
+    return seq, ok, cand
+
+
+@pytest.mark.parametrize("hash_bits", [128, 6, 0])
+@pytest.mark.parametrize("n_codes", [1, 40, 200, 700])
+def test_k3_round_filters_and_dedup_vs_oracle(hash_bits, n_codes):
+    """Short walks on a tiny graph produce many duplicate sequences; truncating the hash to a
+    few bits forces collisions so the verify / re-hash path is exercised too."""
+    C = sp.canonical_csr(synth.branching_graph(n=80, k=4, n_branches=2, seed=5, workers=1, scale=2.0, noise=0.05).T)
+    n = C.shape[0]
+    rng = np.random.default_rng(n_codes)
+    code = rng.integers(n_codes, size=n).astype(np.int32)
+    code[:n_codes] = np.arange(min(n_codes, n))[:n]
+    code = np.unique(code, return_inverse=True)[1].astype(np.int32)
+    roots = np.array([3, 7, 11, 20, 33])
+    end_cells = np.sort(rng.choice(n, size=50, replace=False))
+    min_clusters = 1 if n_codes == 1 else 3
+    g = _lib.Graph(C, _lib.CDF_REFERENCE)
+    cdf = cwalk.build_cdf(C, 0)
+    s, slot = make_session(C, g, roots, code, min_clusters, end_cells, 6, True, 77)
+    s.set_hash_bits(hash_bits)
+    total = 0
+    for rnd, sims in enumerate((50, 400)):
+        st = s.round(rnd, sims, 0, len(roots) * sims)
+        seq, ok, cand = oracle_round(C, cdf, roots, sims, 6, 77, rnd, code, min_clusters, slot, True)
+        assert st["n_walkers"] == len(seq) and st["n_pass_clusters"] == int(ok.sum())
+        assert st["n_terminal"] == int((ok & (slot[seq[:, -1]] >= 0)).sum())
+        assert st["n_kept"] == len(cand), (st, len(cand))
+        if hash_bits < 128 and st["n_terminal"] > st["n_kept"] + 5:
+            assert st["dedup_passes"] >= 2
+        r, w, sl = s.fetch_index(total)
+        np.testing.assert_array_equal(w, cand)
+        np.testing.assert_array_equal(sl, slot[seq[cand, -1]])
+        assert (r == rnd).all()
+        np.testing.assert_array_equal(s.fetch_rows(np.arange(total, total + len(cand))), seq[cand])
+        total += len(cand)
+    assert s.rows() == total
+    pick = np.random.default_rng(1).integers(total, size=33)
+    assert s.fetch_rows(pick).shape == (33, 6)
+    s.close(); g.close()
+
+
+def test_k3_not_unique_keeps_duplicates_and_sharded_prune():
+    C = sp.canonical_csr(synth.branching_graph(n=80, k=4, n_branches=2, seed=5, workers=1, scale=2.0, noise=0.05).T)
+    n = C.shape[0]
+    code = np.zeros(n, dtype=np.int32)
+    roots = np.array([3, 7, 11, 20])
+    end_cells = np.arange(n)
+    g = _lib.Graph(C, _lib.CDF_REFERENCE)
+    cdf = cwalk.build_cdf(C, 0)
+    s, slot = make_session(C, g, roots, code, 1, end_cells, 5, False, 9)
+    st = s.round(0, 300, 0, 1200)
+    assert st["n_kept"] == 1200 and st["dedup_passes"] == 0
+    s.close()
+    # two shards of one round, then global first-occurrence pruning == single-shard result
+    seq, ok, cand = oracle_round(C, cdf, roots, 300, 5, 9, 0, code, 1, slot, True)
+    import torch
+    sa, _ = make_session(C, g, roots, code, 1, end_cells, 5, True, 9)
+    sb, _ = make_session(C, g, roots, code, 1, end_cells, 5, True, 9)
+    sa.round(0, 300, 0, 500)
+    sb.round(0, 300, 500, 1200)
+    recs = []
+    for sess in (sa, sb):
+        p, m = sess.round_records()
+        recs.append(torch.as_tensor(cytopath_b200.sampler._DevPtr(p, m * 3), device="cuda").clone())
+    allr = torch.cat(recs)
+    torch.cuda.synchronize()
+    da = sa.round_prune(allr.data_ptr(), allr.numel() // 3)
+    db = sb.round_prune(allr.data_ptr(), allr.numel() // 3)
+    assert da == 0 and db > 0
+    wa = sa.fetch_index()[1]; wb = sb.fetch_index()[1]
+    np.testing.assert_array_equal(np.concatenate([wa, wb]), cand)
+    np.testing.assert_array_equal(np.vstack([sa.fetch_rows(np.arange(sa.rows())), sb.fetch_rows(np.arange(sb.rows()))]), seq[cand])
+    sa.close(); sb.close(); g.close()
+
+
+# ---- size-independent properties at larger sizes ------------------------------------------
+def test_partition_independence_and_edge_validity_large():
+    """100k cells, 200k walkers: any sharding of the walker range gives the same rows, and
+    every step follows an edge of T (checked against the CSR)."""
+    gph = synth.branching_graph(n=100_000, k=30, n_branches=8, seed=0)
+    C = sp.canonical_csr(gph.T)
+    g = _lib.Graph(C, _lib.CDF_EXACT)
+    roots = np.where(gph.clusters == "stem0")[0][:200]
+    sims, nt = 1000, 50
+    full = g.walk(roots, sims, nt, seed=1234)
+    parts = [g.walk(roots, sims, nt, seed=1234, walker_begin=a, n_walkers=b - a) for a, b in ((0, 70_001), (70_001, 200_000))]
+    np.testing.assert_array_equal(np.vstack(parts), full)
+    src, dst = full[:, :-1].ravel(), full[:, 1:].ravel()
+    assert (np.asarray(C[src, dst]).ravel() > 0).all()
+    np.testing.assert_array_equal(full[:, 0], np.repeat(roots, sims))
+    # the C oracle agrees on a 4k-walker sample of the same round
+    pick = np.arange(0, 200_000, 50)
+    cdf = cwalk.build_cdf(C, 1)
+    for w in pick[:200]:
+        np.testing.assert_array_equal(cwalk.walk(C, cdf, np.repeat(roots, sims)[w:w + 1], nt, seed=1234, walker_begin=int(w))[0], full[w])
+    g.close()
+
+
+def test_native_rng_one_step_frequencies_chi_square():
+    """With the native Philox stream the empirical one-step transition frequencies match the
+    effective probabilities (bin widths of the CDF actually sampled) at p > 1e-4 per row
+    after Bonferroni correction over the tested rows."""
+    from scipy import stats
+    C = sp.canonical_csr(GRAPHS["k30"]())
+    for mode, omode in MODES:
+        g = _lib.Graph(C, mode)
+        cdf = cwalk.build_cdf(C, omode).astype(np.float64)
+        rows = np.array([0, 17, 500, 1234, 3000, 3695])
+        sims = 200_000
+        seq = g.walk(rows, sims, 1, seed=99)
+        for i, r in enumerate(rows):
+            a, b = C.indptr[r], C.indptr[r + 1]
+            width = np.diff(np.concatenate([[0.0], cdf[a:b]]))
+            width = np.maximum(width, 0.0)
+            counts = np.array([(seq[i * sims:(i + 1) * sims, 1] == c).sum() for c in C.indices[a:b]])
+            assert counts.sum() == sims
+            keep = width * sims >= 5                                  # chi-square validity
+            assert counts[~keep].sum() <= max(50, 10 * (width[~keep].sum() * sims))
+            exp = width[keep] / width[keep].sum() * counts[keep].sum()
+            chi2, p = stats.chisquare(counts[keep], exp)
+            assert p > 1e-4 / len(rows), (mode, r, chi2, p)
+        g.close()

@@ -1,0 +1,195 @@
+"""Host logic of cytopath_b200.sampling (a7, a3 host side, a4, a5) on CPU, with the oracle
+standing in for the CUDA kernels (tests/oracle_backend.py).  The GPU suite repeats the
+golden cases through the real library (tests/test_gpu_parity.py)."""
+import contextlib
+import io
+import os
+import subprocess
+import sys
+import warnings
+
+import numpy as np
+import pandas as pd
+import pytest
+from scipy import sparse
+
+import cytopath_b200
+from cytopath_b200 import synth
+from cytopath_b200.sampler import _canonical_csr, check_convergence_criteria, iterate_state_probability
+from tests import oracle_backend
+from tests.helpers import SAMPLING_CASES, adata_from_case, load
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run_quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return fn(*a, **k)
+
+
+def check_against_golden(ad, z, score_rtol=2e-6):
+    s = ad.uns["samples"]
+    ri = ad.uns["run_info"]
+    assert ri["simulation_steps"] == int(z["simulation_steps"])
+    assert ri["didrun"] is True
+    np.testing.assert_array_equal(np.asarray(ri["root_cells"]), z["run_root_cells"])
+    np.testing.assert_array_equal(np.asarray(ri["end_points"]), z["run_end_points"])
+    assert s["cell_sequences"].dtype == np.int32
+    np.testing.assert_array_equal(s["cell_sequences"], z["cell_sequences"])
+    assert s["cluster_sequences"].dtype == z["cluster_sequences"].dtype
+    np.testing.assert_array_equal(s["cluster_sequences"], z["cluster_sequences"])
+    assert s["transition_score"].dtype == np.float32
+    np.testing.assert_allclose(s["transition_score"], z["transition_score"], rtol=score_rtol)
+    assert len(ri["b200"]["rounds"]) == int(z["rounds"])
+
+
+@pytest.mark.parametrize("name", SAMPLING_CASES)
+def test_sampling_host_logic_matches_reference(name):
+    z = load(name)
+    ad, kw = adata_from_case(z)
+    np.random.seed(int(z["np_seed"]))
+    run_quiet(cytopath_b200.sampling, ad, **kw, seed=int(z["seed"]), _backend=oracle_backend, dist=False)
+    check_against_golden(ad, z)
+
+
+def test_copy_returns_new_object_and_leaves_input_alone():
+    z = load("sampling_tiny_dups")
+    ad, kw = adata_from_case(z)
+    np.random.seed(int(z["np_seed"]))
+    out = run_quiet(cytopath_b200.sampling, ad, **kw, seed=int(z["seed"]), copy=True, _backend=oracle_backend, dist=False)
+    assert out is not ad and "samples" not in ad.uns
+    check_against_golden(out, z)
+
+
+def test_signature_is_the_reference_signature():
+    import inspect
+    sig = inspect.signature(cytopath_b200.sampling)
+    names = [p.name for p in sig.parameters.values() if p.kind == p.POSITIONAL_OR_KEYWORD]
+    assert names == ["data", "auto_adjust", "matrix_key", "cluster_key", "max_steps", "min_sim_ratio", "rounds_limit",
+                     "traj_number", "sim_number", "end_point_probability", "root_cell_probability", "end_points",
+                     "root_cells", "end_clusters", "root_clusters", "min_clusters", "max_iter", "tol", "normalize",
+                     "unique", "num_cores", "copy"]
+    d = {p.name: p.default for p in sig.parameters.values()}
+    assert (d["auto_adjust"], d["matrix_key"], d["cluster_key"], d["max_steps"], d["min_sim_ratio"]) == (True, "T_forward", "louvain", 10, 0.6)
+    assert (d["rounds_limit"], d["traj_number"], d["sim_number"], d["min_clusters"], d["max_iter"], d["tol"]) == (10, 200, 500, 2, 200, 1e-3)
+    assert (d["end_point_probability"], d["root_cell_probability"], d["normalize"], d["unique"], d["num_cores"], d["copy"]) == (0.99, 0.99, False, True, 1, False)
+
+
+# ---- error behaviour (reference :156-262, :367) --------------------------------------------
+def small_adata():
+    g = synth.branching_graph(n=300, k=10, n_branches=2, seed=3, workers=1, scale=4.0, noise=0.03)
+    return g, g.to_adata()
+
+
+def test_errors_match_reference_messages():
+    g, ad = small_adata()
+    kw = dict(_backend=oracle_backend, dist=False, auto_adjust=False)
+    bad = ad.copy(); bad.uns["T_forward"] = bad.uns["T_forward"][:100]
+    with pytest.raises(ValueError, match="num_cells x num_cells"):
+        run_quiet(cytopath_b200.sampling, bad, **kw)
+    bad = ad.copy(); bad.uns["T_forward"] = bad.uns["T_forward"] * 1.5
+    with pytest.raises(ValueError, match="has not been normalized"):
+        run_quiet(cytopath_b200.sampling, bad, **kw)
+    bad = ad.copy(); bad.obs["louvain"] = bad.obs["louvain"].astype(str)
+    with pytest.raises(ValueError, match="Categorical cluster labels"):
+        run_quiet(cytopath_b200.sampling, bad, **kw)
+    with pytest.raises(ValueError, match="Categorical cluster labels"):
+        run_quiet(cytopath_b200.sampling, ad.copy(), cluster_key="nope", **kw)
+    bad = ad.copy(); del bad.obs["root_cells"]
+    with pytest.raises(ValueError, match="Root cells must be provided"):
+        run_quiet(cytopath_b200.sampling, bad, **kw)
+    bad = ad.copy(); del bad.obs["end_points"]
+    with pytest.raises(ValueError, match="End points must be provided"):
+        run_quiet(cytopath_b200.sampling, bad, root_clusters=g.root_clusters, **kw)
+    with pytest.raises(ValueError, match="Terminal cluster set is empty"):
+        run_quiet(cytopath_b200.sampling, ad.copy(), end_point_probability=2.0, **kw)
+    # unreachable quota -> the reference's failure rule fires at round rounds_limit + 1 (:360-367)
+    with pytest.raises(ValueError, match="Sampling failed"):
+        run_quiet(cytopath_b200.sampling, ad.copy(), max_steps=3, rounds_limit=1, traj_number=50, sim_number=40,
+                  root_clusters=g.root_clusters, end_clusters=g.end_clusters, **kw)
+
+
+def test_non_louvain_key_warns():
+    g, ad = small_adata()
+    ad.obs["leiden"] = ad.obs["louvain"]
+    with pytest.warns(UserWarning, match="finely resolved clustering"):
+        with contextlib.redirect_stdout(io.StringIO()):
+            cytopath_b200.sampling(ad, auto_adjust=False, cluster_key="leiden", max_steps=60, traj_number=5, sim_number=200,
+                                   _backend=oracle_backend, dist=False)
+
+
+def test_numpy_array_arguments_like_undirected_simulations():
+    """utils.undirected_simulations passes numpy arrays for root_cells / end_points (utils.py:86-90)."""
+    g, ad = small_adata()
+    ad.obs["undirected_sim_included"] = pd.Categorical(["1"] * ad.shape[0])
+    run_quiet(cytopath_b200.sampling, ad, root_cells=np.arange(0, 300, 7), end_points=np.arange(300),
+              cluster_key="undirected_sim_included", auto_adjust=False, min_clusters=1, sim_number=300, traj_number=300,
+              max_steps=6, _backend=oracle_backend, dist=False)
+    assert ad.uns["samples"]["cell_sequences"].shape == (300, 6)
+
+
+def test_canonical_csr_equals_densify_resparsify():
+    M = synth.random_sparse_rows(n=150, max_nnz=9, seed=11, messy=True, dtype=np.float32)
+    want = sparse.csr_matrix(np.float64(np.asarray(M.toarray())))
+    got = _canonical_csr(M)
+    np.testing.assert_array_equal(got.indptr, want.indptr)
+    np.testing.assert_array_equal(got.indices, want.indices)
+    np.testing.assert_array_equal(got.data, want.data)
+    dense = _canonical_csr(np.asarray(M.toarray()))
+    np.testing.assert_array_equal(dense.data, want.data)
+
+
+def test_convergence_helpers():
+    z = load("convergence_probes")
+    for i, want in enumerate(z["result"]):
+        got = check_convergence_criteria(z["p%d" % i], tol=1e-3)
+        assert (-1 if got is None else got) == want
+    g, ad = small_adata()
+    init = (ad.obs["root_cells"] / ad.obs["root_cells"].sum()).values
+    stat = (ad.obs["end_points"] / ad.obs["end_points"].sum()).values
+    h, full, c = run_quiet(iterate_state_probability, ad, init=init, stationary=stat, max_iter=50, tol=1e-3)
+    assert full.shape == (50, 300) and h.shape[0] == c
+    np.testing.assert_array_equal(full[0], init)
+
+
+# ---- multi-rank sharding over gloo (world_size 2), CPU -----------------------------------
+WORKER = r"""
+import contextlib, io, os, sys, warnings
+import numpy as np
+sys.path.insert(0, {root!r})
+import torch.distributed as dist
+import cytopath_b200
+from tests import oracle_backend
+from tests.helpers import adata_from_case, load
+dist.init_process_group("gloo")
+z = load({case!r})
+ad, kw = adata_from_case(z)
+np.random.seed(int(z["np_seed"]))
+with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+    warnings.simplefilter("ignore")
+    cytopath_b200.sampling(ad, **kw, seed=int(z["seed"]), _backend=oracle_backend)
+s = ad.uns["samples"]
+np.savez({out!r} + ".%d.npz" % dist.get_rank(), cell_sequences=s["cell_sequences"], transition_score=s["transition_score"],
+         cluster_sequences=s["cluster_sequences"], world=ad.uns["run_info"]["b200"]["world_size"])
+dist.destroy_process_group()
+"""
+
+
+@pytest.mark.parametrize("case", ["sampling_tiny_dups", "sampling_small_clusters"])
+def test_two_rank_gloo_run_equals_reference(case, tmp_path):
+    script = tmp_path / "worker.py"
+    out = str(tmp_path / "out")
+    script.write_text(WORKER.format(root=ROOT, case=case, out=out))
+    env = dict(os.environ, TQDM_DISABLE="1", OMP_NUM_THREADS="2")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29531", str(script)],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    z = load(case)
+    for rank in (0, 1):
+        got = np.load(out + ".%d.npz" % rank)
+        assert int(got["world"]) == 2
+        np.testing.assert_array_equal(got["cell_sequences"], z["cell_sequences"])
+        np.testing.assert_array_equal(got["cluster_sequences"], z["cluster_sequences"])
+        np.testing.assert_allclose(got["transition_score"], z["transition_score"], rtol=2e-6)
