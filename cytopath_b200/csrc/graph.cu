@@ -52,10 +52,10 @@ build_cdf_kernel(int64_t n, const int64_t *__restrict__ row_ptr, const int32_t *
     const int64_t r0 = static_cast<int64_t>(blockIdx.x) * kK1Threads;
     const int64_t r1 = min(r0 + kK1Threads, n);
     const int nrows = static_cast<int>(r1 - r0);
-    if (threadIdx.x <= nrows) {
-        const int64_t r = r0 + threadIdx.x;
-        s_src[threadIdx.x] = row_ptr[r];
-        s_dst[threadIdx.x] = (r < n) ? static_cast<int64_t>(rows[r].off_units) * align_elems : total_units * align_elems;
+    for (int i = threadIdx.x; i <= nrows; i += kK1Threads) {
+        const int64_t r = r0 + i;
+        s_src[i] = row_ptr[r];
+        s_dst[i] = (r < n) ? static_cast<int64_t>(rows[r].off_units) * align_elems : total_units * align_elems;
     }
     __syncthreads();
     const int64_t src0 = s_src[0], cnt = s_src[nrows] - src0;
