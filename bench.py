@@ -244,6 +244,11 @@ def run_b200(args, w):
     achieved = W * nt * bytes_per_step / (ms_launch * 1e-3) / 1e9
     assert int(d_miss.item()) == 0, "walkers hit rows without a CDF crossing"
 
+    if args.kernel_only:
+        if rank == 0:
+            print(json.dumps({"metric": "walker_steps_per_sec", "value": value, "ms_per_step": ms_max / args.steps,
+                              "kernel": kernel_name, "roofline_frac": achieved / peak, "kernel_only": True}), flush=True)
+        return
     # ---- e2e through the C ABI with host buffers (pinned), every step: upload CSR + K1 + round (K2+K3) + read-back
     row_ptr = torch.from_numpy(np.ascontiguousarray(C.indptr, dtype=np.int64)).pin_memory()
     col = torch.from_numpy(np.ascontiguousarray(C.indices, dtype=np.int32)).pin_memory()
@@ -339,6 +344,7 @@ def main():
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--kernel-only", action="store_true", help="profiling runs: only the device-resident K2 loop")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         print("note: fewer than 3 warm-up steps requested", file=sys.stderr)

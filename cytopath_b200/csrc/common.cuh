@@ -90,6 +90,7 @@ struct cyp_graph {
     int32_t max_len = 0;
     double mean_len = 0.0;
     int align_elems = 4;       // 4 (float64 CDF) or 8 (float32 CDF): 32 bytes
+    int monotone = 1;          // every probability >= 0, so each row's CDF is non-decreasing (binary search is exact)
     cyp::RowInfo *d_row = nullptr;   // [n]
     void *d_cdf = nullptr;           // float or double [padded]
     int32_t *d_col = nullptr;        // [padded]

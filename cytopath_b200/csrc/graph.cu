@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(kK1Threads)
 build_cdf_kernel(int64_t n, const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ raw_col,
                  const double *__restrict__ raw_val, const RowInfo *__restrict__ rows, int align_elems,
                  int64_t total_units, CdfT *__restrict__ cdf, int32_t *__restrict__ col, double *__restrict__ val,
-                 int smem_elems) {
+                 int smem_elems, int *__restrict__ negative_flag) {
     extern __shared__ double s_val[];                 // [smem_elems] raw values, then cumulative sums in place
     __shared__ int64_t s_src[kK1Threads + 1];         // CSR offsets of the CTA's rows
     __shared__ int64_t s_dst[kK1Threads + 1];         // padded offsets of the CTA's rows
@@ -61,7 +61,13 @@ build_cdf_kernel(int64_t n, const int64_t *__restrict__ row_ptr, const int32_t *
     const int64_t src0 = s_src[0], cnt = s_src[nrows] - src0;
     const int64_t dst0 = s_dst[0], dcnt = s_dst[nrows] - dst0;
     if (cnt <= smem_elems) {
-        for (int64_t i = threadIdx.x; i < cnt; i += kK1Threads) s_val[i] = raw_val[src0 + i];
+        bool neg = false;
+        for (int64_t i = threadIdx.x; i < cnt; i += kK1Threads) {
+            const double v = raw_val[src0 + i];
+            neg |= v < 0.0;
+            s_val[i] = v;
+        }
+        if (neg) atomicOr(negative_flag, 1);
         __syncthreads();
         if (threadIdx.x < nrows) {
             const int64_t a = s_src[threadIdx.x] - src0, b = s_src[threadIdx.x + 1] - src0;
@@ -98,6 +104,7 @@ build_cdf_kernel(int64_t n, const int64_t *__restrict__ row_ptr, const int32_t *
         double acc = 0.0;
         for (int64_t j = 0; j < len; ++j) {
             const double v = raw_val[a + j];
+            if (v < 0.0) atomicOr(negative_flag, 1);
             acc = __dadd_rn(acc, v);
             cdf[dst + j] = finish_cdf<CdfT>(acc);
             col[dst + j] = raw_col[a + j];
@@ -195,10 +202,12 @@ extern "C" int cyp_graph_create(int device, int64_t n_cells, int64_t nnz, const 
 
     int32_t *d_raw_col = nullptr;
     double *d_raw_val = nullptr;
+    int *d_flag = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     auto cleanup = [&](int code, const std::string &msg) {
         cudaFree(d_raw_col);
         cudaFree(d_raw_val);
+        cudaFree(d_flag);
         if (e0) cudaEventDestroy(e0);
         if (e1) cudaEventDestroy(e1);
         graph_free(g);
@@ -218,6 +227,8 @@ extern "C" int cyp_graph_create(int device, int64_t n_cells, int64_t nnz, const 
     G_CUDA(cudaMalloc(&g->d_val, sizeof(double) * g->padded));
     G_CUDA(cudaMalloc(&d_raw_col, sizeof(int32_t) * nnz));
     G_CUDA(cudaMalloc(&d_raw_val, sizeof(double) * nnz));
+    G_CUDA(cudaMalloc(&d_flag, sizeof(int)));
+    G_CUDA(cudaMemset(d_flag, 0, sizeof(int)));
     g->device_bytes = sizeof(RowInfo) * n_cells + sizeof(int64_t) * (n_cells + 1) +
                       (cdf_elem + sizeof(int32_t) + sizeof(double)) * g->padded;
     G_CUDA(cudaMemcpy(g->d_row, rows.data(), sizeof(RowInfo) * n_cells, cudaMemcpyHostToDevice));
@@ -239,17 +250,22 @@ extern "C" int cyp_graph_create(int device, int64_t n_cells, int64_t nnz, const 
         G_CUDA(cudaFuncSetAttribute(build_cdf_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         build_cdf_kernel<double><<<grid, kK1Threads, smem_bytes>>>(n_cells, g->d_row_ptr, d_raw_col, d_raw_val, g->d_row, A,
                                                                    units, static_cast<double *>(g->d_cdf), g->d_col,
-                                                                   g->d_val, smem_elems);
+                                                                   g->d_val, smem_elems, d_flag);
     } else {
         G_CUDA(cudaFuncSetAttribute(build_cdf_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         build_cdf_kernel<float><<<grid, kK1Threads, smem_bytes>>>(n_cells, g->d_row_ptr, d_raw_col, d_raw_val, g->d_row, A,
                                                                   units, static_cast<float *>(g->d_cdf), g->d_col,
-                                                                  g->d_val, smem_elems);
+                                                                  g->d_val, smem_elems, d_flag);
     }
     G_CUDA(cudaGetLastError());
     G_CUDA(cudaEventRecord(e1));
     G_CUDA(cudaEventSynchronize(e1));
     G_CUDA(cudaEventElapsedTime(&g->build_ms, e0, e1));
+    int negative = 0;
+    G_CUDA(cudaMemcpy(&negative, d_flag, sizeof(int), cudaMemcpyDeviceToHost));
+    g->monotone = negative ? 0 : 1;
+    cudaFree(d_flag);
+    d_flag = nullptr;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaFree(d_raw_col);

@@ -24,15 +24,6 @@ namespace cyp {
 
 constexpr int kWalkThreads = 256;
 
-__device__ __forceinline__ uint64_t mix64(uint64_t x) {      // murmur3 fmix64
-    x ^= x >> 33;
-    x *= 0xff51afd7ed558ccdull;
-    x ^= x >> 33;
-    x *= 0xc4ceb9fe1a85ec53ull;
-    x ^= x >> 33;
-    return x;
-}
-
 template <typename CdfT> struct Vec16;
 template <> struct Vec16<double> {
     using type = double2;
@@ -61,8 +52,6 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const WalkParams p) 
     constexpr int VEC = V::n;
     constexpr int ALIGN = 32 / sizeof(CdfT);
     constexpr int CHUNK = G * VEC * UNROLL;
-    constexpr int MASKW = (MODE == kModeFilter1) ? 1 : (MODE == kModeFilter4) ? 4 : 0;
-    constexpr bool FILTER = MODE != kModePlain;
 
     const int lane = threadIdx.x & 31;
     const int gl = lane & (G - 1);
@@ -81,18 +70,8 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const WalkParams p) 
 
         int32_t mine = cur;                               // lane (c % G) holds column c until the group flushes
         if (G == 1) out_row[0] = cur;
-        uint64_t h1 = 0x9E3779B97F4A7C15ull, h2 = 0xD6E8FEB86659FD93ull;
-        uint64_t cmask[MASKW > 0 ? MASKW : 1] = {0};
-        if constexpr (FILTER) {
-            h1 = mix64(h1 ^ static_cast<uint32_t>(cur));
-            h2 = (h2 + static_cast<uint32_t>(cur)) * 0x9FB21C651E98DF25ull;
-        }
-        if constexpr (MASKW > 0) {
-            const unsigned code = p.code8[cur];
-#pragma unroll
-            for (int m = 0; m < MASKW; ++m)
-                if ((code >> 6) == static_cast<unsigned>(m)) cmask[m] |= 1ull << (code & 63);
-        }
+        WalkerDigest<MODE> dg;
+        dg.visit(p, cur);
         unsigned misses = 0;
         double u_even = 0.0, u_odd = 0.0;
 
@@ -143,30 +122,12 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const WalkParams p) 
                 const int cbase = c & ~(G - 1);
                 if (cbase + gl <= c) out_row[cbase + gl] = mine;
             }
-            if constexpr (FILTER) {
-                h1 = mix64(h1 ^ static_cast<uint32_t>(cur));
-                h2 = (h2 + static_cast<uint32_t>(cur)) * 0x9FB21C651E98DF25ull;
-                h2 ^= h2 >> 29;
-            }
-            if constexpr (MASKW > 0) {
-                const unsigned code = p.code8[cur];
-#pragma unroll
-                for (int m = 0; m < MASKW; ++m)
-                    if ((code >> 6) == static_cast<unsigned>(m)) cmask[m] |= 1ull << (code & 63);
-            }
+            dg.visit(p, cur);
         }
         if (nt == 0 && G > 1 && gl == 0) out_row[0] = mine;
         if (gl == 0) {
             if (misses && p.nocross) atomicAdd(p.nocross, static_cast<unsigned long long>(misses));
-            if constexpr (FILTER) {
-                int distinct = 0;
-#pragma unroll
-                for (int m = 0; m < MASKW; ++m) distinct += __popcll(cmask[m]);
-                const bool pass = (MASKW == 0) || distinct >= p.min_clusters;
-                p.out_slot[w] = pass ? p.end_slot[cur] : -2;
-                p.out_hash[2 * w] = h1;
-                p.out_hash[2 * w + 1] = mix64(h2);
-            }
+            dg.finish(p, w, cur);
         }
     }
 }
@@ -230,6 +191,7 @@ WalkVariant pick_walk_variant(const cyp_graph *g, int variant) {
 }
 
 int launch_walk(const cyp_graph *g, const WalkParams &p, WalkMode mode, int variant, cudaStream_t stream) {
+    if (variant >= 9000) return launch_walk_tma(g, p, mode, variant, stream);
     const WalkVariant v = pick_walk_variant(g, variant);
     if (g->cdf_mode == CYP_CDF_EXACT) return launch_variant<double>(p, v, mode, stream);
     return launch_variant<float>(p, v, mode, stream);
@@ -242,6 +204,7 @@ using namespace cyp;
 extern "C" const char *cyp_walk_variant_name(const cyp_graph *g, int variant) {
     static thread_local char buf[96];
     if (!g) return "";
+    if (variant >= 9000) return walk_tma_name(g, variant);
     const WalkVariant v = pick_walk_variant(g, variant);
     snprintf(buf, sizeof(buf), "walk_kernel<%s,lanes=%d,unroll=%d>", g->cdf_mode == CYP_CDF_EXACT ? "f64" : "f32", v.lanes,
              v.unroll);

@@ -41,10 +41,62 @@ struct WalkVariant {
     int unroll;   // independent 16-byte loads per lane per chunk
 };
 
+#ifdef __CUDACC__
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {      // murmur3 fmix64
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdull;
+    x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ull;
+    x ^= x >> 33;
+    return x;
+}
+
+// What the filter modes accumulate along a trajectory: a 128-bit hash of the cell sequence
+// (de-duplication key, :329-333) and the bitmap of truncated cluster labels visited (:322).
+template <int MODE>
+struct WalkerDigest {
+    static constexpr int MASKW = (MODE == kModeFilter1) ? 1 : (MODE == kModeFilter4) ? 4 : 0;
+    static constexpr bool FILTER = MODE != kModePlain;
+    uint64_t h1 = 0x9E3779B97F4A7C15ull, h2 = 0xD6E8FEB86659FD93ull;
+    uint64_t cmask[MASKW > 0 ? MASKW : 1] = {0};
+
+    __device__ __forceinline__ void visit(const WalkParams &p, int32_t cell) {
+        if constexpr (FILTER) {
+            h1 = mix64(h1 ^ static_cast<uint32_t>(cell));
+            h2 = (h2 + static_cast<uint32_t>(cell)) * 0x9FB21C651E98DF25ull;
+            h2 ^= h2 >> 29;
+        }
+        if constexpr (MASKW > 0) {
+            const unsigned code = p.code8[cell];
+#pragma unroll
+            for (int m = 0; m < MASKW; ++m)
+                if ((code >> 6) == static_cast<unsigned>(m)) cmask[m] |= 1ull << (code & 63);
+        }
+    }
+    // one thread per walker calls this after the last step
+    __device__ __forceinline__ void finish(const WalkParams &p, int64_t w, int32_t last_cell) const {
+        if constexpr (FILTER) {
+            int distinct = 0;
+#pragma unroll
+            for (int m = 0; m < MASKW; ++m) distinct += __popcll(cmask[m]);
+            const bool pass = (MASKW == 0) || distinct >= p.min_clusters;
+            p.out_slot[w] = pass ? p.end_slot[last_cell] : -2;
+            p.out_hash[2 * w] = h1;
+            p.out_hash[2 * w + 1] = mix64(h2);
+        }
+    }
+};
+#endif
+
 // Chooses lanes/unroll from the mean row length so that one chunk covers a typical row.
 WalkVariant pick_walk_variant(const cyp_graph *g, int variant);
 
 // Enqueues K2 on `stream`.  Returns a CYP_* code.
 int launch_walk(const cyp_graph *g, const WalkParams &p, WalkMode mode, int variant, cudaStream_t stream);
+
+// K2, TMA flavour (walk_tma.cu): one walker per thread, rows staged in shared memory by
+// cp.async.bulk.  `variant` = 9000 + threads per CTA / 32 (e.g. 9016 = 512 threads).
+int launch_walk_tma(const cyp_graph *g, const WalkParams &p, WalkMode mode, int variant, cudaStream_t stream);
+const char *walk_tma_name(const cyp_graph *g, int variant);
 
 }  // namespace cyp

@@ -1,0 +1,240 @@
+// K2, TMA flavour: the Markov-chain step loop (reference cytopath/markov_chain_sampler.py:45-51)
+// with one walker per THREAD and the CDF rows staged in shared memory by the bulk-copy engine.
+//
+// Why: the register flavour (walk.cu) is latency bound — a walker-step is three dependent
+// loads (row descriptor -> CDF row -> column index) and the row bytes in flight are limited by
+// registers (ncu: long-scoreboard stalls, 35 % DRAM utilisation at 40 warps/SM).  Here a row
+// in flight costs no registers: each thread issues ONE cp.async.bulk (UBLKCP) that copies its
+// whole 32-byte-aligned row (up to `slot_elems` entries) from HBM into its private shared
+// memory slot and signals the warp's mbarrier with the byte count.  A 512-thread CTA keeps
+// 512 rows (~210 KB) in flight per SM.  The first-crossing search (`u <= cdf[j]`, ties to the
+// bin, :49) then runs on shared memory: binary search when the row is known to be
+// non-decreasing (all probabilities >= 0), otherwise the literal left-to-right scan.
+// Rows longer than a slot are streamed through it in chunks.
+//
+// Per step and thread: 8-byte RowInfo load, one bulk copy, ~log2(len) LDS, one 4-byte column
+// load, one Philox call every second step, and a 16-byte trajectory store every fourth step.
+#include <cstdio>
+
+#include "walk.cuh"
+
+namespace cyp {
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (TMA, no tensor map); completion is reported to `bar` in bytes
+__device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+}  // namespace
+
+template <typename CdfT, int MODE>
+__global__ void __launch_bounds__(1024, 1) walk_tma_kernel(const WalkParams p, const int slot_elems, const int monotone) {
+    constexpr int ALIGN = 32 / sizeof(CdfT);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nthreads = blockDim.x;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
+    CdfT *slot = reinterpret_cast<CdfT *>(smem_raw + (((nthreads >> 5) * 8 + 127) & ~127)) + static_cast<size_t>(threadIdx.x) * slot_elems;
+    uint64_t *bar = bars + warp;
+    if (lane == 0) mbar_init(bar, 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    uint32_t parity = 0;
+
+    const CdfT *__restrict__ cdf = static_cast<const CdfT *>(p.cdf);
+    const int32_t *__restrict__ col = p.col;
+    const RowInfo *__restrict__ rows = p.rows;
+    const int nt = p.nt;
+    const bool vec_store = (p.ld & 3) == 0;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * nthreads;
+
+    for (int64_t wbase = static_cast<int64_t>(blockIdx.x) * nthreads + warp * 32; wbase < p.n_walkers; wbase += stride) {
+        const int64_t w = wbase + lane;
+        const bool active = w < p.n_walkers;
+        const uint64_t gw = static_cast<uint64_t>(p.walker_begin + w);
+        int32_t cur = active ? p.roots[gw / static_cast<uint64_t>(p.sims_per_root)] : 0;
+        int32_t *__restrict__ out_row = p.out_seq + (active ? w : 0) * p.ld;
+        const double *__restrict__ urow = (p.uniforms && active) ? p.uniforms + w * static_cast<int64_t>(nt) : nullptr;
+        int32_t b0 = cur, b1 = 0, b2 = 0, b3 = 0;         // columns 4q .. 4q+3 of the trajectory
+        if (active && (nt == 0 || !vec_store)) out_row[0] = cur;
+        WalkerDigest<MODE> dg;
+        if (active) dg.visit(p, cur);
+        unsigned misses = 0;
+        double u_even = 0.0, u_odd = 0.0;
+
+        for (int t = 0; t < nt; ++t) {
+            double u;
+            if (urow) {
+                u = urow[t];
+            } else {
+                if ((t & 1) == 0) walker_uniform_pair(p.seed, p.round, gw, static_cast<uint32_t>(t >> 1), u_even, u_odd);
+                u = (t & 1) ? u_odd : u_even;
+            }
+            RowInfo ri{0u, 0u};
+            if (active) ri = rows[cur];
+            const int len = static_cast<int>(ri.len);
+            const int len_pad = (len + ALIGN - 1) & ~(ALIGN - 1);
+            const int64_t off = static_cast<int64_t>(ri.off_units) * ALIGN;
+            int found = -1;
+            for (int base = 0;; base += slot_elems) {    // warp-uniform: all lanes take every barrier phase
+                const bool need = found < 0 && base < len;
+                if (!__any_sync(0xffffffffu, need)) break;
+                const int n = need ? min(len_pad - base, slot_elems) : 0;
+                if (n > 0) {
+                    const uint32_t bytes = static_cast<uint32_t>(n) * sizeof(CdfT);
+                    mbar_arrive_expect_tx(bar, bytes);
+                    bulk_copy_g2s(slot, cdf + off + base, bytes, bar);
+                } else {
+                    mbar_arrive(bar);
+                }
+                mbar_wait(bar, parity);
+                parity ^= 1u;
+                if (n > 0) {
+                    const int m = min(n, len - base);
+                    if (monotone) {                      // first j with u <= slot[j]
+                        int lo = 0, hi = m;
+                        while (lo < hi) {
+                            const int mid = (lo + hi) >> 1;
+                            if (u <= static_cast<double>(slot[mid])) hi = mid; else lo = mid + 1;
+                        }
+                        if (lo < m) found = base + lo;
+                    } else {
+                        for (int j = 0; j < m; ++j)
+                            if (u <= static_cast<double>(slot[j])) { found = base + j; break; }
+                    }
+                }
+                __syncwarp();                            // slot reads done before the next copy may overwrite it
+            }
+            if (active) {
+                if (found >= 0) cur = __ldg(col + off + found);
+                else ++misses;
+                const int c = t + 1;
+                if (vec_store) {
+                    const int q = c & 3;
+                    if (q == 0) b0 = cur; else if (q == 1) b1 = cur; else if (q == 2) b2 = cur; else b3 = cur;
+                    if (q == 3) {
+                        *reinterpret_cast<int4 *>(out_row + (c & ~3)) = make_int4(b0, b1, b2, b3);
+                    } else if (c == nt) {
+                        out_row[c & ~3] = b0;
+                        if (q >= 1) out_row[(c & ~3) + 1] = b1;
+                        if (q >= 2) out_row[(c & ~3) + 2] = b2;
+                    }
+                } else {
+                    out_row[c] = cur;
+                }
+                dg.visit(p, cur);
+            }
+        }
+        if (active) {
+            if (misses && p.nocross) atomicAdd(p.nocross, static_cast<unsigned long long>(misses));
+            dg.finish(p, w, cur);
+        }
+    }
+}
+
+struct TmaConfig {
+    int threads;
+    int slot_elems;
+    size_t smem;
+};
+
+static TmaConfig tma_config(const cyp_graph *g, int variant) {
+    const int elem = (g->cdf_mode == CYP_CDF_EXACT) ? 8 : 4;
+    const int align = 32 / elem;
+    const int max_pad = (g->max_len + align - 1) / align * align;
+    const int mean_pad = (static_cast<int>(g->mean_len + 0.999) + align - 1) / align * align;
+    const size_t budget = 227 * 1024 - 1024;
+    int threads = (variant > 9000) ? (variant - 9000) * 32 : 0;
+    int slot = max_pad;
+    if (threads == 0) {
+        // widest CTA whose slots hold a whole typical row; rows are 32 B .. several KB
+        threads = 1024;
+        const int want = (max_pad <= 2 * mean_pad) ? max_pad : 2 * mean_pad;
+        while (threads > 128 && static_cast<size_t>(threads) * want * elem + 1024 > budget) threads -= 32;
+        slot = want;
+    }
+    if (threads > 1024) threads = 1024;
+    if (threads < 32) threads = 32;
+    size_t cap = (budget - 1024) / (static_cast<size_t>(threads) * elem);
+    cap = cap / align * align;
+    if (static_cast<size_t>(slot) > cap) slot = static_cast<int>(cap);
+    if (slot < align) slot = align;
+    const size_t smem = ((threads / 32 * 8 + 127) & ~127) + static_cast<size_t>(threads) * slot * elem;
+    return TmaConfig{threads, slot, smem};
+}
+
+template <typename CdfT, int MODE>
+static int launch_tma_one(const cyp_graph *g, const WalkParams &p, const TmaConfig &c, cudaStream_t stream) {
+    auto kernel = walk_tma_kernel<CdfT, MODE>;
+    static int sm_count = 0;
+    static size_t smem_set = 0;
+    if (sm_count == 0) {
+        int dev = 0;
+        CYP_CUDA(cudaGetDevice(&dev));
+        CYP_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    if (c.smem > smem_set) {
+        CYP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c.smem)));
+        smem_set = c.smem;
+    }
+    const int64_t need = (p.n_walkers + c.threads - 1) / c.threads;
+    const unsigned grid = static_cast<unsigned>(need < sm_count ? need : sm_count);     // one persistent CTA per SM
+    if (grid == 0) return CYP_OK;
+    kernel<<<grid, c.threads, c.smem, stream>>>(p, c.slot_elems, g->monotone);
+    CYP_CUDA(cudaGetLastError());
+    return CYP_OK;
+}
+
+template <typename CdfT>
+static int launch_tma_mode(const cyp_graph *g, const WalkParams &p, WalkMode mode, const TmaConfig &c, cudaStream_t stream) {
+    switch (mode) {
+        case kModePlain: return launch_tma_one<CdfT, kModePlain>(g, p, c, stream);
+        case kModeFilter0: return launch_tma_one<CdfT, kModeFilter0>(g, p, c, stream);
+        case kModeFilter1: return launch_tma_one<CdfT, kModeFilter1>(g, p, c, stream);
+        case kModeFilter4: return launch_tma_one<CdfT, kModeFilter4>(g, p, c, stream);
+    }
+    return fail(CYP_E_INVALID, "launch_walk_tma: bad mode");
+}
+
+int launch_walk_tma(const cyp_graph *g, const WalkParams &p, WalkMode mode, int variant, cudaStream_t stream) {
+    const TmaConfig c = tma_config(g, variant);
+    if (g->cdf_mode == CYP_CDF_EXACT) return launch_tma_mode<double>(g, p, mode, c, stream);
+    return launch_tma_mode<float>(g, p, mode, c, stream);
+}
+
+const char *walk_tma_name(const cyp_graph *g, int variant) {
+    static thread_local char buf[128];
+    const TmaConfig c = tma_config(g, variant);
+    snprintf(buf, sizeof(buf), "walk_tma_kernel<%s,threads=%d,slot=%d,%s>", g->cdf_mode == CYP_CDF_EXACT ? "f64" : "f32", c.threads,
+             c.slot_elems, g->monotone ? "bsearch" : "scan");
+    return buf;
+}
+
+}  // namespace cyp

@@ -1,0 +1,41 @@
+#!/usr/bin/env python
+"""Times every K2 variant (lanes x unroll) on one workload; prints a table.  GPU box only."""
+import argparse, ctypes, json, os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+from cytopath_b200 import _lib
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--workload", default="c4")
+ap.add_argument("--cdf-mode", default="exact")
+ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--variants", default="404,802,804,1602,1604,3202,3204")
+ap.add_argument("--walkers", type=int, default=0)
+args = ap.parse_args()
+w = bench.WORKLOADS[args.workload]
+g, C, roots = bench.make_graph(w, 1)
+mode = _lib.CDF_EXACT if args.cdf_mode == "exact" else _lib.CDF_REFERENCE
+graph = _lib.Graph(C, mode, 0)
+L = _lib.load()
+W = args.walkers or w["walkers"]; nt = w["max_steps"] - 1
+sims = -(-W // len(roots))
+d_roots = torch.tensor(roots, dtype=torch.int32, device="cuda")
+d_seq = torch.empty((W, nt + 1), dtype=torch.int32, device="cuda")
+sptr = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+elem = 8 if mode == _lib.CDF_EXACT else 4
+bps = elem * (C.nnz / C.shape[0]) + 16
+print("workload %s mode %s W=%d nt=%d build_ms=%.2f" % (args.workload, args.cdf_mode, W, nt, graph.build_ms()))
+for v in [int(x) for x in args.variants.split(",")]:
+    def step(i):
+        _lib.check(L.cyp_walk_device(graph.handle, d_roots.data_ptr(), len(roots), sims, 0, W, nt, 1234, i, None,
+                                     d_seq.data_ptr(), None, v, sptr))
+    step(0); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps): step(1 + i)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    rate = W * nt / ms / 1e6
+    print("variant %5d  %8.2f ms  %7.3f G walker-steps/s  %6.1f GB/s algorithmic (%.1f%% of 6546.6)" % (v, ms, rate, rate * bps, rate * bps / 65.466))

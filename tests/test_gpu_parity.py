@@ -118,6 +118,17 @@ def test_k2_bit_exact_vs_oracle_all_variants(gname, mode, omode):
                                          ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
             torch.cuda.synchronize()
             np.testing.assert_array_equal(out.cpu().numpy(), want, err_msg="lanes=%d unroll=%d" % (lanes, unroll))
+    # TMA flavour: 128 / 256 / 512 / 1024 threads per CTA (1024 forces rows to stream through small slots)
+    for variant in (9004, 9008, 9016, 9032):
+        for n_t in (nt, 62):                                  # 63 columns: scalar stores; 64 columns: int4 stores
+            wnt = want if n_t == nt else cwalk.walk(C, cdf, np.repeat(roots, sims), n_t, seed=seed, round_idx=rnd, strict=False)
+            out = torch.full((len(roots) * sims, n_t + 1), -7, dtype=torch.int32, device="cuda")
+            miss = torch.zeros(1, dtype=torch.int64, device="cuda")
+            _lib.check(L.cyp_walk_device(g.handle, d_roots.data_ptr(), len(roots), sims, 0, len(roots) * sims, n_t, seed, rnd,
+                                         None, out.data_ptr(), miss.data_ptr(), variant,
+                                         ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            torch.cuda.synchronize()
+            np.testing.assert_array_equal(out.cpu().numpy(), wnt, err_msg="%s nt=%d" % (g.variant_name(variant), n_t))
     # auto variant through the host entry point, a shard in the middle of the round
     got = g.walk(roots, sims, nt, seed=seed, round_idx=rnd, walker_begin=100, n_walkers=211, strict=False)
     np.testing.assert_array_equal(got, want[100:311])
@@ -138,6 +149,31 @@ def test_k2_edge_cases_ties_zero_and_last_bin():
         got = g.walk(roots, 1, 3, uniforms=u)
         np.testing.assert_array_equal(got, want)
         np.testing.assert_array_equal(cwalk.walk(C, cdf, roots, 3, uniforms=u), want)
+        g.close()
+
+
+def test_k2_negative_probabilities_use_the_literal_scan():
+    """A row whose CDF is not monotone (negative entry): the reference takes the FIRST index with
+    u <= cdf (np.where(...)[0][0], :49); a binary search would be wrong, so the library must scan."""
+    from scipy import sparse
+    P = np.array([[0.7, -0.2, 0.5, 0.0], [0.0, 1.0, 0.0, 0.0], [0.3, 0.3, -0.1, 0.5], [0.25, 0.25, 0.25, 0.25]])
+    C = sp.canonical_csr(sparse.csr_matrix(P))
+    L = _lib.load()
+    import ctypes
+    import torch
+    for mode, omode in MODES:
+        g = _lib.Graph(C, mode)
+        cdf = cwalk.build_cdf(C, omode)
+        roots = np.array([0, 2, 3])
+        want = cwalk.walk(C, cdf, np.repeat(roots, 500), 20, seed=3)
+        np.testing.assert_array_equal(g.walk(roots, 500, 20, seed=3), want)
+        d_roots = torch.tensor(roots, dtype=torch.int32, device="cuda")
+        out = torch.zeros((1500, 21), dtype=torch.int32, device="cuda")
+        _lib.check(L.cyp_walk_device(g.handle, d_roots.data_ptr(), 3, 500, 0, 1500, 20, 3, 0, None, out.data_ptr(), None, 9008,
+                                     ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        torch.cuda.synchronize()
+        assert "scan" in g.variant_name(9008)
+        np.testing.assert_array_equal(out.cpu().numpy(), want)
         g.close()
 
 
