@@ -34,6 +34,8 @@ WORKLOADS = {
     "c3": dict(n=100_000, k=30, branches=8, stems=1, walkers=1_000_000, max_steps=200, desc="configs[2]: 100k cells k=30, 1M walkers x 200 steps (L2-resident)"),
     "c4": dict(n=1_000_000, k=50, branches=16, stems=1, walkers=1_250_000, max_steps=500,
                desc="configs[3]: 1M cells k=50 (51M nnz), 10M walkers x 500 steps / 8 GPUs = 1.25M walkers per GPU (HBM-bound)"),
+    "c5": dict(n=250_000, k=200, branches=0, stems=1, walkers=1_250_000, max_steps=200,
+               desc="configs[4]-shaped: cycling + convergent graph, 250k cells k=200 (50M nnz, long rows), 1.25M walkers x 200 steps per GPU"),
     "tiny": dict(n=20_000, k=30, branches=4, stems=1, walkers=100_000, max_steps=100, desc="developer smoke size"),
 }
 
@@ -52,10 +54,14 @@ def host_cores():
 def make_graph(w, world):
     from cytopath_b200 import synth
     from cytopath_b200.sampler import _canonical_csr
-    g = synth.branching_graph(n=w["n"], k=w["k"], n_branches=w["branches"], n_root_stems=w["stems"], seed=0,
-                              workers=max(1, host_cores() // world))
+    workers = max(1, host_cores() // world)
+    if w["branches"] == 0:
+        g = synth.cycling_graph(n=w["n"], k=w["k"], seed=0, workers=workers)
+        roots = np.where(g.root_prob >= 0.99)[0].astype(np.int32)        # unsupervised roots (markov_chain_sampler.py:226)
+    else:
+        g = synth.branching_graph(n=w["n"], k=w["k"], n_branches=w["branches"], n_root_stems=w["stems"], seed=0, workers=workers)
+        roots = np.where(np.isin(g.clusters, g.root_clusters))[0].astype(np.int32)
     C = _canonical_csr(g.T)
-    roots = np.where(np.isin(g.clusters, g.root_clusters))[0].astype(np.int32)
     return g, C, roots
 
 
@@ -108,24 +114,40 @@ def mean_visited_row_len(C, seq_sample):
     return float(lens[seq_sample[:, :-1].ravel()].mean())
 
 
+def timed_port_sample(cb, prep, pool, roots, clusters, max_steps, cores, budget_s):
+    """Size one joblib call (one task per root cell, 2 tasks per core, like :306-308) to about
+    `budget_s` of wall time.  The per-walker cost is measured in-process first so that each task
+    steps for ~budget_s/2: the per-task argument pickling of the reference's call pattern (the
+    label array travels with every task) is then a few percent of the timed call, as it would
+    be at the reference's own task sizes.  Returns (roots, sims, rate, wall, dispatch_wall)."""
+    import time as _t
+    from oracle import sampler_port as sp
+    sample_roots = np.resize(roots, 2 * cores)
+    cl = np.asarray(clusters, dtype=object)
+    t0 = _t.perf_counter()
+    sp.markov_sim_port(0, 4, max_steps, sample_roots, cl, None, prep["idx_ell"], prep["cdf_ell"], None, prep["prob_ell"])
+    per_walker = (_t.perf_counter() - t0) / 4.0
+    sims = int(min(65536, max(1, budget_s * cores / (len(sample_roots) * per_walker))))
+    cb.joblib_port_rate(prep, sample_roots[:cores], clusters, min(max_steps, 20), 1, cores, pool)        # warm the pool
+    _, dt1, _ = cb.joblib_port_rate(prep, sample_roots, clusters, min(max_steps, 3), 1, cores, pool)      # dispatch only
+    rate, dt, _ = cb.joblib_port_rate(prep, sample_roots, clusters, max_steps, sims, cores, pool)
+    return sample_roots, sims, rate, dt, dt1
+
+
 def cpu_baseline_sample(C, g, roots, max_steps, cdf_mode, budget_s=12.0):
     """Bounded sample of the same workload on the host cores: faithful joblib port (kind 'port')."""
     from joblib import Parallel
     from oracle import cpu_baseline as cb
     cores = host_cores()
     prep = cb.prepare(C, cdf_mode)
-    sample_roots = roots[: max(4 * cores, 8)]
-    if len(sample_roots) < 4 * cores:
-        sample_roots = np.resize(roots, 4 * cores)
-    with Parallel(n_jobs=cores) as pool:
-        cb.joblib_port_rate(prep, sample_roots[:cores], g.clusters, min(max_steps, 20), 1, cores, pool)      # warm the pool
-        rate, dt, _ = cb.joblib_port_rate(prep, sample_roots, g.clusters, max_steps, 1, cores, pool)          # calibrate
-        sims = int(max(1, min(4096, budget_s / max(dt, 1e-3))))
-        if sims > 1:
-            rate, dt, _ = cb.joblib_port_rate(prep, sample_roots, g.clusters, max_steps, sims, cores, pool)
-    c_rate, c_dt, c_thr = cb.c_port_rate(prep, np.resize(roots, 4096), max_steps, max(1, int(2e8 / (4096 * max_steps))))
-    sample = "%d root cells x %d walkers x %d steps, joblib(n_jobs=%d) over root cells, %.1f s" % (
-        len(sample_roots), sims, max_steps, cores, dt)
+    try:
+        with Parallel(n_jobs=cores) as pool:
+            sample_roots, sims, rate, dt, dt1 = timed_port_sample(cb, prep, pool, roots, g.clusters, max_steps, cores, budget_s)
+        c_rate, c_dt, c_thr = cb.c_port_rate(prep, np.resize(roots, 4096), max_steps, max(1, int(2e8 / (4096 * max_steps))))
+    finally:
+        cb.cleanup(prep)
+    sample = "%d root cells x %d walkers x %d steps, joblib(n_jobs=%d) over root cells, %.1f s (of which %.1f s task dispatch)%s" % (
+        len(sample_roots), sims, max_steps, cores, dt, dt1, ", ELL arrays pre-memmapped" if prep.get("tmpdir") else "")
     return ({"value": rate, "unit": "walker-steps/s", "cores": cores, "kind": "port", "sample": sample},
             {"value": c_rate, "unit": "walker-steps/s", "cores": c_thr, "kind": "port-c-openmp",
              "sample": "oracle/walk.c, %.2f s" % c_dt})
@@ -143,17 +165,17 @@ def run_reference(args, w):
     cores = host_cores()
     mode = 1 if args.cdf_mode == "exact" else 0
     prep = cb.prepare(C, mode)
-    sample_roots = np.resize(roots, 4 * cores)
     max_steps = w["max_steps"]
     times = []
-    with Parallel(n_jobs=cores) as pool:
-        cb.joblib_port_rate(prep, sample_roots[:cores], g.clusters, min(max_steps, 20), 1, cores, pool)
-        _, dt1, _ = cb.joblib_port_rate(prep, sample_roots, g.clusters, max_steps, 1, cores, pool)
-        sims = int(max(1, min(4096, 6.0 / max(dt1, 1e-3))))            # ~6 s per step
-        for i in range(args.warmup + args.steps):
-            rate, dt, _ = cb.joblib_port_rate(prep, sample_roots, g.clusters, max_steps, sims, cores, pool)
-            if i >= args.warmup:
-                times.append(dt)
+    try:
+        with Parallel(n_jobs=cores) as pool:
+            sample_roots, sims, _, _, _ = timed_port_sample(cb, prep, pool, roots, g.clusters, max_steps, cores, 5.0)   # ~5 s of stepping per step
+            for i in range(args.warmup + args.steps):
+                rate, dt, _ = cb.joblib_port_rate(prep, sample_roots, g.clusters, max_steps, sims, cores, pool)
+                if i >= args.warmup:
+                    times.append(dt)
+    finally:
+        cb.cleanup(prep)
     steps_per = len(sample_roots) * sims * (max_steps - 1)
     value = steps_per * len(times) / sum(times)
     sample = "%d root cells x %d walkers x %d steps per step, joblib(n_jobs=%d)" % (len(sample_roots), sims, max_steps, cores)
@@ -256,7 +278,7 @@ def run_b200(args, w):
     trunc = np.array([c[:8] for c in g.clusters], dtype="U8")
     code_names, cell_code = np.unique(trunc, return_inverse=True)
     cell_code = np.ascontiguousarray(cell_code, dtype=np.int32)
-    end_cells = np.where(np.isin(g.clusters, g.end_clusters))[0]
+    end_cells = np.where(np.isin(g.clusters, g.end_clusters))[0] if w["branches"] else np.where(g.end_prob >= 0.99)[0]
     end_slot = np.full(C.shape[0], -1, dtype=np.int32)
     end_slot[end_cells] = np.arange(len(end_cells), dtype=np.int32)
     n_fetch = 2000

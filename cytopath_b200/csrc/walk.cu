@@ -191,7 +191,7 @@ WalkVariant pick_walk_variant(const cyp_graph *g, int variant) {
 }
 
 int launch_walk(const cyp_graph *g, const WalkParams &p, WalkMode mode, int variant, cudaStream_t stream) {
-    if (variant >= 9000) return launch_walk_tma(g, p, mode, variant, stream);
+    if (variant == 0 || variant >= 9000) return launch_walk_tma(g, p, mode, variant, stream);
     const WalkVariant v = pick_walk_variant(g, variant);
     if (g->cdf_mode == CYP_CDF_EXACT) return launch_variant<double>(p, v, mode, stream);
     return launch_variant<float>(p, v, mode, stream);
@@ -204,7 +204,7 @@ using namespace cyp;
 extern "C" const char *cyp_walk_variant_name(const cyp_graph *g, int variant) {
     static thread_local char buf[96];
     if (!g) return "";
-    if (variant >= 9000) return walk_tma_name(g, variant);
+    if (variant == 0 || variant >= 9000) return walk_tma_name(g, variant);
     const WalkVariant v = pick_walk_variant(g, variant);
     snprintf(buf, sizeof(buf), "walk_kernel<%s,lanes=%d,unroll=%d>", g->cdf_mode == CYP_CDF_EXACT ? "f64" : "f32", v.lanes,
              v.unroll);

@@ -130,7 +130,6 @@ __global__ void __launch_bounds__(1024, 1) walk_tma_kernel(const WalkParams p, c
                             if (u <= static_cast<double>(slot[j])) { found = base + j; break; }
                     }
                 }
-                __syncwarp();                            // slot reads done before the next copy may overwrite it
             }
             if (active) {
                 if (found >= 0) cur = __ldg(col + off + found);
@@ -165,26 +164,32 @@ struct TmaConfig {
     size_t smem;
 };
 
+// Launch shape.  Measured on B200 (profiles/r01_sweeps.md): throughput rises with the row bytes
+// in flight per SM until the shared-memory carve-out leaves the L1 (which still serves the
+// RowInfo / column / label loads) less than ~40 KB, then drops by a third.  HBM-bound graphs
+// therefore use ~188 KB of slots and at most 768 threads; graphs that fit the L2 are latency
+// bound instead and take every thread that fits.
 static TmaConfig tma_config(const cyp_graph *g, int variant) {
     const int elem = (g->cdf_mode == CYP_CDF_EXACT) ? 8 : 4;
     const int align = 32 / elem;
     const int max_pad = (g->max_len + align - 1) / align * align;
     const int mean_pad = (static_cast<int>(g->mean_len + 0.999) + align - 1) / align * align;
-    const size_t budget = 227 * 1024 - 1024;
+    const size_t hard_budget = 226 * 1024;
     int threads = (variant > 9000) ? (variant - 9000) * 32 : 0;
-    int slot = max_pad;
+    int slot = (max_pad <= 2 * mean_pad) ? max_pad : 2 * mean_pad;   // ragged graphs: long rows stream in chunks
     if (threads == 0) {
-        // widest CTA whose slots hold a whole typical row; rows are 32 B .. several KB
-        threads = 1024;
-        const int want = (max_pad <= 2 * mean_pad) ? max_pad : 2 * mean_pad;
-        while (threads > 128 && static_cast<size_t>(threads) * want * elem + 1024 > budget) threads -= 32;
-        slot = want;
+        const bool l2_resident = static_cast<double>(g->padded) * (elem + 4) < 64.0 * 1024 * 1024;
+        const size_t budget = l2_resident ? hard_budget : 188 * 1024;
+        const int cap = l2_resident ? 1024 : 768;
+        threads = static_cast<int>(budget / (static_cast<size_t>(slot) * elem)) / 32 * 32;
+        if (threads > cap) threads = cap;
+        if (threads < 128) threads = 128;
     }
     if (threads > 1024) threads = 1024;
     if (threads < 32) threads = 32;
-    size_t cap = (budget - 1024) / (static_cast<size_t>(threads) * elem);
-    cap = cap / align * align;
-    if (static_cast<size_t>(slot) > cap) slot = static_cast<int>(cap);
+    size_t cap_elems = (hard_budget - 1024) / (static_cast<size_t>(threads) * elem);
+    cap_elems = cap_elems / align * align;
+    if (static_cast<size_t>(slot) > cap_elems) slot = static_cast<int>(cap_elems);
     if (slot < align) slot = align;
     const size_t smem = ((threads / 32 * 8 + 127) & ~127) + static_cast<size_t>(threads) * slot * elem;
     return TmaConfig{threads, slot, smem};
