@@ -74,9 +74,18 @@ __device__ __forceinline__ void walker_uniform_pair(uint64_t seed, uint32_t roun
 // Rows are stored "sector aligned": every row starts on a 32-byte boundary of the CDF
 // array (4 doubles / 8 floats), so a row of k entries touches ceil(k*sizeof/32) sectors
 // and 16-byte vector loads are always legal.  col/val use the same element offsets.
-struct RowInfo {          // one 8-byte load per walker-step
+struct RowInfo {          // read once per walker, for its root cell
     uint32_t off_units;   // row start / align_elems
     uint32_t len;         // entries in the row
+};
+// One 16-byte record per edge, at the same offset as the edge's CDF entry: the target cell AND
+// the target's row descriptor.  The walker therefore needs no separate RowInfo lookup between
+// steps: a step is two dependent memory phases (CDF row -> edge record) instead of three.
+struct EdgeRec {
+    int32_t col;          // target cell (-1 in padding)
+    uint32_t off_units;   // target's row start / align_elems
+    uint32_t len;         // target's row length
+    uint32_t reserved;
 };
 
 }  // namespace cyp
@@ -93,7 +102,8 @@ struct cyp_graph {
     int monotone = 1;          // every probability >= 0, so each row's CDF is non-decreasing (binary search is exact)
     cyp::RowInfo *d_row = nullptr;   // [n]
     void *d_cdf = nullptr;           // float or double [padded]
-    int32_t *d_col = nullptr;        // [padded]
+    int32_t *d_col = nullptr;        // [padded] column indices (transition scores look edges up here)
+    cyp::EdgeRec *d_edge = nullptr;  // [padded] what the step kernel reads after the first-crossing search
     double *d_val = nullptr;         // [padded] raw probabilities (transition scores)
     int64_t *d_row_ptr = nullptr;    // [n+1] original CSR offsets (fetch_cdf un-pads with it)
     int64_t device_bytes = 0;

@@ -44,8 +44,8 @@ template <typename CdfT>
 __global__ void __launch_bounds__(kK1Threads)
 build_cdf_kernel(int64_t n, const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ raw_col,
                  const double *__restrict__ raw_val, const RowInfo *__restrict__ rows, int align_elems,
-                 int64_t total_units, CdfT *__restrict__ cdf, int32_t *__restrict__ col, double *__restrict__ val,
-                 int smem_elems, int *__restrict__ negative_flag) {
+                 int64_t total_units, CdfT *__restrict__ cdf, int32_t *__restrict__ col, EdgeRec *__restrict__ edge,
+                 double *__restrict__ val, int smem_elems, int *__restrict__ negative_flag) {
     extern __shared__ double s_val[];                 // [smem_elems] raw values, then cumulative sums in place
     __shared__ int64_t s_src[kK1Threads + 1];         // CSR offsets of the CTA's rows
     __shared__ int64_t s_dst[kK1Threads + 1];         // padded offsets of the CTA's rows
@@ -88,12 +88,16 @@ build_cdf_kernel(int64_t n, const int64_t *__restrict__ row_ptr, const int32_t *
             const int64_t len = s_src[lo + 1] - s_src[lo];
             if (j < len) {
                 const int64_t q = s_src[lo] + j;
+                const int32_t c = raw_col[q];
+                const RowInfo tr = rows[c];
                 cdf[dst0 + p] = finish_cdf<CdfT>(s_val[q - src0]);
-                col[dst0 + p] = raw_col[q];
+                col[dst0 + p] = c;
+                edge[dst0 + p] = EdgeRec{c, tr.off_units, tr.len, 0u};
                 val[dst0 + p] = raw_val[q];
             } else {                                   // padding never matches: u >= 0 > -1
                 cdf[dst0 + p] = static_cast<CdfT>(-1);
                 col[dst0 + p] = -1;
+                edge[dst0 + p] = EdgeRec{-1, 0u, 0u, 0u};
                 val[dst0 + p] = 0.0;
             }
         }
@@ -106,13 +110,17 @@ build_cdf_kernel(int64_t n, const int64_t *__restrict__ row_ptr, const int32_t *
             const double v = raw_val[a + j];
             if (v < 0.0) atomicOr(negative_flag, 1);
             acc = __dadd_rn(acc, v);
+            const int32_t c = raw_col[a + j];
+            const RowInfo tr = rows[c];
             cdf[dst + j] = finish_cdf<CdfT>(acc);
-            col[dst + j] = raw_col[a + j];
+            col[dst + j] = c;
+            edge[dst + j] = EdgeRec{c, tr.off_units, tr.len, 0u};
             val[dst + j] = v;
         }
         for (int64_t j = len; j < len_pad; ++j) {
             cdf[dst + j] = static_cast<CdfT>(-1);
             col[dst + j] = -1;
+            edge[dst + j] = EdgeRec{-1, 0u, 0u, 0u};
             val[dst + j] = 0.0;
         }
     }
@@ -149,6 +157,7 @@ static void graph_free(cyp_graph *g) {
     cudaFree(g->d_row);
     cudaFree(g->d_cdf);
     cudaFree(g->d_col);
+    cudaFree(g->d_edge);
     cudaFree(g->d_val);
     cudaFree(g->d_row_ptr);
     delete g;
@@ -224,13 +233,14 @@ extern "C" int cyp_graph_create(int device, int64_t n_cells, int64_t nnz, const 
     G_CUDA(cudaMalloc(&g->d_row_ptr, sizeof(int64_t) * (n_cells + 1)));
     G_CUDA(cudaMalloc(&g->d_cdf, cdf_elem * g->padded));
     G_CUDA(cudaMalloc(&g->d_col, sizeof(int32_t) * g->padded));
+    G_CUDA(cudaMalloc(&g->d_edge, sizeof(EdgeRec) * g->padded));
     G_CUDA(cudaMalloc(&g->d_val, sizeof(double) * g->padded));
     G_CUDA(cudaMalloc(&d_raw_col, sizeof(int32_t) * nnz));
     G_CUDA(cudaMalloc(&d_raw_val, sizeof(double) * nnz));
     G_CUDA(cudaMalloc(&d_flag, sizeof(int)));
     G_CUDA(cudaMemset(d_flag, 0, sizeof(int)));
     g->device_bytes = sizeof(RowInfo) * n_cells + sizeof(int64_t) * (n_cells + 1) +
-                      (cdf_elem + sizeof(int32_t) + sizeof(double)) * g->padded;
+                      (cdf_elem + sizeof(int32_t) + sizeof(EdgeRec) + sizeof(double)) * g->padded;
     G_CUDA(cudaMemcpy(g->d_row, rows.data(), sizeof(RowInfo) * n_cells, cudaMemcpyHostToDevice));
     G_CUDA(cudaMemcpy(g->d_row_ptr, h_row_ptr, sizeof(int64_t) * (n_cells + 1), cudaMemcpyHostToDevice));
     G_CUDA(cudaMemcpy(d_raw_col, h_col, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice));
@@ -238,6 +248,7 @@ extern "C" int cyp_graph_create(int device, int64_t n_cells, int64_t nnz, const 
     // slack region: never-matching padding
     G_CUDA(cudaMemset(static_cast<char *>(g->d_cdf) + cdf_elem * units * A, 0xFF, cdf_elem * 4 * A));   // NaN: u <= NaN is false
     G_CUDA(cudaMemset(g->d_col + units * A, 0xFF, sizeof(int32_t) * 4 * A));
+    G_CUDA(cudaMemset(g->d_edge + units * A, 0, sizeof(EdgeRec) * 4 * A));
     G_CUDA(cudaMemset(g->d_val + units * A, 0, sizeof(double) * 4 * A));
 
     G_CUDA(cudaEventCreate(&e0));
@@ -250,12 +261,12 @@ extern "C" int cyp_graph_create(int device, int64_t n_cells, int64_t nnz, const 
         G_CUDA(cudaFuncSetAttribute(build_cdf_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         build_cdf_kernel<double><<<grid, kK1Threads, smem_bytes>>>(n_cells, g->d_row_ptr, d_raw_col, d_raw_val, g->d_row, A,
                                                                    units, static_cast<double *>(g->d_cdf), g->d_col,
-                                                                   g->d_val, smem_elems, d_flag);
+                                                                   g->d_edge, g->d_val, smem_elems, d_flag);
     } else {
         G_CUDA(cudaFuncSetAttribute(build_cdf_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         build_cdf_kernel<float><<<grid, kK1Threads, smem_bytes>>>(n_cells, g->d_row_ptr, d_raw_col, d_raw_val, g->d_row, A,
                                                                   units, static_cast<float *>(g->d_cdf), g->d_col,
-                                                                  g->d_val, smem_elems, d_flag);
+                                                                  g->d_edge, g->d_val, smem_elems, d_flag);
     }
     G_CUDA(cudaGetLastError());
     G_CUDA(cudaEventRecord(e1));

@@ -585,7 +585,7 @@ extern "C" int cyp_session_round(cyp_session *s, uint32_t round, int64_t sims_pe
 
     // ---- K2
     WalkParams p{};
-    p.rows = s->g->d_row; p.cdf = s->g->d_cdf; p.col = s->g->d_col;
+    p.rows = s->g->d_row; p.cdf = s->g->d_cdf; p.edge = s->g->d_edge;
     p.roots = s->d_roots; p.sims_per_root = sims_per_root;
     p.walker_begin = walker_begin; p.n_walkers = W; p.nt = nt; p.round = round; p.seed = s->seed;
     p.uniforms = d_u; p.out_seq = d_seq; p.ld = ncol; p.nocross = d_counters;

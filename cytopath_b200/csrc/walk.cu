@@ -2,13 +2,15 @@
 //
 // Work decomposition.  G lanes of a warp (G = 1, 2, 4, 8, 16 or 32, chosen from the mean row
 // length) cooperate on one walker and keep it for its whole trajectory:
-//   1. one 8-byte load of RowInfo{offset, len} for the current cell,
+//   1. the row descriptor {offset, len} of the current cell is already in registers (it came
+//      with the previous step's edge record; the root's is loaded once),
 //   2. the row's CDF segment is fetched with UNROLL independent 16-byte loads per lane
 //      (G * UNROLL * 16 bytes per chunk; a typical row is one chunk, so every sector of the
 //      row is requested once and all requests are in flight together),
 //   3. each lane finds its first element with u <= cdf (ties go to the bin, `<=` at :49),
 //      the group takes the minimum index with redux.sync (first crossing, :49),
-//   4. one 4-byte load of the column index at that position gives the next cell (:48).
+//   4. one 16-byte load of the edge record at that position gives the next cell (:48) and its
+//      row descriptor.
 // Uniforms come from Philox4x32-10 keyed by (seed; walker, t/2, round): lane i of the group
 // computes the pair for transitions 2i, 2i+1 of the current batch of 2G transitions and the
 // group reads them with shuffles, so no lane repeats another lane's Philox work.
@@ -58,13 +60,14 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const WalkParams p) 
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
     const int64_t n_groups = static_cast<int64_t>(gridDim.x) * (kWalkThreads / G);
     const CdfT *__restrict__ cdf = static_cast<const CdfT *>(p.cdf);
-    const int32_t *__restrict__ col = p.col;
+    const EdgeRec *__restrict__ edge = p.edge;
     const RowInfo *__restrict__ rows = p.rows;
     const int nt = p.nt;
 
     for (int64_t w = (static_cast<int64_t>(blockIdx.x) * kWalkThreads + threadIdx.x) / G; w < p.n_walkers; w += n_groups) {
         const uint64_t gw = static_cast<uint64_t>(p.walker_begin + w);
         int32_t cur = p.roots[gw / static_cast<uint64_t>(p.sims_per_root)];
+        RowInfo ri = rows[cur];
         int32_t *__restrict__ out_row = p.out_seq + w * p.ld;
         const double *__restrict__ urow = p.uniforms ? p.uniforms + w * static_cast<int64_t>(nt) : nullptr;
 
@@ -87,7 +90,6 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const WalkParams p) 
                 u = (G == 1) ? mine_u : __shfl_sync(gmask, mine_u, r >> 1, G);
             }
             // ---- row descriptor and first crossing
-            const RowInfo ri = rows[cur];
             const int len = static_cast<int>(ri.len);
             const int64_t off = static_cast<int64_t>(ri.off_units) * ALIGN;
             const CdfT *__restrict__ rowp = cdf + off;
@@ -111,10 +113,13 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const WalkParams p) 
                 found = group_min<G>(gmask, found);
                 if (found != 0xffffffffu) break;
             }
-            int32_t nxt = cur;
-            if (found != 0xffffffffu) nxt = __ldg(col + off + found);
-            else ++misses;
-            cur = nxt;
+            if (found != 0xffffffffu) {
+                const EdgeRec e = load_edge(edge + off + found);
+                cur = e.col;
+                ri = RowInfo{e.off_units, e.len};
+            } else {
+                ++misses;
+            }
             // ---- record column c = t + 1
             const int c = t + 1;
             if ((c & (G - 1)) == gl) mine = cur;
@@ -224,7 +229,7 @@ extern "C" int cyp_walk_device(const cyp_graph *g, const int32_t *d_root_cells, 
     WalkParams p{};
     p.rows = g->d_row;
     p.cdf = g->d_cdf;
-    p.col = g->d_col;
+    p.edge = g->d_edge;
     p.roots = d_root_cells;
     p.sims_per_root = sims_per_root;
     p.walker_begin = walker_begin;

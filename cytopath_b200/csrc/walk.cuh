@@ -6,9 +6,9 @@
 namespace cyp {
 
 struct WalkParams {
-    const RowInfo *rows;            // [n_cells]
+    const RowInfo *rows;            // [n_cells] row descriptor (read for the root cell only)
     const void *cdf;                // float / double, sector-aligned rows
-    const int32_t *col;             // same offsets as cdf
+    const EdgeRec *edge;            // same offsets as cdf: target cell + target's row descriptor
     const int32_t *roots;           // [n_roots]
     int64_t sims_per_root;
     int64_t walker_begin;           // global id of local walker 0
@@ -42,6 +42,15 @@ struct WalkVariant {
 };
 
 #ifdef __CUDACC__
+// 16-byte edge-record load that does not allocate an L1 line: the record is used once, and the
+// L1 left over by the shared-memory carve-out is needed for in-flight misses (profiles/r01).
+__device__ __forceinline__ EdgeRec load_edge(const EdgeRec *p) {
+    int4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return EdgeRec{v.x, static_cast<uint32_t>(v.y), static_cast<uint32_t>(v.z), 0u};
+}
+
 __device__ __forceinline__ uint64_t mix64(uint64_t x) {      // murmur3 fmix64
     x ^= x >> 33;
     x *= 0xff51afd7ed558ccdull;

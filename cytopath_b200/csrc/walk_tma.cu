@@ -12,8 +12,9 @@
 // non-decreasing (all probabilities >= 0), otherwise the literal left-to-right scan.
 // Rows longer than a slot are streamed through it in chunks.
 //
-// Per step and thread: 8-byte RowInfo load, one bulk copy, ~log2(len) LDS, one 4-byte column
-// load, one Philox call every second step, and a 16-byte trajectory store every fourth step.
+// Per step and thread: one bulk copy, ~log2(len) LDS, one 16-byte edge-record load (next cell +
+// its row descriptor, so no separate descriptor lookup), one Philox call every second step and
+// a 16-byte trajectory store every fourth step.
 #include <cstdio>
 
 #include "walk.cuh"
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(1024, 1) walk_tma_kernel(const WalkParams p, c
     uint32_t parity = 0;
 
     const CdfT *__restrict__ cdf = static_cast<const CdfT *>(p.cdf);
-    const int32_t *__restrict__ col = p.col;
+    const EdgeRec *__restrict__ edge = p.edge;
     const RowInfo *__restrict__ rows = p.rows;
     const int nt = p.nt;
     const bool vec_store = (p.ld & 3) == 0;
@@ -80,6 +81,8 @@ __global__ void __launch_bounds__(1024, 1) walk_tma_kernel(const WalkParams p, c
         const bool active = w < p.n_walkers;
         const uint64_t gw = static_cast<uint64_t>(p.walker_begin + w);
         int32_t cur = active ? p.roots[gw / static_cast<uint64_t>(p.sims_per_root)] : 0;
+        RowInfo ri{0u, 0u};
+        if (active) ri = rows[cur];
         int32_t *__restrict__ out_row = p.out_seq + (active ? w : 0) * p.ld;
         const double *__restrict__ urow = (p.uniforms && active) ? p.uniforms + w * static_cast<int64_t>(nt) : nullptr;
         int32_t b0 = cur, b1 = 0, b2 = 0, b3 = 0;         // columns 4q .. 4q+3 of the trajectory
@@ -97,8 +100,6 @@ __global__ void __launch_bounds__(1024, 1) walk_tma_kernel(const WalkParams p, c
                 if ((t & 1) == 0) walker_uniform_pair(p.seed, p.round, gw, static_cast<uint32_t>(t >> 1), u_even, u_odd);
                 u = (t & 1) ? u_odd : u_even;
             }
-            RowInfo ri{0u, 0u};
-            if (active) ri = rows[cur];
             const int len = static_cast<int>(ri.len);
             const int len_pad = (len + ALIGN - 1) & ~(ALIGN - 1);
             const int64_t off = static_cast<int64_t>(ri.off_units) * ALIGN;
@@ -132,8 +133,13 @@ __global__ void __launch_bounds__(1024, 1) walk_tma_kernel(const WalkParams p, c
                 }
             }
             if (active) {
-                if (found >= 0) cur = __ldg(col + off + found);
-                else ++misses;
+                if (found >= 0) {
+                    const EdgeRec e = load_edge(edge + off + found);
+                    cur = e.col;
+                    ri = RowInfo{e.off_units, e.len};
+                } else {
+                    ++misses;
+                }
                 const int c = t + 1;
                 if (vec_store) {
                     const int q = c & 3;
@@ -164,11 +170,10 @@ struct TmaConfig {
     size_t smem;
 };
 
-// Launch shape.  Measured on B200 (profiles/r01_sweeps.md): throughput rises with the row bytes
-// in flight per SM until the shared-memory carve-out leaves the L1 (which still serves the
-// RowInfo / column / label loads) less than ~40 KB, then drops by a third.  HBM-bound graphs
-// therefore use ~188 KB of slots and at most 768 threads; graphs that fit the L2 are latency
-// bound instead and take every thread that fits.
+// Launch shape.  Measured on B200 (profiles/r01_sweep*.log): throughput rises with the row bytes
+// in flight per SM; ~210 KB of slots (512 threads for 416-byte rows) is the best point for
+// HBM-bound graphs, and more than 768 threads per SM brings nothing.  Graphs that fit the L2 are
+// latency bound instead and take every thread that fits.
 static TmaConfig tma_config(const cyp_graph *g, int variant) {
     const int elem = (g->cdf_mode == CYP_CDF_EXACT) ? 8 : 4;
     const int align = 32 / elem;
@@ -179,7 +184,7 @@ static TmaConfig tma_config(const cyp_graph *g, int variant) {
     int slot = (max_pad <= 2 * mean_pad) ? max_pad : 2 * mean_pad;   // ragged graphs: long rows stream in chunks
     if (threads == 0) {
         const bool l2_resident = static_cast<double>(g->padded) * (elem + 4) < 64.0 * 1024 * 1024;
-        const size_t budget = l2_resident ? hard_budget : 188 * 1024;
+        const size_t budget = l2_resident ? hard_budget : 216 * 1024;
         const int cap = l2_resident ? 1024 : 768;
         threads = static_cast<int>(budget / (static_cast<size_t>(slot) * elem)) / 32 * 32;
         if (threads > cap) threads = cap;
