@@ -286,14 +286,24 @@ def run_b200(args, w):
     del d_seq
     torch.cuda.empty_cache()
 
+    e2e_ms = {}
+
+    def lap(name, t0):
+        e2e_ms[name] = e2e_ms.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
+        return time.perf_counter()
+
     def e2e_step(i):
         gh, sh = ctypes.c_void_p(), ctypes.c_void_p()
+        t0 = time.perf_counter()
         _lib.check(L.cyp_graph_create(local_rank, C.shape[0], C.nnz, ctypes.c_void_p(row_ptr.data_ptr()),
                                       ctypes.c_void_p(col.data_ptr()), ctypes.c_void_p(val.data_ptr()), mode, ctypes.byref(gh)))
+        t0 = lap("graph_create", t0)
         _lib.check(L.cyp_session_create(gh, _lib.ptr(roots), n_roots, _lib.ptr(cell_code), len(code_names), 2,
                                         _lib.ptr(end_slot), len(end_cells), max_steps, 1, args.seed, ctypes.byref(sh)))
+        t0 = lap("session_create", t0)
         st = _lib.RoundStats()
         _lib.check(L.cyp_session_round(sh, i, sims_per_root, w0, w0 + W, None, ctypes.byref(st)))
+        t0 = lap("round", t0)
         kept = st.n_kept
         slot = np.empty(kept, dtype=np.int32)
         walker = np.empty(kept, dtype=np.int64)
@@ -304,12 +314,15 @@ def run_b200(args, w):
         out = np.empty((m, max_steps), dtype=np.int32)
         if m:
             _lib.check(L.cyp_session_fetch_rows(sh, _lib.ptr(rows), m, _lib.ptr(out)))
+        t0 = lap("fetch", t0)
         L.cyp_session_destroy(sh)
         L.cyp_graph_destroy(gh)
+        lap("destroy", t0)
         return st, kept * 12 + m * max_steps * 4
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     st, d2h = e2e_step(0)                                          # warm-up
+    e2e_ms.clear()
     torch.cuda.synchronize(); barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
@@ -335,6 +348,7 @@ def run_b200(args, w):
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": "walker-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps, "kept_rows_last_step": int(st.n_kept), "ms_walk": st.ms_walk, "ms_filter": st.ms_filter,
+                "host_ms_per_step": {k: round(v / e2e_steps, 2) for k, v in e2e_ms.items()},
                 "what": "cyp_graph_create(pinned host CSR)+K1, cyp_session_round (K2+K3), fetch kept index + %d rows" % n_fetch},
         "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

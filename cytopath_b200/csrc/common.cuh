@@ -26,6 +26,14 @@ int fail(int code, const std::string &msg);
         if (!(cond)) return ::cyp::fail(CYP_E_INVALID, (msg));   \
     } while (0)
 
+// Device memory comes from the CUDA stream-ordered pool of the current device with its release
+// threshold lifted, so create/destroy cycles (one graph + session per sampling() call) reuse
+// memory instead of paying cudaMalloc/cudaFree each time.  All calls use the legacy default stream.
+cudaError_t dev_alloc(void **p, size_t bytes);
+void dev_free(void *p);
+template <typename T>
+inline cudaError_t dev_alloc(T **p, size_t bytes) { return dev_alloc(reinterpret_cast<void **>(p), bytes); }
+
 struct DeviceGuard {
     int prev = -1;
     explicit DeviceGuard(int dev) {
@@ -85,7 +93,7 @@ struct EdgeRec {
     int32_t col;          // target cell (-1 in padding)
     uint32_t off_units;   // target's row start / align_elems
     uint32_t len;         // target's row length
-    uint32_t reserved;
+    uint32_t code;        // target's cluster-label code for the session that last labelled the graph
 };
 
 }  // namespace cyp
@@ -108,4 +116,5 @@ struct cyp_graph {
     int64_t *d_row_ptr = nullptr;    // [n+1] original CSR offsets (fetch_cdf un-pads with it)
     int64_t device_bytes = 0;
     float build_ms = 0.f;
+    mutable uint64_t labels_owner = 0;   // id of the session whose label codes are in d_edge[].code (0 = none)
 };

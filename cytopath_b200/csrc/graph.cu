@@ -22,6 +22,26 @@ int fail(int code, const std::string &msg) {
     return code;
 }
 
+cudaError_t dev_alloc(void **p, size_t bytes) {
+    static bool pool_ready[64] = {false};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64 && !pool_ready[dev]) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        pool_ready[dev] = true;
+    }
+    *p = nullptr;
+    return cudaMallocAsync(p, bytes ? bytes : 1, nullptr);
+}
+void dev_free(void *p) {
+    if (p) cudaFreeAsync(p, nullptr);
+}
+
 // One CTA handles kK1Threads consecutive rows.  The CTA's slice of the CSR value array is
 // contiguous in HBM, so it is staged through shared memory with coalesced loads; each
 // thread then walks its own row sequentially in shared memory (the serial float64 chain,
@@ -154,12 +174,12 @@ extern "C" int cyp_device_count(int *n) {
 static void graph_free(cyp_graph *g) {
     if (!g) return;
     DeviceGuard guard(g->device);
-    cudaFree(g->d_row);
-    cudaFree(g->d_cdf);
-    cudaFree(g->d_col);
-    cudaFree(g->d_edge);
-    cudaFree(g->d_val);
-    cudaFree(g->d_row_ptr);
+    dev_free(g->d_row);
+    dev_free(g->d_cdf);
+    dev_free(g->d_col);
+    dev_free(g->d_edge);
+    dev_free(g->d_val);
+    dev_free(g->d_row_ptr);
     delete g;
 }
 
@@ -214,9 +234,9 @@ extern "C" int cyp_graph_create(int device, int64_t n_cells, int64_t nnz, const 
     int *d_flag = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     auto cleanup = [&](int code, const std::string &msg) {
-        cudaFree(d_raw_col);
-        cudaFree(d_raw_val);
-        cudaFree(d_flag);
+        dev_free(d_raw_col);
+        dev_free(d_raw_val);
+        dev_free(d_flag);
         if (e0) cudaEventDestroy(e0);
         if (e1) cudaEventDestroy(e1);
         graph_free(g);
@@ -229,15 +249,15 @@ extern "C" int cyp_graph_create(int device, int64_t n_cells, int64_t nnz, const 
                                               std::string(#expr) + ": " + cudaGetErrorString(_e));    \
     } while (0)
 
-    G_CUDA(cudaMalloc(&g->d_row, sizeof(RowInfo) * n_cells));
-    G_CUDA(cudaMalloc(&g->d_row_ptr, sizeof(int64_t) * (n_cells + 1)));
-    G_CUDA(cudaMalloc(&g->d_cdf, cdf_elem * g->padded));
-    G_CUDA(cudaMalloc(&g->d_col, sizeof(int32_t) * g->padded));
-    G_CUDA(cudaMalloc(&g->d_edge, sizeof(EdgeRec) * g->padded));
-    G_CUDA(cudaMalloc(&g->d_val, sizeof(double) * g->padded));
-    G_CUDA(cudaMalloc(&d_raw_col, sizeof(int32_t) * nnz));
-    G_CUDA(cudaMalloc(&d_raw_val, sizeof(double) * nnz));
-    G_CUDA(cudaMalloc(&d_flag, sizeof(int)));
+    G_CUDA(dev_alloc(&g->d_row, sizeof(RowInfo) * n_cells));
+    G_CUDA(dev_alloc(&g->d_row_ptr, sizeof(int64_t) * (n_cells + 1)));
+    G_CUDA(dev_alloc(&g->d_cdf, cdf_elem * g->padded));
+    G_CUDA(dev_alloc(&g->d_col, sizeof(int32_t) * g->padded));
+    G_CUDA(dev_alloc(&g->d_edge, sizeof(EdgeRec) * g->padded));
+    G_CUDA(dev_alloc(&g->d_val, sizeof(double) * g->padded));
+    G_CUDA(dev_alloc(&d_raw_col, sizeof(int32_t) * nnz));
+    G_CUDA(dev_alloc(&d_raw_val, sizeof(double) * nnz));
+    G_CUDA(dev_alloc(&d_flag, sizeof(int)));
     G_CUDA(cudaMemset(d_flag, 0, sizeof(int)));
     g->device_bytes = sizeof(RowInfo) * n_cells + sizeof(int64_t) * (n_cells + 1) +
                       (cdf_elem + sizeof(int32_t) + sizeof(EdgeRec) + sizeof(double)) * g->padded;
@@ -275,12 +295,12 @@ extern "C" int cyp_graph_create(int device, int64_t n_cells, int64_t nnz, const 
     int negative = 0;
     G_CUDA(cudaMemcpy(&negative, d_flag, sizeof(int), cudaMemcpyDeviceToHost));
     g->monotone = negative ? 0 : 1;
-    cudaFree(d_flag);
+    dev_free(d_flag);
     d_flag = nullptr;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    cudaFree(d_raw_col);
-    cudaFree(d_raw_val);
+    dev_free(d_raw_col);
+    dev_free(d_raw_val);
 #undef G_CUDA
     *out = g;
     return CYP_OK;
@@ -314,7 +334,7 @@ extern "C" int cyp_graph_fetch_cdf(const cyp_graph *g, void *h_cdf) {
     DeviceGuard guard(g->device);
     const size_t elem = (g->cdf_mode == CYP_CDF_EXACT) ? 8 : 4;
     void *d_out = nullptr;
-    CYP_CUDA(cudaMalloc(&d_out, elem * g->nnz));
+    CYP_CUDA(dev_alloc(&d_out, elem * g->nnz));
     const int threads = 256;
     const unsigned grid = static_cast<unsigned>((g->n * 32 + threads - 1) / threads);
     if (g->cdf_mode == CYP_CDF_EXACT)
@@ -325,7 +345,7 @@ extern "C" int cyp_graph_fetch_cdf(const cyp_graph *g, void *h_cdf) {
                                                   static_cast<const float *>(g->d_cdf), static_cast<float *>(d_out));
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpy(h_cdf, d_out, elem * g->nnz, cudaMemcpyDeviceToHost);
-    cudaFree(d_out);
+    dev_free(d_out);
     if (e != cudaSuccess) return fail(CYP_E_CUDA, std::string("cyp_graph_fetch_cdf: ") + cudaGetErrorString(e));
     return CYP_OK;
 }

@@ -60,9 +60,9 @@ extern "C" int cyp_transition_scores(const cyp_graph *g, const int32_t *h_seq, i
     int32_t *d_seq = nullptr;
     float *d_score = nullptr;
     unsigned long long *d_missing = nullptr;
-    cudaError_t e = cudaMalloc(&d_seq, sizeof(int32_t) * count);
-    if (e == cudaSuccess) e = cudaMalloc(&d_score, sizeof(float) * n_rows);
-    if (e == cudaSuccess) e = cudaMalloc(&d_missing, sizeof(unsigned long long));
+    cudaError_t e = dev_alloc(&d_seq, sizeof(int32_t) * count);
+    if (e == cudaSuccess) e = dev_alloc(&d_score, sizeof(float) * n_rows);
+    if (e == cudaSuccess) e = dev_alloc(&d_missing, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(d_missing, 0, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemcpy(d_seq, h_seq, sizeof(int32_t) * count, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
@@ -72,9 +72,9 @@ extern "C" int cyp_transition_scores(const cyp_graph *g, const int32_t *h_seq, i
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpy(h_score, d_score, sizeof(float) * n_rows, cudaMemcpyDeviceToHost);
-    cudaFree(d_seq);
-    cudaFree(d_score);
-    cudaFree(d_missing);
+    dev_free(d_seq);
+    dev_free(d_score);
+    dev_free(d_missing);
     if (e != cudaSuccess) return fail(CYP_E_CUDA, std::string("cyp_transition_scores: ") + cudaGetErrorString(e));
     return CYP_OK;
 }

@@ -287,6 +287,16 @@ distinct_codes_kernel(int64_t n_walkers, const int32_t *__restrict__ seq, int64_
     }
 }
 
+// writes the session's label code of every edge's target into the edge records, so the step
+// loop gets the label with the 16 bytes it loads anyway (no per-step code lookup)
+__global__ void __launch_bounds__(kThreads)
+label_edges_kernel(int64_t n_edges, EdgeRec *__restrict__ edge, const uint8_t *__restrict__ code8) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
+    if (i >= n_edges) return;
+    const int32_t c = edge[i].col;
+    edge[i].code = (c >= 0) ? code8[c] : 0u;
+}
+
 // prune against records gathered from all ranks: drop[k] = 1 if another record with the same
 // key has a lower walker id
 __global__ void __launch_bounds__(kThreads)
@@ -351,6 +361,7 @@ move_rows_kernel(int64_t n_keep, const int64_t *__restrict__ src_rank, int64_t r
 using namespace cyp;
 
 struct cyp_session {
+    uint64_t id = 0;
     const cyp_graph *g = nullptr;
     int device = 0;
     int64_t n_roots = 0;
@@ -379,12 +390,12 @@ namespace {
 struct Scratch {                   // frees everything it allocated when it goes out of scope
     std::vector<void *> ptrs;
     ~Scratch() {
-        for (void *p : ptrs) cudaFree(p);
+        for (void *p : ptrs) dev_free(p);
     }
     template <typename T>
     cudaError_t alloc(T **p, size_t count) {
         *p = nullptr;
-        cudaError_t e = cudaMalloc(reinterpret_cast<void **>(p), std::max<size_t>(count, 1) * sizeof(T));
+        cudaError_t e = dev_alloc(reinterpret_cast<void **>(p), std::max<size_t>(count, 1) * sizeof(T));
         if (e == cudaSuccess) ptrs.push_back(*p);
         return e;
     }
@@ -446,10 +457,10 @@ int grow_store(cyp_session *s, int64_t need_rows) {
     int32_t *n_store = nullptr, *n_round = nullptr, *n_slot = nullptr;
     int64_t *n_walker = nullptr;
     const size_t row_bytes = sizeof(int32_t) * static_cast<size_t>(s->max_steps);
-    cudaError_t e = cudaMalloc(&n_store, row_bytes * cap);
-    if (e == cudaSuccess) e = cudaMalloc(&n_round, sizeof(int32_t) * cap);
-    if (e == cudaSuccess) e = cudaMalloc(&n_walker, sizeof(int64_t) * cap);
-    if (e == cudaSuccess) e = cudaMalloc(&n_slot, sizeof(int32_t) * cap);
+    cudaError_t e = dev_alloc(&n_store, row_bytes * cap);
+    if (e == cudaSuccess) e = dev_alloc(&n_round, sizeof(int32_t) * cap);
+    if (e == cudaSuccess) e = dev_alloc(&n_walker, sizeof(int64_t) * cap);
+    if (e == cudaSuccess) e = dev_alloc(&n_slot, sizeof(int32_t) * cap);
     if (e == cudaSuccess && s->store_rows) {
         e = cudaMemcpy(n_store, s->d_store, row_bytes * s->store_rows, cudaMemcpyDeviceToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(n_round, s->d_st_round, sizeof(int32_t) * s->store_rows, cudaMemcpyDeviceToDevice);
@@ -457,10 +468,10 @@ int grow_store(cyp_session *s, int64_t need_rows) {
         if (e == cudaSuccess) e = cudaMemcpy(n_slot, s->d_st_slot, sizeof(int32_t) * s->store_rows, cudaMemcpyDeviceToDevice);
     }
     if (e != cudaSuccess) {
-        cudaFree(n_store); cudaFree(n_round); cudaFree(n_walker); cudaFree(n_slot);
+        dev_free(n_store); dev_free(n_round); dev_free(n_walker); dev_free(n_slot);
         return fail(e == cudaErrorMemoryAllocation ? CYP_E_NOMEM : CYP_E_CUDA, std::string("grow_store: ") + cudaGetErrorString(e));
     }
-    cudaFree(s->d_store); cudaFree(s->d_st_round); cudaFree(s->d_st_walker); cudaFree(s->d_st_slot);
+    dev_free(s->d_store); dev_free(s->d_st_round); dev_free(s->d_st_walker); dev_free(s->d_st_slot);
     s->d_store = n_store; s->d_st_round = n_round; s->d_st_walker = n_walker; s->d_st_slot = n_slot;
     s->store_cap = cap;
     return CYP_OK;
@@ -490,7 +501,9 @@ extern "C" int cyp_session_create(const cyp_graph *g, const int32_t *h_root_cell
         CYP_REQUIRE(h_end_slot_of_cell[i] >= -1 && h_end_slot_of_cell[i] < n_end_slots, "cyp_session_create: end slot out of range");
     }
     DeviceGuard guard(g->device);
+    static uint64_t next_id = 0;
     cyp_session *s = new cyp_session();
+    s->id = ++next_id;
     s->g = g;
     s->device = g->device;
     s->n_roots = n_roots;
@@ -500,18 +513,18 @@ extern "C" int cyp_session_create(const cyp_graph *g, const int32_t *h_root_cell
     s->max_steps = max_steps;
     s->unique = unique;
     s->seed = seed;
-    cudaError_t e = cudaMalloc(&s->d_roots, sizeof(int32_t) * n_roots);
+    cudaError_t e = dev_alloc(&s->d_roots, sizeof(int32_t) * n_roots);
     if (e == cudaSuccess) e = cudaMemcpy(s->d_roots, h_root_cells, sizeof(int32_t) * n_roots, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMalloc(&s->d_end_slot, sizeof(int32_t) * g->n);
+    if (e == cudaSuccess) e = dev_alloc(&s->d_end_slot, sizeof(int32_t) * g->n);
     if (e == cudaSuccess) e = cudaMemcpy(s->d_end_slot, h_end_slot_of_cell, sizeof(int32_t) * g->n, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && min_clusters > 1) {
         if (n_codes <= 256) {
             std::vector<uint8_t> c8(static_cast<size_t>(g->n));
             for (int64_t i = 0; i < g->n; ++i) c8[i] = static_cast<uint8_t>(h_cell_code[i]);
-            e = cudaMalloc(&s->d_code8, g->n);
+            e = dev_alloc(&s->d_code8, g->n);
             if (e == cudaSuccess) e = cudaMemcpy(s->d_code8, c8.data(), g->n, cudaMemcpyHostToDevice);
         } else {
-            e = cudaMalloc(&s->d_code32, sizeof(int32_t) * g->n);
+            e = dev_alloc(&s->d_code32, sizeof(int32_t) * g->n);
             if (e == cudaSuccess) e = cudaMemcpy(s->d_code32, h_cell_code, sizeof(int32_t) * g->n, cudaMemcpyHostToDevice);
         }
     }
@@ -526,9 +539,9 @@ extern "C" int cyp_session_create(const cyp_graph *g, const int32_t *h_root_cell
 extern "C" int cyp_session_destroy(cyp_session *s) {
     if (!s) return CYP_OK;
     DeviceGuard guard(s->device);
-    cudaFree(s->d_roots); cudaFree(s->d_code8); cudaFree(s->d_code32); cudaFree(s->d_end_slot);
-    cudaFree(s->d_store); cudaFree(s->d_st_round); cudaFree(s->d_st_walker); cudaFree(s->d_st_slot);
-    cudaFree(s->d_records);
+    dev_free(s->d_roots); dev_free(s->d_code8); dev_free(s->d_code32); dev_free(s->d_end_slot);
+    dev_free(s->d_store); dev_free(s->d_st_round); dev_free(s->d_st_walker); dev_free(s->d_st_slot);
+    dev_free(s->d_records);
     delete s;
     return CYP_OK;
 }
@@ -558,6 +571,14 @@ extern "C" int cyp_session_round(cyp_session *s, uint32_t round, int64_t sims_pe
     // HBM budget: trajectories + hash + slot (+ uniforms), and the worst-case dedup scratch and store growth
     size_t free_b = 0, total_b = 0;
     S_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    {   // memory the stream-ordered pool holds but is not using is available to this round too
+        cudaMemPool_t pool;
+        uint64_t reserved = 0, used = 0;
+        if (cudaDeviceGetDefaultMemPool(&pool, s->device) == cudaSuccess &&
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+            free_b += static_cast<size_t>(reserved - used);
+    }
     const double need = static_cast<double>(W) * (4.0 * ncol + 16 + 4 + (h_uniforms ? 8.0 * nt : 0.0)) * 1.05 +
                         static_cast<double>(W) * (4.0 * ncol + 100.0);
     if (need > static_cast<double>(free_b))
@@ -584,6 +605,11 @@ extern "C" int cyp_session_round(cyp_session *s, uint32_t round, int64_t sims_pe
     struct EvGuard { cudaEvent_t *e; ~EvGuard() { for (int i = 0; i < 3; ++i) cudaEventDestroy(e[i]); } } evg{ev};
 
     // ---- K2
+    if (s->d_code8 && s->g->labels_owner != s->id) {     // label the edge records for this session (once)
+        label_edges_kernel<<<blocks_for(s->g->padded, kThreads), kThreads, 0, st>>>(s->g->padded, s->g->d_edge, s->d_code8);
+        S_CUDA(cudaGetLastError());
+        s->g->labels_owner = s->id;
+    }
     WalkParams p{};
     p.rows = s->g->d_row; p.cdf = s->g->d_cdf; p.edge = s->g->d_edge;
     p.roots = s->d_roots; p.sims_per_root = sims_per_root;
@@ -657,10 +683,10 @@ extern "C" int cyp_session_round(cyp_session *s, uint32_t round, int64_t sims_pe
     rc = grow_store(s, s->store_rows + n_kept);
     if (rc != CYP_OK) return rc;
     if (n_kept > s->records_cap) {
-        cudaFree(s->d_records);
+        dev_free(s->d_records);
         s->d_records = nullptr;
         s->records_cap = 0;
-        S_CUDA(cudaMalloc(&s->d_records, sizeof(uint64_t) * 3 * n_kept));
+        S_CUDA(dev_alloc(&s->d_records, sizeof(uint64_t) * 3 * n_kept));
         s->records_cap = n_kept;
     }
     if (n_kept) {

@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const WalkParams p) 
         int32_t mine = cur;                               // lane (c % G) holds column c until the group flushes
         if (G == 1) out_row[0] = cur;
         WalkerDigest<MODE> dg;
-        dg.visit(p, cur);
+        dg.visit(cur, WalkerDigest<MODE>::MASKW > 0 ? p.code8[cur] : 0u);
         unsigned misses = 0;
         double u_even = 0.0, u_odd = 0.0;
 
@@ -113,12 +113,15 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const WalkParams p) 
                 found = group_min<G>(gmask, found);
                 if (found != 0xffffffffu) break;
             }
+            unsigned code = 0;
             if (found != 0xffffffffu) {
                 const EdgeRec e = load_edge(edge + off + found);
                 cur = e.col;
                 ri = RowInfo{e.off_units, e.len};
+                code = e.code;
             } else {
                 ++misses;
+                if constexpr (WalkerDigest<MODE>::MASKW > 0) code = p.code8[cur];
             }
             // ---- record column c = t + 1
             const int c = t + 1;
@@ -127,7 +130,7 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const WalkParams p) 
                 const int cbase = c & ~(G - 1);
                 if (cbase + gl <= c) out_row[cbase + gl] = mine;
             }
-            dg.visit(p, cur);
+            dg.visit(cur, code);
         }
         if (nt == 0 && G > 1 && gl == 0) out_row[0] = mine;
         if (gl == 0) {
@@ -265,15 +268,15 @@ extern "C" int cyp_walk(const cyp_graph *g, const int32_t *h_root_cells, int64_t
         return err == cudaSuccess;
     };
     unsigned long long miss = 0;
-    if (chk(cudaMalloc(&d_roots, sizeof(int32_t) * n_roots), "cudaMalloc roots") &&
-        chk(cudaMalloc(&d_seq, seq_bytes ? seq_bytes : 4), "cudaMalloc seq") &&
-        chk(cudaMalloc(&d_miss, sizeof(unsigned long long)), "cudaMalloc counter") &&
+    if (chk(dev_alloc(&d_roots, sizeof(int32_t) * n_roots), "cudaMalloc roots") &&
+        chk(dev_alloc(&d_seq, seq_bytes ? seq_bytes : 4), "cudaMalloc seq") &&
+        chk(dev_alloc(&d_miss, sizeof(unsigned long long)), "cudaMalloc counter") &&
         chk(cudaMemset(d_miss, 0, sizeof(unsigned long long)), "cudaMemset") &&
         chk(cudaMemcpy(d_roots, h_root_cells, sizeof(int32_t) * n_roots, cudaMemcpyHostToDevice), "H2D roots")) {
         bool ok = true;
         if (h_uniforms && n_walkers * n_transitions > 0) {
             const size_t ub = sizeof(double) * static_cast<size_t>(n_walkers) * n_transitions;
-            ok = chk(cudaMalloc(&d_u, ub), "cudaMalloc uniforms") && chk(cudaMemcpy(d_u, h_uniforms, ub, cudaMemcpyHostToDevice), "H2D uniforms");
+            ok = chk(dev_alloc(&d_u, ub), "cudaMalloc uniforms") && chk(cudaMemcpy(d_u, h_uniforms, ub, cudaMemcpyHostToDevice), "H2D uniforms");
         }
         if (ok) {
             rc = cyp_walk_device(g, d_roots, n_roots, sims_per_root, walker_begin, n_walkers, n_transitions, seed, round,
@@ -286,10 +289,10 @@ extern "C" int cyp_walk(const cyp_graph *g, const int32_t *h_root_cells, int64_t
         }
     }
     (void)e;
-    cudaFree(d_roots);
-    cudaFree(d_seq);
-    cudaFree(d_u);
-    cudaFree(d_miss);
+    dev_free(d_roots);
+    dev_free(d_seq);
+    dev_free(d_u);
+    dev_free(d_miss);
     if (n_nocrossing) *n_nocrossing = static_cast<int64_t>(miss);
     if (rc == CYP_OK && miss) return fail(CYP_E_NOCROSSING, "cyp_walk: a uniform exceeded its row's last CDF value (reference: IndexError at markov_chain_sampler.py:49)");
     return rc;

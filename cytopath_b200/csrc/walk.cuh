@@ -21,7 +21,8 @@ struct WalkParams {
     int64_t ld;                     // row stride of out_seq in elements (>= nt + 1)
     unsigned long long *nocross;    // may be nullptr
     // filter outputs, only read/written by the FILTER modes
-    const uint8_t *code8;           // [n_cells] code of the truncated cluster label (n_codes <= 256)
+    const uint8_t *code8;           // [n_cells] code of the truncated cluster label (n_codes <= 256); the step
+                                    // loop reads the same code from EdgeRec.code, this array serves the roots
     int32_t min_clusters;
     const int32_t *end_slot;        // [n_cells] end-point slot or -1
     int32_t *out_slot;              // [n_walkers]: -2 fails min_clusters, -1 not terminal, else end slot
@@ -48,7 +49,7 @@ __device__ __forceinline__ EdgeRec load_edge(const EdgeRec *p) {
     int4 v;
     asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];"
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    return EdgeRec{v.x, static_cast<uint32_t>(v.y), static_cast<uint32_t>(v.z), 0u};
+    return EdgeRec{v.x, static_cast<uint32_t>(v.y), static_cast<uint32_t>(v.z), static_cast<uint32_t>(v.w)};
 }
 
 __device__ __forceinline__ uint64_t mix64(uint64_t x) {      // murmur3 fmix64
@@ -69,14 +70,14 @@ struct WalkerDigest {
     uint64_t h1 = 0x9E3779B97F4A7C15ull, h2 = 0xD6E8FEB86659FD93ull;
     uint64_t cmask[MASKW > 0 ? MASKW : 1] = {0};
 
-    __device__ __forceinline__ void visit(const WalkParams &p, int32_t cell) {
+    // `code` = label code of `cell`: from the edge record for steps, from code8 for the root
+    __device__ __forceinline__ void visit(int32_t cell, unsigned code) {
         if constexpr (FILTER) {
             h1 = mix64(h1 ^ static_cast<uint32_t>(cell));
             h2 = (h2 + static_cast<uint32_t>(cell)) * 0x9FB21C651E98DF25ull;
             h2 ^= h2 >> 29;
         }
         if constexpr (MASKW > 0) {
-            const unsigned code = p.code8[cell];
 #pragma unroll
             for (int m = 0; m < MASKW; ++m)
                 if ((code >> 6) == static_cast<unsigned>(m)) cmask[m] |= 1ull << (code & 63);

@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(1024, 1) walk_tma_kernel(const WalkParams p, c
         int32_t b0 = cur, b1 = 0, b2 = 0, b3 = 0;         // columns 4q .. 4q+3 of the trajectory
         if (active && (nt == 0 || !vec_store)) out_row[0] = cur;
         WalkerDigest<MODE> dg;
-        if (active) dg.visit(p, cur);
+        if (active) dg.visit(cur, WalkerDigest<MODE>::MASKW > 0 ? p.code8[cur] : 0u);
         unsigned misses = 0;
         double u_even = 0.0, u_odd = 0.0;
 
@@ -133,12 +133,15 @@ __global__ void __launch_bounds__(1024, 1) walk_tma_kernel(const WalkParams p, c
                 }
             }
             if (active) {
+                unsigned code = 0;
                 if (found >= 0) {
                     const EdgeRec e = load_edge(edge + off + found);
                     cur = e.col;
                     ri = RowInfo{e.off_units, e.len};
+                    code = e.code;
                 } else {
                     ++misses;
+                    if constexpr (WalkerDigest<MODE>::MASKW > 0) code = p.code8[cur];
                 }
                 const int c = t + 1;
                 if (vec_store) {
@@ -154,7 +157,7 @@ __global__ void __launch_bounds__(1024, 1) walk_tma_kernel(const WalkParams p, c
                 } else {
                     out_row[c] = cur;
                 }
-                dg.visit(p, cur);
+                dg.visit(cur, code);
             }
         }
         if (active) {
