@@ -68,7 +68,7 @@ struct WalkerDigest {
     static constexpr int MASKW = (MODE == kModeFilter1) ? 1 : (MODE == kModeFilter4) ? 4 : 0;
     static constexpr bool FILTER = MODE != kModePlain;
     uint64_t h1 = 0x9E3779B97F4A7C15ull, h2 = 0xD6E8FEB86659FD93ull;
-    uint64_t cmask[MASKW > 0 ? MASKW : 1] = {0};
+    uint64_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;          // label bitmap words (scalars: no local-memory array)
 
     // `code` = label code of `cell`: from the edge record for steps, from code8 for the root
     __device__ __forceinline__ void visit(int32_t cell, unsigned code) {
@@ -78,17 +78,22 @@ struct WalkerDigest {
             h2 ^= h2 >> 29;
         }
         if constexpr (MASKW > 0) {
-#pragma unroll
-            for (int m = 0; m < MASKW; ++m)
-                if ((code >> 6) == static_cast<unsigned>(m)) cmask[m] |= 1ull << (code & 63);
+            const uint64_t bit = 1ull << (code & 63);
+            if constexpr (MASKW == 1) {
+                m0 |= bit;
+            } else {
+                const unsigned word = code >> 6;
+                m0 |= (word == 0) ? bit : 0ull;
+                m1 |= (word == 1) ? bit : 0ull;
+                m2 |= (word == 2) ? bit : 0ull;
+                m3 |= (word == 3) ? bit : 0ull;
+            }
         }
     }
     // one thread per walker calls this after the last step
     __device__ __forceinline__ void finish(const WalkParams &p, int64_t w, int32_t last_cell) const {
         if constexpr (FILTER) {
-            int distinct = 0;
-#pragma unroll
-            for (int m = 0; m < MASKW; ++m) distinct += __popcll(cmask[m]);
+            const int distinct = __popcll(m0) + __popcll(m1) + __popcll(m2) + __popcll(m3);
             const bool pass = (MASKW == 0) || distinct >= p.min_clusters;
             p.out_slot[w] = pass ? p.end_slot[last_cell] : -2;
             p.out_hash[2 * w] = h1;
@@ -105,7 +110,7 @@ WalkVariant pick_walk_variant(const cyp_graph *g, int variant);
 int launch_walk(const cyp_graph *g, const WalkParams &p, WalkMode mode, int variant, cudaStream_t stream);
 
 // K2, TMA flavour (walk_tma.cu): one walker per thread, rows staged in shared memory by
-// cp.async.bulk.  `variant` = 9000 + threads per CTA / 32 (e.g. 9016 = 512 threads).
+// cp.async.bulk.  `variant` = 9000 + threads per CTA / 32 (e.g. 9016 = 512 threads); 0 = auto.
 int launch_walk_tma(const cyp_graph *g, const WalkParams &p, WalkMode mode, int variant, cudaStream_t stream);
 const char *walk_tma_name(const cyp_graph *g, int variant);
 

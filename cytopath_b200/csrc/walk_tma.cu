@@ -167,6 +167,11 @@ __global__ void __launch_bounds__(1024, 1) walk_tma_kernel(const WalkParams p, c
     }
 }
 
+// Tried and dropped (profiles/r01_sweep4_pingpong_*.log): a ping-pong flavour with two walkers per
+// thread sharing one slot, so that one walker's row copy overlaps the other's edge-record load.
+// Same throughput as this kernel at equal thread counts (19.1 vs 19.0 G walker-steps/s at C4): the
+// memory system, not the per-thread dependency chain, is the limit at this point.
+
 struct TmaConfig {
     int threads;
     int slot_elems;
