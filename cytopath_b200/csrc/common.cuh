@@ -79,11 +79,14 @@ __device__ __forceinline__ void walker_uniform_pair(uint64_t seed, uint32_t roun
 }
 
 // ---- device-resident graph ----------------------------------------------------------
-// Rows are stored "sector aligned": every row starts on a 32-byte boundary of the CDF
-// array (4 doubles / 8 floats), so a row of k entries touches ceil(k*sizeof/32) sectors
-// and 16-byte vector loads are always legal.  col/val use the same element offsets.
+// Rows are stored aligned: every row starts at a multiple of kRowAlign = 16 elements in every
+// per-edge array (CDF float64/float32, 16-bit CDF codes, edge records, col, val), i.e. on a
+// 32-byte sector boundary even for the 2-byte codes.  A row of k entries touches
+// ceil(k*size/32) sectors, 16-byte vector loads are always legal, and a row is a legal
+// cp.async.bulk source.  One offset (in units of 16 elements) addresses all arrays.
+constexpr int kRowAlign = 16;
 struct RowInfo {          // read once per walker, for its root cell
-    uint32_t off_units;   // row start / align_elems
+    uint32_t off_units;   // row start / kRowAlign
     uint32_t len;         // entries in the row
 };
 // One 16-byte record per edge, at the same offset as the edge's CDF entry: the target cell AND
@@ -91,7 +94,7 @@ struct RowInfo {          // read once per walker, for its root cell
 // steps: a step is two dependent memory phases (CDF row -> edge record) instead of three.
 struct EdgeRec {
     int32_t col;          // target cell (-1 in padding)
-    uint32_t off_units;   // target's row start / align_elems
+    uint32_t off_units;   // target's row start / kRowAlign
     uint32_t len;         // target's row length
     uint32_t code;        // target's cluster-label code for the session that last labelled the graph
 };
@@ -106,10 +109,12 @@ struct cyp_graph {
     int64_t padded = 0;        // elements in the padded arrays
     int32_t max_len = 0;
     double mean_len = 0.0;
-    int align_elems = 4;       // 4 (float64 CDF) or 8 (float32 CDF): 32 bytes
+    int align_elems = cyp::kRowAlign;
+    int q16_ok = 0;            // the 16-bit CDF codes are usable (all CDF values in range, CDF non-decreasing)
     int monotone = 1;          // every probability >= 0, so each row's CDF is non-decreasing (binary search is exact)
     cyp::RowInfo *d_row = nullptr;   // [n]
     void *d_cdf = nullptr;           // float or double [padded]
+    uint16_t *d_q16 = nullptr;       // [padded] 16-bit CDF codes (see walk_tma.cu)
     int32_t *d_col = nullptr;        // [padded] column indices (transition scores look edges up here)
     cyp::EdgeRec *d_edge = nullptr;  // [padded] what the step kernel reads after the first-crossing search
     double *d_val = nullptr;         // [padded] raw probabilities (transition scores)

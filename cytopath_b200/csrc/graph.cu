@@ -60,12 +60,30 @@ __device__ __forceinline__ CdfT finish_cdf(double acc) {
     }
 }
 
+// 16-bit code of a CDF value (what walk_tma's q16 flavour searches):
+//   exact mode      q = min(65535, floor(c * 65536)); c is then known to lie in [q, q+1) / 65536
+//                   (or above 65535/65536), the kernel resolves the rare ambiguous compare in float64;
+//   reference mode  q = m, where the stored float32 value is exactly fl32(m / 1000) (:31): lossless.
+// Values outside the representable range clear bit 1 of the flag word (q16 unusable).
+template <typename CdfT>
+__device__ __forceinline__ uint16_t cdf_code(double acc, int *flags) {
+    if constexpr (sizeof(CdfT) == 8) {
+        if (!(acc >= 0.0)) { atomicOr(flags, 2); return 0; }
+        const double x = floor(acc * 65536.0);
+        return static_cast<uint16_t>(x > 65535.0 ? 65535.0 : x);
+    } else {
+        const float m = rintf(__fmul_rn(__double2float_rn(acc), 1000.0f));
+        if (!(m >= 0.0f && m <= 65535.0f)) { atomicOr(flags, 2); return 0; }
+        return static_cast<uint16_t>(m);
+    }
+}
+
 template <typename CdfT>
 __global__ void __launch_bounds__(kK1Threads)
 build_cdf_kernel(int64_t n, const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ raw_col,
                  const double *__restrict__ raw_val, const RowInfo *__restrict__ rows, int align_elems,
-                 int64_t total_units, CdfT *__restrict__ cdf, int32_t *__restrict__ col, EdgeRec *__restrict__ edge,
-                 double *__restrict__ val, int smem_elems, int *__restrict__ negative_flag) {
+                 int64_t total_units, CdfT *__restrict__ cdf, uint16_t *__restrict__ q16, int32_t *__restrict__ col,
+                 EdgeRec *__restrict__ edge, double *__restrict__ val, int smem_elems, int *__restrict__ negative_flag) {
     extern __shared__ double s_val[];                 // [smem_elems] raw values, then cumulative sums in place
     __shared__ int64_t s_src[kK1Threads + 1];         // CSR offsets of the CTA's rows
     __shared__ int64_t s_dst[kK1Threads + 1];         // padded offsets of the CTA's rows
@@ -111,11 +129,13 @@ build_cdf_kernel(int64_t n, const int64_t *__restrict__ row_ptr, const int32_t *
                 const int32_t c = raw_col[q];
                 const RowInfo tr = rows[c];
                 cdf[dst0 + p] = finish_cdf<CdfT>(s_val[q - src0]);
+                q16[dst0 + p] = cdf_code<CdfT>(s_val[q - src0], negative_flag);
                 col[dst0 + p] = c;
                 edge[dst0 + p] = EdgeRec{c, tr.off_units, tr.len, 0u};
                 val[dst0 + p] = raw_val[q];
             } else {                                   // padding never matches: u >= 0 > -1
                 cdf[dst0 + p] = static_cast<CdfT>(-1);
+                q16[dst0 + p] = 0;
                 col[dst0 + p] = -1;
                 edge[dst0 + p] = EdgeRec{-1, 0u, 0u, 0u};
                 val[dst0 + p] = 0.0;
@@ -133,12 +153,14 @@ build_cdf_kernel(int64_t n, const int64_t *__restrict__ row_ptr, const int32_t *
             const int32_t c = raw_col[a + j];
             const RowInfo tr = rows[c];
             cdf[dst + j] = finish_cdf<CdfT>(acc);
+            q16[dst + j] = cdf_code<CdfT>(acc, negative_flag);
             col[dst + j] = c;
             edge[dst + j] = EdgeRec{c, tr.off_units, tr.len, 0u};
             val[dst + j] = v;
         }
         for (int64_t j = len; j < len_pad; ++j) {
             cdf[dst + j] = static_cast<CdfT>(-1);
+            q16[dst + j] = 0;
             col[dst + j] = -1;
             edge[dst + j] = EdgeRec{-1, 0u, 0u, 0u};
             val[dst + j] = 0.0;
@@ -176,6 +198,7 @@ static void graph_free(cyp_graph *g) {
     DeviceGuard guard(g->device);
     dev_free(g->d_row);
     dev_free(g->d_cdf);
+    dev_free(g->d_q16);
     dev_free(g->d_col);
     dev_free(g->d_edge);
     dev_free(g->d_val);
@@ -202,7 +225,7 @@ extern "C" int cyp_graph_create(int device, int64_t n_cells, int64_t nnz, const 
     g->cdf_mode = cdf_mode;
     g->n = n_cells;
     g->nnz = nnz;
-    g->align_elems = (cdf_mode == CYP_CDF_EXACT) ? 4 : 8;
+    g->align_elems = kRowAlign;
     const int A = g->align_elems;
 
     // host: padded row offsets (O(n))
@@ -252,6 +275,7 @@ extern "C" int cyp_graph_create(int device, int64_t n_cells, int64_t nnz, const 
     G_CUDA(dev_alloc(&g->d_row, sizeof(RowInfo) * n_cells));
     G_CUDA(dev_alloc(&g->d_row_ptr, sizeof(int64_t) * (n_cells + 1)));
     G_CUDA(dev_alloc(&g->d_cdf, cdf_elem * g->padded));
+    G_CUDA(dev_alloc(&g->d_q16, sizeof(uint16_t) * g->padded));
     G_CUDA(dev_alloc(&g->d_col, sizeof(int32_t) * g->padded));
     G_CUDA(dev_alloc(&g->d_edge, sizeof(EdgeRec) * g->padded));
     G_CUDA(dev_alloc(&g->d_val, sizeof(double) * g->padded));
@@ -260,13 +284,14 @@ extern "C" int cyp_graph_create(int device, int64_t n_cells, int64_t nnz, const 
     G_CUDA(dev_alloc(&d_flag, sizeof(int)));
     G_CUDA(cudaMemset(d_flag, 0, sizeof(int)));
     g->device_bytes = sizeof(RowInfo) * n_cells + sizeof(int64_t) * (n_cells + 1) +
-                      (cdf_elem + sizeof(int32_t) + sizeof(EdgeRec) + sizeof(double)) * g->padded;
+                      (cdf_elem + sizeof(uint16_t) + sizeof(int32_t) + sizeof(EdgeRec) + sizeof(double)) * g->padded;
     G_CUDA(cudaMemcpy(g->d_row, rows.data(), sizeof(RowInfo) * n_cells, cudaMemcpyHostToDevice));
     G_CUDA(cudaMemcpy(g->d_row_ptr, h_row_ptr, sizeof(int64_t) * (n_cells + 1), cudaMemcpyHostToDevice));
     G_CUDA(cudaMemcpy(d_raw_col, h_col, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice));
     G_CUDA(cudaMemcpy(d_raw_val, h_val, sizeof(double) * nnz, cudaMemcpyHostToDevice));
     // slack region: never-matching padding
     G_CUDA(cudaMemset(static_cast<char *>(g->d_cdf) + cdf_elem * units * A, 0xFF, cdf_elem * 4 * A));   // NaN: u <= NaN is false
+    G_CUDA(cudaMemset(g->d_q16 + units * A, 0, sizeof(uint16_t) * 4 * A));
     G_CUDA(cudaMemset(g->d_col + units * A, 0xFF, sizeof(int32_t) * 4 * A));
     G_CUDA(cudaMemset(g->d_edge + units * A, 0, sizeof(EdgeRec) * 4 * A));
     G_CUDA(cudaMemset(g->d_val + units * A, 0, sizeof(double) * 4 * A));
@@ -280,13 +305,13 @@ extern "C" int cyp_graph_create(int device, int64_t n_cells, int64_t nnz, const 
     if (cdf_mode == CYP_CDF_EXACT) {
         G_CUDA(cudaFuncSetAttribute(build_cdf_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         build_cdf_kernel<double><<<grid, kK1Threads, smem_bytes>>>(n_cells, g->d_row_ptr, d_raw_col, d_raw_val, g->d_row, A,
-                                                                   units, static_cast<double *>(g->d_cdf), g->d_col,
-                                                                   g->d_edge, g->d_val, smem_elems, d_flag);
+                                                                   units, static_cast<double *>(g->d_cdf), g->d_q16,
+                                                                   g->d_col, g->d_edge, g->d_val, smem_elems, d_flag);
     } else {
         G_CUDA(cudaFuncSetAttribute(build_cdf_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         build_cdf_kernel<float><<<grid, kK1Threads, smem_bytes>>>(n_cells, g->d_row_ptr, d_raw_col, d_raw_val, g->d_row, A,
-                                                                  units, static_cast<float *>(g->d_cdf), g->d_col,
-                                                                  g->d_edge, g->d_val, smem_elems, d_flag);
+                                                                  units, static_cast<float *>(g->d_cdf), g->d_q16,
+                                                                  g->d_col, g->d_edge, g->d_val, smem_elems, d_flag);
     }
     G_CUDA(cudaGetLastError());
     G_CUDA(cudaEventRecord(e1));
@@ -294,7 +319,8 @@ extern "C" int cyp_graph_create(int device, int64_t n_cells, int64_t nnz, const 
     G_CUDA(cudaEventElapsedTime(&g->build_ms, e0, e1));
     int negative = 0;
     G_CUDA(cudaMemcpy(&negative, d_flag, sizeof(int), cudaMemcpyDeviceToHost));
-    g->monotone = negative ? 0 : 1;
+    g->monotone = (negative & 1) ? 0 : 1;
+    g->q16_ok = (negative == 0) ? 1 : 0;
     dev_free(d_flag);
     d_flag = nullptr;
     cudaEventDestroy(e0);

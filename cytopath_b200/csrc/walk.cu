@@ -52,7 +52,7 @@ template <typename CdfT, int G, int UNROLL, int MODE>
 __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const WalkParams p) {
     using V = Vec16<CdfT>;
     constexpr int VEC = V::n;
-    constexpr int ALIGN = 32 / sizeof(CdfT);
+    constexpr int ALIGN = kRowAlign;
     constexpr int CHUNK = G * VEC * UNROLL;
 
     const int lane = threadIdx.x & 31;

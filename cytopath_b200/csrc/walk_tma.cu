@@ -16,6 +16,7 @@
 // its row descriptor, so no separate descriptor lookup), one Philox call every second step and
 // a 16-byte trajectory store every fourth step.
 #include <cstdio>
+#include <type_traits>
 
 #include "walk.cuh"
 
@@ -54,14 +55,89 @@ __device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gmem_s
 
 }  // namespace
 
-template <typename CdfT, int MODE>
-__global__ void __launch_bounds__(1024, 1) walk_tma_kernel(const WalkParams p, const int slot_elems, const int monotone) {
-    constexpr int ALIGN = 32 / sizeof(CdfT);
+// ---- row formats ------------------------------------------------------------------------------
+// What is copied into the slot and how the first crossing `min j : u <= cdf[j]` (:49) is found.
+//   RowF64 / RowF32   the CDF itself (exact / reference mode): 8 or 4 bytes per entry.
+//   RowQ16Exact       16-bit codes q = floor(cdf * 65536) of the float64 CDF: 2 bytes per entry.
+//                     u <= q/65536 proves u <= cdf; u > (q+1)/65536 proves u > cdf; only entries
+//                     whose code equals floor(u*65536)-ish (probability ~ k / 65536 per step) are
+//                     ambiguous, and those are compared against the float64 value in HBM, so the
+//                     selected index is ALWAYS the one the float64 comparison selects.
+//   RowQ16Ref         reference mode: the stored float32 value is exactly fl32(m / 1000) with
+//                     integer m (np.round(decimals=3), :31), so the code m is lossless; u is mapped
+//                     to the smallest m with u <= fl32(m/1000) and the search is an integer compare.
+struct RowF64 {
+    using elem = double;
+    static constexpr const char *name = "f64";
+};
+struct RowF32 {
+    using elem = float;
+    static constexpr const char *name = "f32";
+};
+struct RowQ16Exact {
+    using elem = uint16_t;
+    static constexpr const char *name = "q16/f64";
+};
+struct RowQ16Ref {
+    using elem = uint16_t;
+    static constexpr const char *name = "q16/f32";
+};
+
+// first j in [0, m) with slot[j] >= key (slot non-decreasing); m if none
+__device__ __forceinline__ int lower_bound_u16(const uint16_t *slot, int m, int key) {
+    int lo = 0, hi = m;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (static_cast<int>(slot[mid]) >= key) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+// Returns the first index j in [0, m) of the chunk with u <= cdf[row_off + base + j], or -1.
+template <typename Row>
+__device__ __forceinline__ int first_crossing(const typename Row::elem *slot, int m, double u, int monotone,
+                                              const void *cdf_full, int64_t row_elem0) {
+    if constexpr (std::is_same<Row, RowQ16Exact>::value) {
+        const int t_def = static_cast<int>(ceil(u * 65536.0));       // q >= t_def      <=>  u <= q / 65536
+        int j = lower_bound_u16(slot, m, t_def - 1);                   // q >= t_def - 1  <=>  u <= (q + 1) / 65536
+        const double *exact = static_cast<const double *>(cdf_full) + row_elem0;
+        while (j < m && static_cast<int>(slot[j]) < t_def) {          // ambiguous entries: decide in float64
+            if (u <= __ldg(exact + j)) return j;
+            ++j;
+        }
+        return j < m ? j : -1;
+    } else if constexpr (std::is_same<Row, RowQ16Ref>::value) {
+        // smallest integer key with u <= (double)fl32(key / 1000)
+        int key = static_cast<int>(ceil(u * 1000.0));
+        while (key > 0 && u <= static_cast<double>(__fdiv_rn(static_cast<float>(key - 1), 1000.0f))) --key;
+        while (u > static_cast<double>(__fdiv_rn(static_cast<float>(key), 1000.0f))) ++key;
+        const int j = lower_bound_u16(slot, m, key);
+        return j < m ? j : -1;
+    } else {
+        if (monotone) {
+            int lo = 0, hi = m;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (u <= static_cast<double>(slot[mid])) hi = mid; else lo = mid + 1;
+            }
+            return lo < m ? lo : -1;
+        }
+        for (int j = 0; j < m; ++j)
+            if (u <= static_cast<double>(slot[j])) return j;
+        return -1;
+    }
+}
+
+template <typename Row, int MODE>
+__global__ void __launch_bounds__(1024, 1) walk_tma_kernel(const WalkParams p, const void *__restrict__ row_data,
+                                                           const int slot_elems, const int monotone) {
+    using Elem = typename Row::elem;
+    constexpr int COPY_ALIGN = 32 / sizeof(Elem);        // copies are whole 32-byte sectors
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nthreads = blockDim.x;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
-    CdfT *slot = reinterpret_cast<CdfT *>(smem_raw + (((nthreads >> 5) * 8 + 127) & ~127)) + static_cast<size_t>(threadIdx.x) * slot_elems;
+    Elem *slot = reinterpret_cast<Elem *>(smem_raw + (((nthreads >> 5) * 8 + 127) & ~127)) + static_cast<size_t>(threadIdx.x) * slot_elems;
     uint64_t *bar = bars + warp;
     if (lane == 0) mbar_init(bar, 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -69,7 +145,7 @@ __global__ void __launch_bounds__(1024, 1) walk_tma_kernel(const WalkParams p, c
     __syncthreads();
     uint32_t parity = 0;
 
-    const CdfT *__restrict__ cdf = static_cast<const CdfT *>(p.cdf);
+    const Elem *__restrict__ rowsrc = static_cast<const Elem *>(row_data);
     const EdgeRec *__restrict__ edge = p.edge;
     const RowInfo *__restrict__ rows = p.rows;
     const int nt = p.nt;
@@ -101,35 +177,25 @@ __global__ void __launch_bounds__(1024, 1) walk_tma_kernel(const WalkParams p, c
                 u = (t & 1) ? u_odd : u_even;
             }
             const int len = static_cast<int>(ri.len);
-            const int len_pad = (len + ALIGN - 1) & ~(ALIGN - 1);
-            const int64_t off = static_cast<int64_t>(ri.off_units) * ALIGN;
+            const int len_pad = (len + COPY_ALIGN - 1) & ~(COPY_ALIGN - 1);
+            const int64_t off = static_cast<int64_t>(ri.off_units) * kRowAlign;
             int found = -1;
             for (int base = 0;; base += slot_elems) {    // warp-uniform: all lanes take every barrier phase
                 const bool need = found < 0 && base < len;
                 if (!__any_sync(0xffffffffu, need)) break;
                 const int n = need ? min(len_pad - base, slot_elems) : 0;
                 if (n > 0) {
-                    const uint32_t bytes = static_cast<uint32_t>(n) * sizeof(CdfT);
+                    const uint32_t bytes = static_cast<uint32_t>(n) * sizeof(Elem);
                     mbar_arrive_expect_tx(bar, bytes);
-                    bulk_copy_g2s(slot, cdf + off + base, bytes, bar);
+                    bulk_copy_g2s(slot, rowsrc + off + base, bytes, bar);
                 } else {
                     mbar_arrive(bar);
                 }
                 mbar_wait(bar, parity);
                 parity ^= 1u;
                 if (n > 0) {
-                    const int m = min(n, len - base);
-                    if (monotone) {                      // first j with u <= slot[j]
-                        int lo = 0, hi = m;
-                        while (lo < hi) {
-                            const int mid = (lo + hi) >> 1;
-                            if (u <= static_cast<double>(slot[mid])) hi = mid; else lo = mid + 1;
-                        }
-                        if (lo < m) found = base + lo;
-                    } else {
-                        for (int j = 0; j < m; ++j)
-                            if (u <= static_cast<double>(slot[j])) { found = base + j; break; }
-                    }
+                    const int j = first_crossing<Row>(slot, min(n, len - base), u, monotone, p.cdf, off + base);
+                    if (j >= 0) found = base + j;
                 }
             }
             if (active) {
@@ -176,24 +242,27 @@ struct TmaConfig {
     int threads;
     int slot_elems;
     size_t smem;
+    bool q16;
 };
 
 // Launch shape.  Measured on B200 (profiles/r01_sweep*.log): throughput rises with the row bytes
 // in flight per SM; ~210 KB of slots (512 threads for 416-byte rows) is the best point for
-// HBM-bound graphs, and more than 768 threads per SM brings nothing.  Graphs that fit the L2 are
-// latency bound instead and take every thread that fits.
+// HBM-bound float64 rows and more than 768 threads brings nothing there; 2-byte rows and graphs
+// that fit the L2 are latency bound and take every thread that fits.
+// variant: 0 = auto; 9000 + T/32 = full-precision rows, T threads; 9200 + T/32 = 16-bit rows.
 static TmaConfig tma_config(const cyp_graph *g, int variant) {
-    const int elem = (g->cdf_mode == CYP_CDF_EXACT) ? 8 : 4;
+    const bool want_q16 = (variant == 0 || variant >= 9200) && g->q16_ok && g->monotone;
+    const int elem = want_q16 ? 2 : (g->cdf_mode == CYP_CDF_EXACT) ? 8 : 4;
     const int align = 32 / elem;
     const int max_pad = (g->max_len + align - 1) / align * align;
     const int mean_pad = (static_cast<int>(g->mean_len + 0.999) + align - 1) / align * align;
     const size_t hard_budget = 226 * 1024;
-    int threads = (variant > 9000) ? (variant - 9000) * 32 : 0;
+    int threads = (variant > 9200) ? (variant - 9200) * 32 : (variant > 9000 && variant < 9200) ? (variant - 9000) * 32 : 0;
     int slot = (max_pad <= 2 * mean_pad) ? max_pad : 2 * mean_pad;   // ragged graphs: long rows stream in chunks
     if (threads == 0) {
-        const bool l2_resident = static_cast<double>(g->padded) * (elem + 4) < 64.0 * 1024 * 1024;
-        const size_t budget = l2_resident ? hard_budget : 216 * 1024;
-        const int cap = l2_resident ? 1024 : 768;
+        const bool l2_resident = static_cast<double>(g->padded) * (elem + 16) < 64.0 * 1024 * 1024;
+        const size_t budget = (l2_resident || want_q16) ? hard_budget : 216 * 1024;
+        const int cap = (l2_resident || want_q16) ? 1024 : 768;
         threads = static_cast<int>(budget / (static_cast<size_t>(slot) * elem)) / 32 * 32;
         if (threads > cap) threads = cap;
         if (threads < 128) threads = 128;
@@ -205,12 +274,12 @@ static TmaConfig tma_config(const cyp_graph *g, int variant) {
     if (static_cast<size_t>(slot) > cap_elems) slot = static_cast<int>(cap_elems);
     if (slot < align) slot = align;
     const size_t smem = ((threads / 32 * 8 + 127) & ~127) + static_cast<size_t>(threads) * slot * elem;
-    return TmaConfig{threads, slot, smem};
+    return TmaConfig{threads, slot, smem, want_q16};
 }
 
-template <typename CdfT, int MODE>
+template <typename Row, int MODE>
 static int launch_tma_one(const cyp_graph *g, const WalkParams &p, const TmaConfig &c, cudaStream_t stream) {
-    auto kernel = walk_tma_kernel<CdfT, MODE>;
+    auto kernel = walk_tma_kernel<Row, MODE>;
     static int sm_count = 0;
     static size_t smem_set = 0;
     if (sm_count == 0) {
@@ -225,33 +294,37 @@ static int launch_tma_one(const cyp_graph *g, const WalkParams &p, const TmaConf
     const int64_t need = (p.n_walkers + c.threads - 1) / c.threads;
     const unsigned grid = static_cast<unsigned>(need < sm_count ? need : sm_count);     // one persistent CTA per SM
     if (grid == 0) return CYP_OK;
-    kernel<<<grid, c.threads, c.smem, stream>>>(p, c.slot_elems, g->monotone);
+    const void *row_data = std::is_same<typename Row::elem, uint16_t>::value ? static_cast<const void *>(g->d_q16) : g->d_cdf;
+    kernel<<<grid, c.threads, c.smem, stream>>>(p, row_data, c.slot_elems, g->monotone);
     CYP_CUDA(cudaGetLastError());
     return CYP_OK;
 }
 
-template <typename CdfT>
+template <typename Row>
 static int launch_tma_mode(const cyp_graph *g, const WalkParams &p, WalkMode mode, const TmaConfig &c, cudaStream_t stream) {
     switch (mode) {
-        case kModePlain: return launch_tma_one<CdfT, kModePlain>(g, p, c, stream);
-        case kModeFilter0: return launch_tma_one<CdfT, kModeFilter0>(g, p, c, stream);
-        case kModeFilter1: return launch_tma_one<CdfT, kModeFilter1>(g, p, c, stream);
-        case kModeFilter4: return launch_tma_one<CdfT, kModeFilter4>(g, p, c, stream);
+        case kModePlain: return launch_tma_one<Row, kModePlain>(g, p, c, stream);
+        case kModeFilter0: return launch_tma_one<Row, kModeFilter0>(g, p, c, stream);
+        case kModeFilter1: return launch_tma_one<Row, kModeFilter1>(g, p, c, stream);
+        case kModeFilter4: return launch_tma_one<Row, kModeFilter4>(g, p, c, stream);
     }
     return fail(CYP_E_INVALID, "launch_walk_tma: bad mode");
 }
 
 int launch_walk_tma(const cyp_graph *g, const WalkParams &p, WalkMode mode, int variant, cudaStream_t stream) {
     const TmaConfig c = tma_config(g, variant);
-    if (g->cdf_mode == CYP_CDF_EXACT) return launch_tma_mode<double>(g, p, mode, c, stream);
-    return launch_tma_mode<float>(g, p, mode, c, stream);
+    const bool exact = g->cdf_mode == CYP_CDF_EXACT;
+    if (c.q16) return exact ? launch_tma_mode<RowQ16Exact>(g, p, mode, c, stream) : launch_tma_mode<RowQ16Ref>(g, p, mode, c, stream);
+    return exact ? launch_tma_mode<RowF64>(g, p, mode, c, stream) : launch_tma_mode<RowF32>(g, p, mode, c, stream);
 }
 
 const char *walk_tma_name(const cyp_graph *g, int variant) {
     static thread_local char buf[128];
     const TmaConfig c = tma_config(g, variant);
-    snprintf(buf, sizeof(buf), "walk_tma_kernel<%s,threads=%d,slot=%d,%s>", g->cdf_mode == CYP_CDF_EXACT ? "f64" : "f32", c.threads,
-             c.slot_elems, g->monotone ? "bsearch" : "scan");
+    const bool exact = g->cdf_mode == CYP_CDF_EXACT;
+    const char *row = c.q16 ? (exact ? RowQ16Exact::name : RowQ16Ref::name) : (exact ? RowF64::name : RowF32::name);
+    snprintf(buf, sizeof(buf), "walk_tma_kernel<%s,threads=%d,slot=%d,%s>", row, c.threads, c.slot_elems,
+             g->monotone ? "bsearch" : "scan");
     return buf;
 }
 

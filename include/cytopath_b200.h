@@ -82,9 +82,11 @@ int cyp_walk(const cyp_graph *g, const int32_t *h_root_cells, int64_t n_roots, i
              int64_t walker_begin, int64_t n_walkers, int32_t n_transitions, uint64_t seed, uint32_t round,
              const double *h_uniforms, int32_t *h_out_seq, int64_t *n_nocrossing);
 /* Same, everything resident in HBM, enqueued on `stream`.  d_nocrossing (may be NULL) is
- * incremented atomically.  `variant` selects the step kernel: 0 = auto (TMA flavour, CTA size
- * from the row length), 9000 + T/32 = TMA flavour with T threads per CTA, L*100 + U = register
- * flavour with L lanes per walker and U 16-byte loads per lane per chunk. */
+ * incremented atomically.  `variant` selects the step kernel: 0 = auto (TMA flavour on 16-bit
+ * CDF codes when the graph allows it, CTA size from the row length), 9200 + T/32 = TMA flavour
+ * on 16-bit codes with T threads per CTA, 9000 + T/32 = TMA flavour on the CDF rows as stored,
+ * L*100 + U = register flavour with L lanes per walker and U 16-byte loads per lane per chunk.
+ * All flavours return identical sequences. */
 int cyp_walk_device(const cyp_graph *g, const int32_t *d_root_cells, int64_t n_roots, int64_t sims_per_root,
                     int64_t walker_begin, int64_t n_walkers, int32_t n_transitions, uint64_t seed,
                     uint32_t round, const double *d_uniforms, int32_t *d_out_seq,

@@ -119,7 +119,7 @@ def test_k2_bit_exact_vs_oracle_all_variants(gname, mode, omode):
             torch.cuda.synchronize()
             np.testing.assert_array_equal(out.cpu().numpy(), want, err_msg="lanes=%d unroll=%d" % (lanes, unroll))
     # TMA flavour: 128 / 256 / 512 / 1024 threads per CTA (1024 forces rows to stream through small slots)
-    for variant in (9004, 9008, 9016, 9032):
+    for variant in (9004, 9008, 9016, 9032, 9204, 9216, 9232):     # 90xx: CDF rows as stored; 92xx: 16-bit CDF codes
         for n_t in (nt, 62):                                  # 63 columns: scalar stores; 64 columns: int4 stores
             wnt = want if n_t == nt else cwalk.walk(C, cdf, np.repeat(roots, sims), n_t, seed=seed, round_idx=rnd, strict=False)
             out = torch.full((len(roots) * sims, n_t + 1), -7, dtype=torch.int32, device="cuda")
@@ -188,6 +188,49 @@ def test_k2_under_normalised_row_raises_like_the_reference():
     with pytest.raises(IndexError):
         cwalk.walk(C, cwalk.build_cdf(C, 0), np.array([0]), 2, uniforms=u)
     g.close()
+
+
+def test_k2_q16_ambiguous_codes_are_resolved_in_float64():
+    """Rows whose CDF values crowd into single 1/65536 buckets, and uniforms aimed exactly at and next to
+    those values: the 16-bit flavour must still return what the float64 comparison returns."""
+    from scipy import sparse
+    rng = np.random.default_rng(3)
+    n, k = 64, 40
+    rows, cols, vals = [], [], []
+    for i in range(n):
+        c = np.sort(rng.choice(n, size=k, replace=False))
+        v = np.full(k, 2.0 ** -20)                       # 16 consecutive entries share one 16-bit code
+        v[rng.choice(k, size=3, replace=False)] = rng.random(3) + 0.1
+        v = v / v.sum()
+        rows += [i] * k; cols += list(c); vals += list(v)
+    C = sp.canonical_csr(sparse.csr_matrix((vals, (rows, cols)), shape=(n, n)))
+    import ctypes
+    import torch
+    L = _lib.load()
+    for mode, omode in MODES:
+        g = _lib.Graph(C, mode)
+        assert "q16" in g.variant_name(0)
+        cdf = cwalk.build_cdf(C, omode)
+        cdf64 = cdf.astype(np.float64)
+        roots = np.arange(n)
+        nt = 24
+        # uniforms: exact CDF values of row 0..n-1 (ties), their neighbours, and plain random numbers
+        u = rng.random((n * 8, nt))
+        pool = np.concatenate([cdf64, np.nextafter(cdf64, 0), np.nextafter(cdf64, 2)])
+        pool = pool[(pool >= 0) & (pool < 1)]
+        mask = rng.random(u.shape) < 0.7
+        u[mask] = rng.choice(pool, size=int(mask.sum()))
+        want = cwalk.walk(C, cdf, np.repeat(roots, 8), nt, uniforms=u, strict=False)
+        d_roots = torch.tensor(roots, dtype=torch.int32, device="cuda")
+        d_u = torch.tensor(u, dtype=torch.float64, device="cuda")
+        for variant in (0, 9204, 9008, 404):
+            out = torch.zeros((n * 8, nt + 1), dtype=torch.int32, device="cuda")
+            miss = torch.zeros(1, dtype=torch.int64, device="cuda")
+            _lib.check(L.cyp_walk_device(g.handle, d_roots.data_ptr(), n, 8, 0, n * 8, nt, 0, 0, d_u.data_ptr(), out.data_ptr(),
+                                         miss.data_ptr(), variant, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            torch.cuda.synchronize()
+            np.testing.assert_array_equal(out.cpu().numpy(), want, err_msg=g.variant_name(variant))
+        g.close()
 
 
 def test_k2_single_step_and_zero_transitions():
