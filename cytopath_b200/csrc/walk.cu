@@ -19,6 +19,7 @@
 // Roofline: HBM.  Algorithmic bytes per walker-step = sizeof(cdf) * row_len + 8 + 4 + 4
 // (SURVEY.md 8d).  The kernel is latency/occupancy bound below that; see DESIGN.md.
 #include <cstdio>
+#include <cstdlib>
 
 #include "walk.cuh"
 

@@ -128,7 +128,20 @@ __device__ __forceinline__ int first_crossing(const typename Row::elem *slot, in
     }
 }
 
-template <typename Row, int MODE>
+// COPY selects how a warp's 32 rows reach the slots:
+//   kCopyBulk     every lane issues its own cp.async.bulk (UBLKCP).  ptxas serialises the 32 lanes of a
+//                 warp (the instruction takes uniform-register operands): ~10 issue slots per row,
+//                 independent of the row size.  Right for rows of several hundred bytes.
+//   kCopyCpAsync  the warp copies cooperatively with 16-byte cp.async (LDGSTS): slot_bytes/16 lanes per
+//                 row, so a 128-byte row of 16-bit codes costs one instruction per 4 rows.  Row
+//                 addresses travel by shuffle.  Right for small rows (<= 512 bytes per slot).
+constexpr int kCopyBulk = 0, kCopyCpAsync = 1;
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+
+template <typename Row, int MODE, int COPY>
 __global__ void __launch_bounds__(1024, 1) walk_tma_kernel(const WalkParams p, const void *__restrict__ row_data,
                                                            const int slot_elems, const int monotone) {
     using Elem = typename Row::elem;
@@ -139,11 +152,18 @@ __global__ void __launch_bounds__(1024, 1) walk_tma_kernel(const WalkParams p, c
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
     Elem *slot = reinterpret_cast<Elem *>(smem_raw + (((nthreads >> 5) * 8 + 127) & ~127)) + static_cast<size_t>(threadIdx.x) * slot_elems;
     uint64_t *bar = bars + warp;
-    if (lane == 0) mbar_init(bar, 32);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if constexpr (COPY == kCopyBulk) {
+        if (lane == 0) mbar_init(bar, 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     __syncthreads();
     uint32_t parity = 0;
+    // cooperative copy geometry: `cpr` 16-byte chunks per slot (a power of two <= 32)
+    constexpr int EPC = 16 / sizeof(Elem);               // elements per 16-byte chunk
+    const int cpr = slot_elems / EPC;
+    const int cpr_shift = 31 - __clz(cpr);
+    Elem *const warp_slots = slot - static_cast<size_t>(lane) * slot_elems;
 
     const Elem *__restrict__ rowsrc = static_cast<const Elem *>(row_data);
     const EdgeRec *__restrict__ edge = p.edge;
@@ -184,19 +204,38 @@ __global__ void __launch_bounds__(1024, 1) walk_tma_kernel(const WalkParams p, c
                 const bool need = found < 0 && base < len;
                 if (!__any_sync(0xffffffffu, need)) break;
                 const int n = need ? min(len_pad - base, slot_elems) : 0;
-                if (n > 0) {
-                    const uint32_t bytes = static_cast<uint32_t>(n) * sizeof(Elem);
-                    mbar_arrive_expect_tx(bar, bytes);
-                    bulk_copy_g2s(slot, rowsrc + off + base, bytes, bar);
+                if constexpr (COPY == kCopyBulk) {
+                    if (n > 0) {
+                        const uint32_t bytes = static_cast<uint32_t>(n) * sizeof(Elem);
+                        mbar_arrive_expect_tx(bar, bytes);
+                        bulk_copy_g2s(slot, rowsrc + off + base, bytes, bar);
+                    } else {
+                        mbar_arrive(bar);
+                    }
+                    mbar_wait(bar, parity);
+                    parity ^= 1u;
                 } else {
-                    mbar_arrive(bar);
+                    const int my_chunk = lane & (cpr - 1);
+                    const unsigned my_units = ri.off_units;
+                    for (int i = 0; i < cpr; ++i) {          // instruction i serves walkers i*(32/cpr) .. of the warp
+                        const int src_lane = ((i << 5) >> cpr_shift) + (lane >> cpr_shift);
+                        const unsigned units = __shfl_sync(0xffffffffu, my_units, src_lane);
+                        const int n_w = __shfl_sync(0xffffffffu, n, src_lane);
+                        if (my_chunk * EPC < n_w) {
+                            Elem *dst = warp_slots + static_cast<size_t>(src_lane) * slot_elems + my_chunk * EPC;
+                            const Elem *src = rowsrc + static_cast<int64_t>(units) * kRowAlign + base + my_chunk * EPC;
+                            cp_async16(dst, src);
+                        }
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    __syncwarp();
                 }
-                mbar_wait(bar, parity);
-                parity ^= 1u;
                 if (n > 0) {
                     const int j = first_crossing<Row>(slot, min(n, len - base), u, monotone, p.cdf, off + base);
                     if (j >= 0) found = base + j;
                 }
+                if constexpr (COPY == kCopyCpAsync) __syncwarp();   // other lanes write this slot in the next copy
             }
             if (active) {
                 unsigned code = 0;
@@ -233,7 +272,11 @@ __global__ void __launch_bounds__(1024, 1) walk_tma_kernel(const WalkParams p, c
     }
 }
 
-// Tried and dropped (profiles/r01_sweep4_pingpong_*.log): a ping-pong flavour with two walkers per
+// Tried and dropped: (1) L2 eviction-priority hints (rows evict_last, edge records and trajectory
+// stores evict_first through createpolicy descriptors): identical timings on every workload;
+// (2) two CTAs of 768 threads per SM for the cp.async flavour (needs <= 42 registers): slower than
+// one CTA of 1024 threads (29.9 vs 32.9 G walker-steps/s at C4);
+// (3) (profiles/r01_sweep4_pingpong_*.log) a ping-pong flavour with two walkers per
 // thread sharing one slot, so that one walker's row copy overlaps the other's edge-record load.
 // Same throughput as this kernel at equal thread counts (19.1 vs 19.0 G walker-steps/s at C4): the
 // memory system, not the per-thread dependency chain, is the limit at this point.
@@ -243,15 +286,19 @@ struct TmaConfig {
     int slot_elems;
     size_t smem;
     bool q16;
+    bool cpasync;         // cooperative 16-byte cp.async copies instead of per-lane bulk copies
 };
 
 // Launch shape.  Measured on B200 (profiles/r01_sweep*.log): throughput rises with the row bytes
 // in flight per SM; ~210 KB of slots (512 threads for 416-byte rows) is the best point for
 // HBM-bound float64 rows and more than 768 threads brings nothing there; 2-byte rows and graphs
 // that fit the L2 are latency bound and take every thread that fits.
-// variant: 0 = auto; 9000 + T/32 = full-precision rows, T threads; 9200 + T/32 = 16-bit rows.
+// variant: 0 = auto; 9000 + T/32 = CDF rows as stored, bulk copies, T threads; 9200 + T/32 = 16-bit
+// codes, bulk copies; 9300 + T/32 = 16-bit codes, cooperative cp.async copies.
 static TmaConfig tma_config(const cyp_graph *g, int variant) {
     const bool want_q16 = (variant == 0 || variant >= 9200) && g->q16_ok && g->monotone;
+    bool cpasync = want_q16 && (variant == 0 || variant >= 9300);
+    if (variant >= 9300) variant -= 100;
     const int elem = want_q16 ? 2 : (g->cdf_mode == CYP_CDF_EXACT) ? 8 : 4;
     const int align = 32 / elem;
     const int max_pad = (g->max_len + align - 1) / align * align;
@@ -273,13 +320,21 @@ static TmaConfig tma_config(const cyp_graph *g, int variant) {
     cap_elems = cap_elems / align * align;
     if (static_cast<size_t>(slot) > cap_elems) slot = static_cast<int>(cap_elems);
     if (slot < align) slot = align;
+    if (cpasync) {                                     // slot = power-of-two number of 16-byte chunks, at most 32
+        int bytes = 16;
+        while (bytes < slot * elem && bytes < 512) bytes <<= 1;
+        const bool fits = static_cast<size_t>(bytes) * threads + 1024 <= hard_budget && bytes >= slot * elem;
+        const bool small = bytes <= 256 || variant != 0;             // auto: bulk copies win for slots above 256 bytes (C5)
+        if (fits && small) slot = bytes / elem;
+        else cpasync = false;
+    }
     const size_t smem = ((threads / 32 * 8 + 127) & ~127) + static_cast<size_t>(threads) * slot * elem;
-    return TmaConfig{threads, slot, smem, want_q16};
+    return TmaConfig{threads, slot, smem, want_q16, cpasync};
 }
 
-template <typename Row, int MODE>
+template <typename Row, int MODE, int COPY>
 static int launch_tma_one(const cyp_graph *g, const WalkParams &p, const TmaConfig &c, cudaStream_t stream) {
-    auto kernel = walk_tma_kernel<Row, MODE>;
+    auto kernel = walk_tma_kernel<Row, MODE, COPY>;
     static int sm_count = 0;
     static size_t smem_set = 0;
     if (sm_count == 0) {
@@ -291,8 +346,12 @@ static int launch_tma_one(const cyp_graph *g, const WalkParams &p, const TmaConf
         CYP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c.smem)));
         smem_set = c.smem;
     }
+    int ctas_per_sm = 1;
+    CYP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, c.threads, c.smem));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
     const int64_t need = (p.n_walkers + c.threads - 1) / c.threads;
-    const unsigned grid = static_cast<unsigned>(need < sm_count ? need : sm_count);     // one persistent CTA per SM
+    const int64_t resident = static_cast<int64_t>(sm_count) * ctas_per_sm;                // persistent CTAs, grid-stride over walkers
+    const unsigned grid = static_cast<unsigned>(need < resident ? need : resident);
     if (grid == 0) return CYP_OK;
     const void *row_data = std::is_same<typename Row::elem, uint16_t>::value ? static_cast<const void *>(g->d_q16) : g->d_cdf;
     kernel<<<grid, c.threads, c.smem, stream>>>(p, row_data, c.slot_elems, g->monotone);
@@ -300,13 +359,13 @@ static int launch_tma_one(const cyp_graph *g, const WalkParams &p, const TmaConf
     return CYP_OK;
 }
 
-template <typename Row>
+template <typename Row, int COPY>
 static int launch_tma_mode(const cyp_graph *g, const WalkParams &p, WalkMode mode, const TmaConfig &c, cudaStream_t stream) {
     switch (mode) {
-        case kModePlain: return launch_tma_one<Row, kModePlain>(g, p, c, stream);
-        case kModeFilter0: return launch_tma_one<Row, kModeFilter0>(g, p, c, stream);
-        case kModeFilter1: return launch_tma_one<Row, kModeFilter1>(g, p, c, stream);
-        case kModeFilter4: return launch_tma_one<Row, kModeFilter4>(g, p, c, stream);
+        case kModePlain: return launch_tma_one<Row, kModePlain, COPY>(g, p, c, stream);
+        case kModeFilter0: return launch_tma_one<Row, kModeFilter0, COPY>(g, p, c, stream);
+        case kModeFilter1: return launch_tma_one<Row, kModeFilter1, COPY>(g, p, c, stream);
+        case kModeFilter4: return launch_tma_one<Row, kModeFilter4, COPY>(g, p, c, stream);
     }
     return fail(CYP_E_INVALID, "launch_walk_tma: bad mode");
 }
@@ -314,8 +373,13 @@ static int launch_tma_mode(const cyp_graph *g, const WalkParams &p, WalkMode mod
 int launch_walk_tma(const cyp_graph *g, const WalkParams &p, WalkMode mode, int variant, cudaStream_t stream) {
     const TmaConfig c = tma_config(g, variant);
     const bool exact = g->cdf_mode == CYP_CDF_EXACT;
-    if (c.q16) return exact ? launch_tma_mode<RowQ16Exact>(g, p, mode, c, stream) : launch_tma_mode<RowQ16Ref>(g, p, mode, c, stream);
-    return exact ? launch_tma_mode<RowF64>(g, p, mode, c, stream) : launch_tma_mode<RowF32>(g, p, mode, c, stream);
+    if (c.q16 && c.cpasync)
+        return exact ? launch_tma_mode<RowQ16Exact, kCopyCpAsync>(g, p, mode, c, stream)
+                     : launch_tma_mode<RowQ16Ref, kCopyCpAsync>(g, p, mode, c, stream);
+    if (c.q16)
+        return exact ? launch_tma_mode<RowQ16Exact, kCopyBulk>(g, p, mode, c, stream)
+                     : launch_tma_mode<RowQ16Ref, kCopyBulk>(g, p, mode, c, stream);
+    return exact ? launch_tma_mode<RowF64, kCopyBulk>(g, p, mode, c, stream) : launch_tma_mode<RowF32, kCopyBulk>(g, p, mode, c, stream);
 }
 
 const char *walk_tma_name(const cyp_graph *g, int variant) {
@@ -323,8 +387,8 @@ const char *walk_tma_name(const cyp_graph *g, int variant) {
     const TmaConfig c = tma_config(g, variant);
     const bool exact = g->cdf_mode == CYP_CDF_EXACT;
     const char *row = c.q16 ? (exact ? RowQ16Exact::name : RowQ16Ref::name) : (exact ? RowF64::name : RowF32::name);
-    snprintf(buf, sizeof(buf), "walk_tma_kernel<%s,threads=%d,slot=%d,%s>", row, c.threads, c.slot_elems,
-             g->monotone ? "bsearch" : "scan");
+    snprintf(buf, sizeof(buf), "walk_tma_kernel<%s,%s,threads=%d,slot=%d,%s>", row, c.cpasync ? "cp.async" : "bulk", c.threads,
+             c.slot_elems, g->monotone ? "bsearch" : "scan");
     return buf;
 }
 

@@ -119,7 +119,7 @@ def test_k2_bit_exact_vs_oracle_all_variants(gname, mode, omode):
             torch.cuda.synchronize()
             np.testing.assert_array_equal(out.cpu().numpy(), want, err_msg="lanes=%d unroll=%d" % (lanes, unroll))
     # TMA flavour: 128 / 256 / 512 / 1024 threads per CTA (1024 forces rows to stream through small slots)
-    for variant in (9004, 9008, 9016, 9032, 9204, 9216, 9232):     # 90xx: CDF rows as stored; 92xx: 16-bit CDF codes
+    for variant in (9004, 9008, 9016, 9032, 9204, 9216, 9232, 9304, 9316, 9332):     # 90xx: CDF rows as stored; 92xx: 16-bit CDF codes
         for n_t in (nt, 62):                                  # 63 columns: scalar stores; 64 columns: int4 stores
             wnt = want if n_t == nt else cwalk.walk(C, cdf, np.repeat(roots, sims), n_t, seed=seed, round_idx=rnd, strict=False)
             out = torch.full((len(roots) * sims, n_t + 1), -7, dtype=torch.int32, device="cuda")
@@ -223,7 +223,7 @@ def test_k2_q16_ambiguous_codes_are_resolved_in_float64():
         want = cwalk.walk(C, cdf, np.repeat(roots, 8), nt, uniforms=u, strict=False)
         d_roots = torch.tensor(roots, dtype=torch.int32, device="cuda")
         d_u = torch.tensor(u, dtype=torch.float64, device="cuda")
-        for variant in (0, 9204, 9008, 404):
+        for variant in (0, 9204, 9304, 9008, 404):
             out = torch.zeros((n * 8, nt + 1), dtype=torch.int32, device="cuda")
             miss = torch.zeros(1, dtype=torch.int64, device="cuda")
             _lib.check(L.cyp_walk_device(g.handle, d_roots.data_ptr(), n, 8, 0, n * 8, nt, 0, 0, d_u.data_ptr(), out.data_ptr(),
