@@ -264,6 +264,15 @@ def run_b200(args, w):
     else:
         peak, peak_src = 6650.0, "fallback of B200_PROFILING.md"
     achieved = W * nt * bytes_per_step / (ms_launch * 1e-3) / 1e9
+    # bytes the default kernel actually requests per walker-step (sector granular): the staged row + one edge-record sector + the store
+    row_elem = 2 if "q16" in kernel_name else elem
+    layout_bytes = np.ceil(row_elem * kbar / 32.0) * 32.0 + 32.0 + 4.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        rec = json.load(open(tpath)).get("%s|%s" % (args.workload, kernel_name))
+        if rec and W == w["walkers"]:
+            traffic = rec["dram_bytes_read"] + rec["dram_bytes_write"]
     assert int(d_miss.item()) == 0, "walkers hit rows without a CDF crossing"
 
     if args.kernel_only:
@@ -352,8 +361,13 @@ def run_b200(args, w):
                 "what": "cyp_graph_create(pinned host CSR)+K1, cyp_session_round (K2+K3), fetch kept index + %d rows" % n_fetch},
         "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "bytes_per_walker_step": bytes_per_step,
-                     "mean_visited_row_nnz": kbar, "ms_per_launch": ms_launch},
+                     "traffic": traffic, "peak_source": peak_src, "bytes_per_walker_step": bytes_per_step,
+                     "mean_visited_row_nnz": kbar, "ms_per_launch": ms_launch,
+                     "layout_bytes_per_walker_step": layout_bytes,
+                     "layout_achieved": W * nt * layout_bytes / (ms_launch * 1e-3) / 1e9,
+                     "note": "achieved uses SURVEY 8d's algorithmic bytes (full float64/float32 CDF row + 16 B); the default kernel "
+                             "stages 2-byte CDF codes (exact by construction, DESIGN.md 5), so it requests layout_bytes per step "
+                             "and frac can exceed 1; traffic = dram read+write bytes of one launch from the committed ncu capture"},
     }
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu, cpu_c = cpu_baseline_sample(C, g, roots, max_steps, 1 if mode == _lib.CDF_EXACT else 0)
