@@ -10,6 +10,7 @@ The compute lives in a CUDA C-ABI library (include/cytopath_b200.h); there is no
 fallback: without the library or a CUDA device, `sampling` raises.
 """
 from .sampler import check_convergence_criteria, iterate_state_probability, sampling
+from .undirected import undirected_simulations
 
 __version__ = "0.1.0"
-__all__ = ["sampling", "iterate_state_probability", "check_convergence_criteria", "__version__"]
+__all__ = ["sampling", "undirected_simulations", "iterate_state_probability", "check_convergence_criteria", "__version__"]

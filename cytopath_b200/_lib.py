@@ -21,7 +21,7 @@ E_NOCROSSING = -4
 EXPORTS = [
     "cyp_version", "cyp_last_error", "cyp_device_count",
     "cyp_graph_create", "cyp_graph_destroy", "cyp_graph_info", "cyp_graph_fetch_cdf", "cyp_graph_build_ms",
-    "cyp_walk", "cyp_walk_device", "cyp_walk_variant_name", "cyp_transition_scores",
+    "cyp_power_iteration", "cyp_walk", "cyp_walk_device", "cyp_walk_variant_name", "cyp_transition_scores",
     "cyp_session_create", "cyp_session_destroy", "cyp_session_round", "cyp_session_rows",
     "cyp_session_fetch_index", "cyp_session_fetch_rows", "cyp_session_round_records",
     "cyp_session_round_prune", "cyp_session_set_hash_bits",
@@ -70,6 +70,7 @@ def load():
     L.cyp_graph_info.argtypes = [vp, P(i64), P(i64), P(i32), P(ci), P(ci), P(i64)]
     L.cyp_graph_fetch_cdf.argtypes = [vp, vp]
     L.cyp_graph_build_ms.argtypes = [vp, P(ctypes.c_float)]
+    L.cyp_power_iteration.argtypes = [ci, i64, i64, vp, vp, vp, vp, vp, i32, vp, vp]
     L.cyp_walk.argtypes = [vp, vp, i64, i64, i64, i64, i32, u64, u32, vp, vp, P(i64)]
     L.cyp_walk_device.argtypes = [vp, vp, i64, i64, i64, i64, i32, u64, u32, vp, vp, vp, ci, vp]
     L.cyp_walk_variant_name.argtypes = [vp, ci]
@@ -121,6 +122,26 @@ def ptr(a):
         assert a.flags["C_CONTIGUOUS"]
         return a.ctypes.data_as(ctypes.c_void_p)
     return ctypes.c_void_p(int(a))          # raw address (e.g. torch.Tensor.data_ptr())
+
+
+def power_iteration(T, init, stationary, max_iter: int, device: int = 0, return_state: bool = False):
+    """eps history of iterate_state_probability (markov_chain_sampler.py:62-87) computed on the GPU (K4).
+    T: scipy sparse or dense n x n matrix as stored in adata.uns[matrix_key] (not normalised, like :73)."""
+    from scipy import sparse
+    require_device(device)
+    M = sparse.csc_matrix(T)
+    M.sort_indices()
+    n = M.shape[0]
+    col_ptr = np.ascontiguousarray(M.indptr, dtype=np.int64)
+    row_idx = np.ascontiguousarray(M.indices, dtype=np.int32)
+    val = np.ascontiguousarray(M.data, dtype=np.float64)
+    init = np.ascontiguousarray(init, dtype=np.float64)
+    stationary = np.ascontiguousarray(stationary, dtype=np.float64)
+    eps = np.empty(max_iter, dtype=np.float64)
+    state = np.empty(n, dtype=np.float64) if return_state else None
+    check(load().cyp_power_iteration(device, n, val.shape[0], ptr(col_ptr), ptr(row_idx), ptr(val), ptr(init),
+                                     ptr(stationary), max_iter, ptr(eps), ptr(state)))
+    return (eps, state) if return_state else eps
 
 
 class Graph:

@@ -1,0 +1,118 @@
+// a5: iterate_state_probability (reference cytopath/markov_chain_sampler.py:62-87) on the device.
+//
+// K4: p <- p @ T repeated max_iter times, recording eps_i = cosine distance(p_i, stationary) (:73-76).
+// The matrix arrives as CSC (columns of T), so that output j is the dot product of p with column j,
+// accumulated strictly in increasing row order with separate multiply and add: the same order and
+// rounding as scipy's csc_matvec, which is what `ndarray @ csr_matrix` (:73) runs.  The three dot
+// products of the cosine are reduced in a fixed order (per-block partials, then one block), so the
+// result is deterministic; they differ from BLAS' association by O(1e-16), which only matters if a
+// |difference of eps| lands within that distance of `tol` (:55-58).  The host derives max_steps from
+// the eps history exactly like check_convergence_criteria (:54-60).
+#include <vector>
+
+#include "common.cuh"
+
+namespace cyp {
+
+constexpr int kPiThreads = 256;
+
+__global__ void __launch_bounds__(kPiThreads)
+spmv_t_kernel(int64_t n, const int64_t *__restrict__ col_ptr, const int32_t *__restrict__ row_idx,
+              const double *__restrict__ val, const double *__restrict__ p, double *__restrict__ p_new) {
+    const int64_t j = static_cast<int64_t>(blockIdx.x) * kPiThreads + threadIdx.x;
+    if (j >= n) return;
+    double acc = 0.0;
+    for (int64_t e = col_ptr[j]; e < col_ptr[j + 1]; ++e) acc = __dadd_rn(acc, __dmul_rn(val[e], p[row_idx[e]]));
+    p_new[j] = acc;
+}
+
+// partial[b] = {sum p*s, sum p*p, sum s*s} over the block's slice
+__global__ void __launch_bounds__(kPiThreads)
+dots_partial_kernel(int64_t n, const double *__restrict__ p, const double *__restrict__ s, double *__restrict__ partial) {
+    __shared__ double sh[3][kPiThreads];
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * kPiThreads + threadIdx.x;
+    const double a = (i < n) ? p[i] : 0.0, b = (i < n) ? s[i] : 0.0;
+    sh[0][threadIdx.x] = a * b;
+    sh[1][threadIdx.x] = a * a;
+    sh[2][threadIdx.x] = b * b;
+    __syncthreads();
+    for (int d = kPiThreads / 2; d > 0; d >>= 1) {
+        if (threadIdx.x < d)
+            for (int k = 0; k < 3; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + d];
+        __syncthreads();
+    }
+    if (threadIdx.x < 3) partial[3 * static_cast<int64_t>(blockIdx.x) + threadIdx.x] = sh[threadIdx.x][0];
+}
+
+// one block: fixed-order sum of the partials, eps = 1 - uv / sqrt(uu * vv), clipped to [0, 2] like scipy
+__global__ void __launch_bounds__(kPiThreads)
+dots_final_kernel(int64_t n_blocks, const double *__restrict__ partial, double *__restrict__ eps_out) {
+    __shared__ double sh[3][kPiThreads];
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (int64_t b = threadIdx.x; b < n_blocks; b += kPiThreads)
+        for (int k = 0; k < 3; ++k) acc[k] += partial[3 * b + k];
+    for (int k = 0; k < 3; ++k) sh[k][threadIdx.x] = acc[k];
+    __syncthreads();
+    for (int d = kPiThreads / 2; d > 0; d >>= 1) {
+        if (threadIdx.x < d)
+            for (int k = 0; k < 3; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + d];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double dist = 1.0 - sh[0][0] / sqrt(sh[1][0] * sh[2][0]);
+        dist = fmin(fmax(dist, 0.0), 2.0);
+        *eps_out = dist;
+    }
+}
+
+}  // namespace cyp
+
+using namespace cyp;
+
+extern "C" int cyp_power_iteration(int device, int64_t n_cells, int64_t nnz, const int64_t *h_col_ptr,
+                                   const int32_t *h_row_idx, const double *h_val, const double *h_init,
+                                   const double *h_stationary, int32_t max_iter, double *h_eps_history,
+                                   double *h_final_state) {
+    CYP_REQUIRE(h_col_ptr && h_row_idx && h_val && h_init && h_stationary && h_eps_history, "cyp_power_iteration: NULL argument");
+    CYP_REQUIRE(n_cells > 0 && nnz >= 0 && max_iter >= 0, "cyp_power_iteration: bad sizes");
+    CYP_REQUIRE(h_col_ptr[0] == 0 && h_col_ptr[n_cells] == nnz, "cyp_power_iteration: col_ptr does not span nnz");
+    int ndev = 0;
+    CYP_CUDA(cudaGetDeviceCount(&ndev));
+    CYP_REQUIRE(device >= 0 && device < ndev, "cyp_power_iteration: no such CUDA device");
+    DeviceGuard guard(device);
+    int64_t *d_ptr = nullptr;
+    int32_t *d_idx = nullptr;
+    double *d_val = nullptr, *d_p = nullptr, *d_q = nullptr, *d_s = nullptr, *d_partial = nullptr, *d_eps = nullptr;
+    const unsigned blocks = static_cast<unsigned>((n_cells + kPiThreads - 1) / kPiThreads);
+    cudaError_t e = dev_alloc(&d_ptr, sizeof(int64_t) * (n_cells + 1));
+    auto step = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    step(dev_alloc(&d_idx, sizeof(int32_t) * nnz));
+    step(dev_alloc(&d_val, sizeof(double) * nnz));
+    step(dev_alloc(&d_p, sizeof(double) * n_cells));
+    step(dev_alloc(&d_q, sizeof(double) * n_cells));
+    step(dev_alloc(&d_s, sizeof(double) * n_cells));
+    step(dev_alloc(&d_partial, sizeof(double) * 3 * blocks));
+    step(dev_alloc(&d_eps, sizeof(double) * (max_iter > 0 ? max_iter : 1)));
+    if (e == cudaSuccess) {
+        step(cudaMemcpy(d_ptr, h_col_ptr, sizeof(int64_t) * (n_cells + 1), cudaMemcpyHostToDevice));
+        step(cudaMemcpy(d_idx, h_row_idx, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice));
+        step(cudaMemcpy(d_val, h_val, sizeof(double) * nnz, cudaMemcpyHostToDevice));
+        step(cudaMemcpy(d_p, h_init, sizeof(double) * n_cells, cudaMemcpyHostToDevice));
+        step(cudaMemcpy(d_s, h_stationary, sizeof(double) * n_cells, cudaMemcpyHostToDevice));
+    }
+    if (e == cudaSuccess) {
+        for (int32_t i = 0; i < max_iter; ++i) {
+            spmv_t_kernel<<<blocks, kPiThreads>>>(n_cells, d_ptr, d_idx, d_val, d_p, d_q);
+            dots_partial_kernel<<<blocks, kPiThreads>>>(n_cells, d_q, d_s, d_partial);
+            dots_final_kernel<<<1, kPiThreads>>>(blocks, d_partial, d_eps + i);
+            double *t = d_p; d_p = d_q; d_q = t;
+        }
+        step(cudaGetLastError());
+        if (max_iter > 0) step(cudaMemcpy(h_eps_history, d_eps, sizeof(double) * max_iter, cudaMemcpyDeviceToHost));
+        if (h_final_state) step(cudaMemcpy(h_final_state, d_p, sizeof(double) * n_cells, cudaMemcpyDeviceToHost));
+    }
+    dev_free(d_ptr); dev_free(d_idx); dev_free(d_val); dev_free(d_p); dev_free(d_q); dev_free(d_s); dev_free(d_partial); dev_free(d_eps);
+    if (e != cudaSuccess)
+        return fail(e == cudaErrorMemoryAllocation ? CYP_E_NOMEM : CYP_E_CUDA, std::string("cyp_power_iteration: ") + cudaGetErrorString(e));
+    return CYP_OK;
+}

@@ -5,7 +5,7 @@ the reference; the work is done by the CUDA library (cytopath_b200/csrc) through
 
   a7  validation / argument resolution (:148-262)      host, this file (no densification)
   a1  matrix_prep (:11-31)                              K1  cyp_graph_create
-  a5  auto max_steps (:62-87, :265-279)                 host scipy SpMV^T (tiny)
+  a5  auto max_steps (:62-87, :265-279)                 K4  cyp_power_iteration (SpMV^T + cosine on the device)
   a2  markov_sim (:35-52)                               K2  inside cyp_session_round
   a3  min_clusters / terminal / unique filters (:322-354)  K3  inside cyp_session_round
   a6  joblib fan-out over root cells (:306-319)         walkers sharded by id over ranks/GPUs
@@ -65,14 +65,19 @@ def iterate_state_probability(adata, matrix_key="T_forward", init=None, stationa
     return history[:converged], history, converged
 
 
-def _auto_max_steps(T, init, stationary, max_iter, tol):
+def _auto_max_steps(T, init, stationary, max_iter, tol, backend=None, device=0):
     """The only thing `sampling` keeps from iterate_state_probability is its last element
-    (:275-278); this avoids the [max_iter, n] history buffer (1.6 GB at 1M cells)."""
-    eps_history = np.empty(max_iter)
-    p = np.asarray(init, dtype=np.float64)
-    for i in range(max_iter):
-        p = p @ T
-        eps_history[i] = cosine(p, stationary)
+    (:275-278): max_steps.  The power iteration runs on the GPU (K4, cyp_power_iteration) without
+    the [max_iter, n] history buffer (1.6 GB at 1M cells); test backends without a device run the
+    reference's scipy expression."""
+    if backend is not None and hasattr(backend, "power_iteration"):
+        eps_history = backend.power_iteration(T, init, stationary, max_iter, device)
+    else:
+        eps_history = np.empty(max_iter)
+        p = np.asarray(init, dtype=np.float64)
+        for i in range(max_iter):
+            p = p @ T
+            eps_history[i] = cosine(p, stationary)
     converged = check_convergence_criteria(eps_history, tol=tol)
     if isinstance(converged, int) and converged < max_iter:
         print("Tolerance reached after {} iterations of {}.".format(converged, max_iter))
@@ -263,9 +268,11 @@ def sampling(data, auto_adjust=True, matrix_key="T_forward", cluster_key="louvai
         print("Number of required simulations per end point (traj_number) set to {}".format(traj_number))
         sim_number = math.ceil(traj_number * len(end_clusters_) * np.log2(n_roots + 1))
         print("Number of initial simulations (sim_number) set to {}".format(sim_number))
+        auto_device = device if device is not None else int(os.environ.get("LOCAL_RANK", "0"))
         max_steps = _auto_max_steps(adata.uns[matrix_key],
                                     (adata.obs["root_cells"] / adata.obs["root_cells"].sum()).values,
-                                    (adata.obs["end_points"] / adata.obs["end_points"].sum()).values, max_iter, tol)
+                                    (adata.obs["end_points"] / adata.obs["end_points"].sum()).values, max_iter, tol,
+                                    _backend if _backend is not None else _lib, auto_device)
         print("Number of initial simulation steps (max_steps) set to {}".format(max_steps))
     max_steps = int(max_steps)
 

@@ -116,9 +116,52 @@ def run_sampling_case(ref, name, graph, kwargs, seed, np_seed, matrix_dtype=None
         name, s["cell_sequences"].shape[0], s["cell_sequences"].shape[1], rounds, n_roots))
 
 
+def load_reference_utils():
+    """cytopath/utils.py needs `anndata` (absent) only for a module-level import and the package's
+    __init__ pulls in fastdtw/hausdorff; load it as cytopath.utils under a stub package instead."""
+    import importlib
+    import types
+    if "anndata" not in sys.modules:
+        stub = types.ModuleType("anndata")
+        stub.AnnData = object                      # only used in type annotations (utils.py:148 ff.)
+        sys.modules["anndata"] = stub
+    pkg = types.ModuleType("cytopath")
+    pkg.__path__ = [os.path.dirname(REF)]
+    sys.modules["cytopath"] = pkg
+    try:
+        return importlib.import_module("cytopath.utils")
+    finally:
+        sys.modules.pop("cytopath", None)
+
+
+def run_undirected_case(name, graph, kwargs, seed, np_seed):
+    utils = load_reference_utils()
+    ad = graph.to_adata()
+    n = ad.shape[0]
+    sim_number = kwargs.get("sim_number") or n
+    rand = PhiloxRand(seed, min(sim_number, n))
+    np.random.seed(np_seed)
+    with patched_rand(rand), contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        utils.undirected_simulations(ad, **kwargs)
+    s = ad.uns["undirected_samples"]
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **csr_fields("T_", ad.uns["T_forward"]),
+                        clusters=np.asarray(graph.clusters, dtype=str), root_prob=graph.root_prob, end_prob=graph.end_prob,
+                        kwargs=np.asarray(json.dumps(kwargs)), seed=np.asarray(seed), np_seed=np.asarray(np_seed),
+                        log_terminal_state_freq=np.asarray(ad.obs["log_terminal_state_freq"], dtype=np.float64),
+                        cell_sequences=s["cell_sequences"], transition_score=s["transition_score"],
+                        cluster_sequences=s["cluster_sequences"])
+    print("%-28s rows=%d steps=%d" % (name, s["cell_sequences"].shape[0], s["cell_sequences"].shape[1]))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = load_reference()
+    und = synth.branching_graph(n=300, k=10, n_branches=2, seed=6, workers=1, scale=3.0, noise=0.03)
+    run_undirected_case("undirected_all_cells", und, dict(max_steps=6), seed=21, np_seed=12)
+    run_undirected_case("undirected_subset", und, dict(max_steps=8, sim_number=120, unique=False), seed=22, np_seed=13)
+    if "--undirected-only" in sys.argv:
+        return
 
     # ---- matrix_prep on a messy CSR (unsorted, duplicates, explicit zeros), float64 and float32
     for tag, dt in (("f64", np.float64), ("f32", np.float32)):

@@ -71,6 +71,29 @@ def test_k1_ragged_rows_with_staging_overflow():
         g.close()
 
 
+# ---- K4 ---------------------------------------------------------------------------------
+def test_k4_power_iteration_matches_scipy():
+    """eps history of iterate_state_probability (:62-87): the state vector is bit-equal to scipy's
+    `p @ T` (same accumulation order), eps agrees to 1e-13 (the cosine's dot products are reduced in a
+    different association than BLAS), and the derived max_steps is the same integer."""
+    from scipy.spatial.distance import cosine
+    from cytopath_b200.sampler import check_convergence_criteria
+    for n, k, dtype in ((3696, 30, np.float32), (900, 16, np.float64)):
+        gph = synth.branching_graph(n=n, k=k, n_branches=4, seed=0, workers=1)
+        T = gph.T.astype(dtype)
+        init = gph.root_prob / gph.root_prob.sum()
+        stat = gph.end_prob / gph.end_prob.sum()
+        want = np.empty(120)
+        p = init
+        for i in range(120):
+            p = p @ T
+            want[i] = cosine(p, stat)
+        got, state = _lib.power_iteration(T, init, stat, 120, return_state=True)
+        np.testing.assert_array_equal(state, p)
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-13)
+        assert check_convergence_criteria(got, tol=1e-3) == check_convergence_criteria(want, tol=1e-3)
+
+
 # ---- K2 ---------------------------------------------------------------------------------
 def test_k2_matches_reference_markov_sim_golden():
     z = load("markov_sim_small")
@@ -252,6 +275,12 @@ def test_sampling_cuda_matches_reference_golden(name):
     run_quiet(cytopath_b200.sampling, ad, **kw, seed=int(z["seed"]))
     check_against_golden(ad, z)
     assert "walk_" in ad.uns["run_info"]["b200"]["kernel"]
+
+
+@pytest.mark.parametrize("name", ["undirected_all_cells", "undirected_subset"])
+def test_undirected_simulations_cuda_matches_reference(name):
+    from tests.test_sampling_host import check_undirected
+    check_undirected(name)
 
 
 def make_session(C, g, roots, code, min_clusters, end_cells, max_steps, unique, seed):

@@ -129,6 +129,30 @@ def test_numpy_array_arguments_like_undirected_simulations():
     assert ad.uns["samples"]["cell_sequences"].shape == (300, 6)
 
 
+UNDIRECTED_CASES = ["undirected_all_cells", "undirected_subset"]
+
+
+def check_undirected(name, **extra):
+    """cytopath_b200.undirected_simulations against the reference's utils.undirected_simulations (utils.py:42-101)."""
+    import json
+    z = load(name)
+    ad, _ = adata_from_case(dict(z, kwargs=np.asarray(json.dumps({"cluster_key": "louvain"}))))
+    kw = json.loads(str(z["kwargs"]))
+    np.random.seed(int(z["np_seed"]))
+    run_quiet(cytopath_b200.undirected_simulations, ad, **kw, seed=int(z["seed"]), **extra)
+    s = ad.uns["undirected_samples"]
+    np.testing.assert_array_equal(s["cell_sequences"], z["cell_sequences"])
+    np.testing.assert_array_equal(s["cluster_sequences"], z["cluster_sequences"])
+    np.testing.assert_allclose(s["transition_score"], z["transition_score"], rtol=2e-6)
+    np.testing.assert_array_equal(np.asarray(ad.obs["log_terminal_state_freq"], dtype=np.float64), z["log_terminal_state_freq"])
+    assert "samples" not in ad.uns and "undirected_sim_included" not in ad.obs      # the reference works on a copy (utils.py:73)
+
+
+@pytest.mark.parametrize("name", UNDIRECTED_CASES)
+def test_undirected_simulations_host_logic_matches_reference(name):
+    check_undirected(name, _backend=oracle_backend, dist=False)
+
+
 def test_canonical_csr_equals_densify_resparsify():
     M = synth.random_sparse_rows(n=150, max_nnz=9, seed=11, messy=True, dtype=np.float32)
     want = sparse.csr_matrix(np.float64(np.asarray(M.toarray())))
