@@ -24,7 +24,7 @@ EXPORTS = [
     "cyp_power_iteration", "cyp_walk", "cyp_walk_device", "cyp_walk_variant_name", "cyp_transition_scores",
     "cyp_session_create", "cyp_session_destroy", "cyp_session_round", "cyp_session_rows",
     "cyp_session_fetch_index", "cyp_session_fetch_rows", "cyp_session_round_records",
-    "cyp_session_round_prune", "cyp_session_set_hash_bits",
+    "cyp_session_round_prune", "cyp_session_set_hash_bits", "cyp_session_set_chunk_walkers",
 ]
 
 
@@ -33,6 +33,7 @@ class RoundStats(ctypes.Structure):
         ("n_walkers", ctypes.c_int64), ("n_pass_clusters", ctypes.c_int64), ("n_terminal", ctypes.c_int64),
         ("n_kept", ctypes.c_int64), ("n_nocrossing", ctypes.c_int64), ("store_rows", ctypes.c_int64),
         ("dedup_passes", ctypes.c_int32), ("ms_walk", ctypes.c_float), ("ms_filter", ctypes.c_float),
+        ("n_chunks", ctypes.c_int32),
     ]
 
     def as_dict(self):
@@ -85,6 +86,7 @@ def load():
     L.cyp_session_round_records.argtypes = [vp, P(vp), P(i64)]
     L.cyp_session_round_prune.argtypes = [vp, vp, i64, P(i64)]
     L.cyp_session_set_hash_bits.argtypes = [vp, ci]
+    L.cyp_session_set_chunk_walkers.argtypes = [vp, i64]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("cyp_last_error", "cyp_walk_variant_name"):
@@ -286,6 +288,9 @@ class Session:
 
     def set_hash_bits(self, bits: int):
         check(load().cyp_session_set_hash_bits(self._h, bits))
+
+    def set_chunk_walkers(self, walkers: int):
+        check(load().cyp_session_set_chunk_walkers(self._h, walkers))
 
     def close(self):
         if self._h:

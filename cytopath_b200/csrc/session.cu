@@ -149,7 +149,8 @@ rehash_rows_kernel(int64_t n_items, const int64_t *__restrict__ items, const int
     const int64_t k = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
     if (k >= n_items) return;
     const int64_t c = items[k];
-    const int32_t *row = seq + cand[c] * ld;
+    const int64_t rw = cand ? cand[c] : c;
+    const int32_t *row = seq + rw * ld;
     uint64_t h1 = fmix(salt ^ 0x9E3779B97F4A7C15ull), h2 = fmix(salt + 0xD6E8FEB86659FD93ull);
     for (int i = 0; i < n_cols; ++i) {
         const uint64_t x = static_cast<uint32_t>(row[i]);
@@ -157,21 +158,22 @@ rehash_rows_kernel(int64_t n_items, const int64_t *__restrict__ items, const int
         h2 = (h2 ^ x) * 0x9FB21C651E98DF25ull + salt;
         h2 ^= h2 >> 31;
     }
-    hash[2 * cand[c]] = h1;
-    hash[2 * cand[c] + 1] = fmix(h2);
+    hash[2 * rw] = h1;
+    hash[2 * rw + 1] = fmix(h2);
 }
 
-// items[k] = candidate rank (or nullptr: identity); cand[c] = local walker index.
+// items[k] = candidate rank (or nullptr: identity); cand[c] = row of candidate c in `seq`/`hash`
+// (or nullptr: identity); the hash of row w sits at hash[stride*w], hash[stride*w + 1].
 __global__ void __launch_bounds__(kThreads)
 dedup_insert_kernel(int64_t n_items, const int64_t *__restrict__ items, const int64_t *__restrict__ cand,
-                    const uint64_t *__restrict__ hash, uint64_t lo_mask, uint64_t hi_mask, DedupTable t,
+                    const uint64_t *__restrict__ hash, int hash_stride, uint64_t lo_mask, uint64_t hi_mask, DedupTable t,
                     uint64_t *__restrict__ slot_of) {
     const int64_t k = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
     if (k >= n_items) return;
     const int64_t c = items ? items[k] : k;
-    const int64_t w = cand[c];
-    const uint64_t lo = (hash[2 * w] & lo_mask) | 1ull;          // never 0
-    const uint64_t hi = (hash[2 * w + 1] & hi_mask) | 1ull;
+    const int64_t w = cand ? cand[c] : c;
+    const uint64_t lo = (hash[hash_stride * w] & lo_mask) | 1ull;          // never 0
+    const uint64_t hi = (hash[hash_stride * w + 1] & hi_mask) | 1ull;
     uint64_t idx = fmix(lo ^ (hi * 0x9E3779B97F4A7C15ull)) & t.mask;
     while (true) {
         const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long *>(t.key_lo + idx), 0ull, lo);
@@ -201,8 +203,8 @@ dedup_resolve_kernel(int64_t n_items, const int64_t *__restrict__ items, const i
         if (lane == 0) keep[c] = 1;
         return;
     }
-    const int32_t *a = seq + cand[c] * ld;
-    const int32_t *b = seq + cand[winner] * ld;
+    const int32_t *a = seq + (cand ? cand[c] : c) * ld;
+    const int32_t *b = seq + (cand ? cand[winner] : winner) * ld;
     bool diff = false;
     for (int i = lane; i < n_cols; i += 32) diff |= (a[i] != b[i]);
     diff = __any_sync(0xffffffffu, diff);
@@ -383,6 +385,7 @@ struct cyp_session {
     uint64_t *d_records = nullptr;
     int64_t n_records = 0, records_cap = 0;
     int64_t last_row0 = 0;
+    int64_t chunk_walkers = 0;   // 0 = as many walkers per chunk as the free HBM allows
 };
 
 namespace {
@@ -552,40 +555,127 @@ extern "C" int cyp_session_set_hash_bits(cyp_session *s, int bits) {
     return CYP_OK;
 }
 
-extern "C" int cyp_session_round(cyp_session *s, uint32_t round, int64_t sims_per_root, int64_t walker_begin,
-                                 int64_t walker_end, const double *h_uniforms, cyp_round_stats *stats) {
-    CYP_REQUIRE(s != nullptr && stats != nullptr, "cyp_session_round: NULL argument");
-    CYP_REQUIRE(sims_per_root > 0 && walker_begin >= 0 && walker_end >= walker_begin &&
-                    walker_end <= s->n_roots * sims_per_root, "cyp_session_round: bad walker range");
-    DeviceGuard guard(s->device);
-    cudaStream_t st = nullptr;
-    *stats = cyp_round_stats{};
-    const int64_t W = walker_end - walker_begin;
-    const int32_t ncol = s->max_steps, nt = s->max_steps - 1;
-    stats->n_walkers = W;
-    s->n_records = 0;
-    s->last_row0 = s->store_rows;
-    stats->store_rows = s->store_rows;
-    if (W == 0) return CYP_OK;
+namespace {
 
-    // HBM budget: trajectories + hash + slot (+ uniforms), and the worst-case dedup scratch and store growth
-    size_t free_b = 0, total_b = 0;
-    S_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    {   // memory the stream-ordered pool holds but is not using is available to this round too
-        cudaMemPool_t pool;
-        uint64_t reserved = 0, used = 0;
-        if (cudaDeviceGetDefaultMemPool(&pool, s->device) == cudaSuccess &&
-            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
-            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
-            free_b += static_cast<size_t>(reserved - used);
+// First-occurrence de-duplication of n_cand rows (candidate c = row `cand ? cand[c] : c` of `seq`, hash at
+// hash[stride*row]).  keep[c]: 1 = first occurrence, 0 = verified duplicate.  Exact for any hash quality:
+// non-winners are compared against the winner's row, true collisions are re-hashed with another salt.
+int dedup_rows(cyp_session *s, Scratch &sc, int64_t n_cand, const int64_t *d_cand, const int32_t *seq, int64_t ld,
+               int32_t ncol, const uint64_t *hash, int hash_stride, int64_t hash_rows, unsigned long long *d_unresolved,
+               cudaStream_t st, uint8_t **d_keep_out, int *passes_out) {
+    uint8_t *d_keep = nullptr;
+    uint64_t *d_slot_of = nullptr;
+    S_CUDA(sc.alloc(&d_keep, n_cand));
+    S_CUDA(sc.alloc(&d_slot_of, n_cand));
+    int64_t *d_items = nullptr, n_items = n_cand;      // nullptr = all candidates
+    const uint64_t *hash_pass = hash;                   // later passes re-hash into their own buffer
+    uint64_t *d_hash_pass = nullptr;
+    int stride = hash_stride;
+    uint64_t lo_mask, hi_mask;
+    hash_masks(s->hash_bits, &lo_mask, &hi_mask);
+    int passes = 0;
+    while (n_items > 0) {
+        Scratch pass_sc;
+        DedupTable tab{};
+        int rc = alloc_table(n_items, pass_sc, &tab, st);
+        if (rc != CYP_OK) return rc;
+        if (passes > 0) {
+            if (!d_hash_pass) S_CUDA(sc.alloc(&d_hash_pass, 2 * hash_rows));
+            rehash_rows_kernel<<<blocks_for(n_items, kThreads), kThreads, 0, st>>>(
+                n_items, d_items, d_cand, seq, ld, ncol, 0x5851F42D4C957F2Dull * static_cast<uint64_t>(passes), d_hash_pass);
+            hash_pass = d_hash_pass;
+            stride = 2;
+            lo_mask = hi_mask = ~0ull;
+        }
+        S_CUDA(cudaMemsetAsync(d_unresolved, 0, sizeof(unsigned long long), st));
+        dedup_insert_kernel<<<blocks_for(n_items, kThreads), kThreads, 0, st>>>(n_items, d_items, d_cand, hash_pass, stride,
+                                                                               lo_mask, hi_mask, tab, d_slot_of);
+        dedup_resolve_kernel<<<blocks_for(n_items * 32, kThreads), kThreads, 0, st>>>(n_items, d_items, d_cand, seq, ld, ncol, tab,
+                                                                                     d_slot_of, d_keep, d_unresolved);
+        S_CUDA(cudaGetLastError());
+        unsigned long long unresolved = 0;
+        S_CUDA(cudaMemcpyAsync(&unresolved, d_unresolved, sizeof(unresolved), cudaMemcpyDeviceToHost, st));
+        S_CUDA(cudaStreamSynchronize(st));
+        ++passes;
+        if (unresolved == 0) break;
+        if (passes > 64) return fail(CYP_E_CUDA, "cyp_session_round: de-duplication did not converge");
+        rc = compact_indices(n_cand, PredFlagEq{d_keep, 2}, sc, &d_items, &n_items, st);
+        if (rc != CYP_OK) return rc;
     }
-    const double need = static_cast<double>(W) * (4.0 * ncol + 16 + 4 + (h_uniforms ? 8.0 * nt : 0.0)) * 1.05 +
-                        static_cast<double>(W) * (4.0 * ncol + 100.0);
-    if (need > static_cast<double>(free_b))
-        return fail(CYP_E_NOMEM, "cyp_session_round: " + std::to_string(W) + " walkers x " + std::to_string(ncol) +
-                                     " steps need ~" + std::to_string(static_cast<long long>(need / (1 << 20))) + " MiB, " +
-                                     std::to_string(free_b >> 20) + " MiB free; shard the round over more GPUs");
+    *d_keep_out = d_keep;
+    *passes_out = passes;
+    return CYP_OK;
+}
 
+int ensure_records(cyp_session *s, int64_t need) {
+    if (need <= s->records_cap) return CYP_OK;
+    const int64_t cap = std::max<int64_t>(need, s->records_cap + s->records_cap / 2);
+    uint64_t *n_rec = nullptr;
+    S_CUDA(dev_alloc(&n_rec, sizeof(uint64_t) * 3 * cap));
+    if (s->n_records) S_CUDA(cudaMemcpy(n_rec, s->d_records, sizeof(uint64_t) * 3 * s->n_records, cudaMemcpyDeviceToDevice));
+    dev_free(s->d_records);
+    s->d_records = n_rec;
+    s->records_cap = cap;
+    return CYP_OK;
+}
+
+// Keeps the rows of the last round's store segment whose flag is 1 (order preserved).
+int compact_last_round(cyp_session *s, const uint8_t *d_keep, Scratch &sc, cudaStream_t st, int64_t *n_keep_out) {
+    const int64_t m = s->n_records;
+    int64_t *d_src = nullptr, n_keep = 0;
+    int rc = compact_indices(m, PredFlagEq{d_keep, 1}, sc, &d_src, &n_keep, st);
+    if (rc != CYP_OK) return rc;
+    if (n_keep < m) {
+        // move through a temporary so overlapping source/destination rows cannot race
+        int32_t *t_store = nullptr, *t_round = nullptr, *t_slot = nullptr;
+        int64_t *t_walker = nullptr;
+        uint64_t *t_rec = nullptr;
+        const int32_t ncol = s->max_steps;
+        S_CUDA(sc.alloc(&t_store, static_cast<size_t>(n_keep) * ncol));
+        S_CUDA(sc.alloc(&t_round, n_keep));
+        S_CUDA(sc.alloc(&t_walker, n_keep));
+        S_CUDA(sc.alloc(&t_slot, n_keep));
+        S_CUDA(sc.alloc(&t_rec, 3 * n_keep));
+        if (n_keep) {
+            const int64_t row0 = s->last_row0;
+            move_rows_kernel<<<blocks_for(n_keep * 32, kThreads), kThreads, 0, st>>>(
+                n_keep, d_src, row0, s->d_store + row0 * ncol, ncol, s->d_st_round, s->d_st_walker, s->d_st_slot, s->d_records,
+                t_store, t_round, t_walker, t_slot, t_rec);
+            S_CUDA(cudaGetLastError());
+            S_CUDA(cudaMemcpyAsync(s->d_store + row0 * ncol, t_store, sizeof(int32_t) * static_cast<size_t>(n_keep) * ncol, cudaMemcpyDeviceToDevice, st));
+            S_CUDA(cudaMemcpyAsync(s->d_st_round + row0, t_round, sizeof(int32_t) * n_keep, cudaMemcpyDeviceToDevice, st));
+            S_CUDA(cudaMemcpyAsync(s->d_st_walker + row0, t_walker, sizeof(int64_t) * n_keep, cudaMemcpyDeviceToDevice, st));
+            S_CUDA(cudaMemcpyAsync(s->d_st_slot + row0, t_slot, sizeof(int32_t) * n_keep, cudaMemcpyDeviceToDevice, st));
+            S_CUDA(cudaMemcpyAsync(s->d_records, t_rec, sizeof(uint64_t) * 3 * n_keep, cudaMemcpyDeviceToDevice, st));
+        }
+        S_CUDA(cudaStreamSynchronize(st));
+        s->store_rows = s->last_row0 + n_keep;
+        s->n_records = n_keep;
+    }
+    *n_keep_out = n_keep;
+    return CYP_OK;
+}
+
+size_t free_device_bytes(int device) {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return 0;
+    // memory the stream-ordered pool holds but is not using is available too
+    cudaMemPool_t pool;
+    uint64_t reserved = 0, used = 0;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess &&
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+        free_b += static_cast<size_t>(reserved - used);
+    return free_b;
+}
+
+// One chunk of a round: walkers [wb, we).  K2 in filter mode, K3 within the chunk, survivors appended to
+// the store and to the round's record list.  Statistics are accumulated into *stats.
+int run_chunk(cyp_session *s, uint32_t round, int64_t sims_per_root, int64_t wb, int64_t we, const double *h_uniforms,
+              cyp_round_stats *stats) {
+    cudaStream_t st = nullptr;
+    const int64_t W = we - wb;
+    const int32_t ncol = s->max_steps, nt = s->max_steps - 1;
     Scratch sc;
     int32_t *d_seq = nullptr, *d_slot = nullptr;
     uint64_t *d_hash = nullptr;
@@ -613,7 +703,7 @@ extern "C" int cyp_session_round(cyp_session *s, uint32_t round, int64_t sims_pe
     WalkParams p{};
     p.rows = s->g->d_row; p.cdf = s->g->d_cdf; p.edge = s->g->d_edge;
     p.roots = s->d_roots; p.sims_per_root = sims_per_root;
-    p.walker_begin = walker_begin; p.n_walkers = W; p.nt = nt; p.round = round; p.seed = s->seed;
+    p.walker_begin = wb; p.n_walkers = W; p.nt = nt; p.round = round; p.seed = s->seed;
     p.uniforms = d_u; p.out_seq = d_seq; p.ld = ncol; p.nocross = d_counters;
     p.code8 = s->d_code8; p.min_clusters = s->min_clusters; p.end_slot = s->d_end_slot;
     p.out_slot = d_slot; p.out_hash = d_hash;
@@ -642,39 +732,8 @@ extern "C" int cyp_session_round(cyp_session *s, uint32_t round, int64_t sims_pe
     int passes = 0;
     if (s->unique && n_cand > 1) {
         uint8_t *d_keep = nullptr;
-        uint64_t *d_slot_of = nullptr;
-        S_CUDA(sc.alloc(&d_keep, n_cand));
-        S_CUDA(sc.alloc(&d_slot_of, n_cand));
-        int64_t *d_items = nullptr, n_items = n_cand;   // nullptr = all candidates
-        uint64_t *d_hash_pass = d_hash;                 // later passes re-hash into their own buffer: d_hash feeds the records
-        uint64_t lo_mask, hi_mask;
-        hash_masks(s->hash_bits, &lo_mask, &hi_mask);
-        while (n_items > 0) {
-            Scratch pass_sc;
-            DedupTable tab{};
-            rc = alloc_table(n_items, pass_sc, &tab, st);
-            if (rc != CYP_OK) return rc;
-            if (passes > 0) {
-                if (d_hash_pass == d_hash) S_CUDA(sc.alloc(&d_hash_pass, 2 * W));
-                rehash_rows_kernel<<<blocks_for(n_items, kThreads), kThreads, 0, st>>>(
-                    n_items, d_items, d_cand, d_seq, ncol, ncol, 0x5851F42D4C957F2Dull * static_cast<uint64_t>(passes), d_hash_pass);
-                lo_mask = hi_mask = ~0ull;
-            }
-            S_CUDA(cudaMemsetAsync(d_counters + 3, 0, sizeof(unsigned long long), st));
-            dedup_insert_kernel<<<blocks_for(n_items, kThreads), kThreads, 0, st>>>(n_items, d_items, d_cand, d_hash_pass, lo_mask,
-                                                                                   hi_mask, tab, d_slot_of);
-            dedup_resolve_kernel<<<blocks_for(n_items * 32, kThreads), kThreads, 0, st>>>(
-                n_items, d_items, d_cand, d_seq, ncol, ncol, tab, d_slot_of, d_keep, d_counters + 3);
-            S_CUDA(cudaGetLastError());
-            unsigned long long unresolved = 0;
-            S_CUDA(cudaMemcpyAsync(&unresolved, d_counters + 3, sizeof(unresolved), cudaMemcpyDeviceToHost, st));
-            S_CUDA(cudaStreamSynchronize(st));
-            ++passes;
-            if (unresolved == 0) break;
-            if (passes > 64) return fail(CYP_E_CUDA, "cyp_session_round: de-duplication did not converge");
-            rc = compact_indices(n_cand, PredFlagEq{d_keep, 2}, sc, &d_items, &n_items, st);
-            if (rc != CYP_OK) return rc;
-        }
+        rc = dedup_rows(s, sc, n_cand, d_cand, d_seq, ncol, ncol, d_hash, 2, W, d_counters + 3, st, &d_keep, &passes);
+        if (rc != CYP_OK) return rc;
         rc = compact_indices(n_cand, PredFlagEq{d_keep, 1}, sc, &d_kept, &n_kept, st);
         if (rc != CYP_OK) return rc;
     }
@@ -682,34 +741,94 @@ extern "C" int cyp_session_round(cyp_session *s, uint32_t round, int64_t sims_pe
     // ---- append survivors to the store
     rc = grow_store(s, s->store_rows + n_kept);
     if (rc != CYP_OK) return rc;
-    if (n_kept > s->records_cap) {
-        dev_free(s->d_records);
-        s->d_records = nullptr;
-        s->records_cap = 0;
-        S_CUDA(dev_alloc(&s->d_records, sizeof(uint64_t) * 3 * n_kept));
-        s->records_cap = n_kept;
-    }
+    rc = ensure_records(s, s->n_records + n_kept);
+    if (rc != CYP_OK) return rc;
     if (n_kept) {
         gather_rows_kernel<<<blocks_for(n_kept * 32, kThreads), kThreads, 0, st>>>(
-            n_kept, d_kept, d_cand, d_seq, ncol, ncol, d_slot, d_hash, walker_begin, static_cast<int32_t>(round), s->d_store,
-            s->store_rows, s->d_st_round, s->d_st_walker, s->d_st_slot, s->d_records);
+            n_kept, d_kept, d_cand, d_seq, ncol, ncol, d_slot, d_hash, wb, static_cast<int32_t>(round), s->d_store,
+            s->store_rows, s->d_st_round, s->d_st_walker, s->d_st_slot, s->d_records + 3 * s->n_records);
         S_CUDA(cudaGetLastError());
     }
     S_CUDA(cudaEventRecord(ev[2], st));
     unsigned long long counters[4] = {0, 0, 0, 0};
     S_CUDA(cudaMemcpyAsync(counters, d_counters, sizeof(counters), cudaMemcpyDeviceToHost, st));
     S_CUDA(cudaStreamSynchronize(st));
-    S_CUDA(cudaEventElapsedTime(&stats->ms_walk, ev[0], ev[1]));
-    S_CUDA(cudaEventElapsedTime(&stats->ms_filter, ev[1], ev[2]));
+    float ms_walk = 0.f, ms_filter = 0.f;
+    S_CUDA(cudaEventElapsedTime(&ms_walk, ev[0], ev[1]));
+    S_CUDA(cudaEventElapsedTime(&ms_filter, ev[1], ev[2]));
     s->store_rows += n_kept;
-    s->n_records = n_kept;
-    stats->n_nocrossing = static_cast<int64_t>(counters[0]);
-    stats->n_pass_clusters = static_cast<int64_t>(counters[1]);
-    stats->n_terminal = static_cast<int64_t>(counters[2]);
-    stats->n_kept = n_kept;
+    s->n_records += n_kept;
+    stats->ms_walk += ms_walk;
+    stats->ms_filter += ms_filter;
+    stats->n_nocrossing += static_cast<int64_t>(counters[0]);
+    stats->n_pass_clusters += static_cast<int64_t>(counters[1]);
+    stats->n_terminal += static_cast<int64_t>(counters[2]);
+    stats->dedup_passes = std::max(stats->dedup_passes, passes);
+    return CYP_OK;
+}
+
+}  // namespace
+
+extern "C" int cyp_session_set_chunk_walkers(cyp_session *s, int64_t walkers) {
+    CYP_REQUIRE(s != nullptr && walkers >= 0, "cyp_session_set_chunk_walkers: bad argument");
+    s->chunk_walkers = walkers;
+    return CYP_OK;
+}
+
+extern "C" int cyp_session_round(cyp_session *s, uint32_t round, int64_t sims_per_root, int64_t walker_begin,
+                                 int64_t walker_end, const double *h_uniforms, cyp_round_stats *stats) {
+    CYP_REQUIRE(s != nullptr && stats != nullptr, "cyp_session_round: NULL argument");
+    CYP_REQUIRE(sims_per_root > 0 && walker_begin >= 0 && walker_end >= walker_begin &&
+                    walker_end <= s->n_roots * sims_per_root, "cyp_session_round: bad walker range");
+    DeviceGuard guard(s->device);
+    cudaStream_t st = nullptr;
+    *stats = cyp_round_stats{};
+    const int64_t W = walker_end - walker_begin;
+    const int32_t ncol = s->max_steps, nt = s->max_steps - 1;
+    stats->n_walkers = W;
+    s->n_records = 0;
+    s->last_row0 = s->store_rows;
     stats->store_rows = s->store_rows;
-    stats->dedup_passes = passes;
-    if (counters[0])
+    if (W == 0) return CYP_OK;
+
+    // A round is walked in chunks that fit the free HBM: per walker the trajectory, hash and slot
+    // (+ injected uniforms), the K3 scratch if every walker were a candidate, and room for the store to
+    // take the chunk's survivors (grow_store copies, hence the factor).
+    const double per_walker = 4.0 * ncol + 20.0 + (h_uniforms ? 8.0 * nt : 0.0) + 120.0 + 2.5 * 4.0 * ncol;
+    int64_t chunk = s->chunk_walkers;
+    if (chunk <= 0) {
+        const double free_b = static_cast<double>(free_device_bytes(s->device));
+        chunk = static_cast<int64_t>(0.8 * free_b / per_walker);
+        if (chunk < 1024)
+            return fail(CYP_E_NOMEM, "cyp_session_round: " + std::to_string(static_cast<long long>(free_b / (1 << 20))) +
+                                         " MiB free is not enough for 1024 walkers x " + std::to_string(ncol) + " steps");
+    }
+    int n_chunks = 0;
+    for (int64_t wb = walker_begin; wb < walker_end; wb += chunk, ++n_chunks) {
+        const int64_t we = std::min(walker_end, wb + chunk);
+        const double *u = h_uniforms ? h_uniforms + (wb - walker_begin) * static_cast<int64_t>(nt) : nullptr;
+        const int rc = run_chunk(s, round, sims_per_root, wb, we, u, stats);
+        if (rc != CYP_OK) return rc;
+    }
+    // first occurrence across chunks: de-duplicate the round's store segment (chunks are in walker order)
+    if (n_chunks > 1 && s->unique && s->n_records > 1) {
+        Scratch sc;
+        unsigned long long *d_unres = nullptr;
+        S_CUDA(sc.alloc(&d_unres, 1));
+        uint8_t *d_keep = nullptr;
+        int passes = 0;
+        int rc = dedup_rows(s, sc, s->n_records, nullptr, s->d_store + s->last_row0 * ncol, ncol, ncol, s->d_records, 3,
+                            s->n_records, d_unres, st, &d_keep, &passes);
+        if (rc != CYP_OK) return rc;
+        int64_t n_keep = 0;
+        rc = compact_last_round(s, d_keep, sc, st, &n_keep);
+        if (rc != CYP_OK) return rc;
+        stats->dedup_passes = std::max(stats->dedup_passes, passes);
+    }
+    stats->n_kept = s->n_records;
+    stats->store_rows = s->store_rows;
+    stats->n_chunks = n_chunks;
+    if (stats->n_nocrossing)
         return fail(CYP_E_NOCROSSING, "cyp_session_round: a uniform exceeded its row's last CDF value (reference: IndexError at markov_chain_sampler.py:49)");
     return CYP_OK;
 }
@@ -774,36 +893,9 @@ extern "C" int cyp_session_round_prune(cyp_session *s, const uint64_t *d_all_rec
     S_CUDA(sc.alloc(&d_keep, m));
     records_lookup_kernel<<<blocks_for(m, kThreads), kThreads, 0, st>>>(m, s->d_records, tab, d_keep);
     S_CUDA(cudaGetLastError());
-    int64_t *d_src = nullptr, n_keep = 0;
-    rc = compact_indices(m, PredFlagEq{d_keep, 1}, sc, &d_src, &n_keep, st);
+    int64_t n_keep = 0;
+    rc = compact_last_round(s, d_keep, sc, st, &n_keep);
     if (rc != CYP_OK) return rc;
-    if (n_keep < m) {
-        // move through a temporary so overlapping source/destination rows cannot race
-        int32_t *t_store = nullptr, *t_round = nullptr, *t_slot = nullptr;
-        int64_t *t_walker = nullptr;
-        uint64_t *t_rec = nullptr;
-        const int32_t ncol = s->max_steps;
-        S_CUDA(sc.alloc(&t_store, static_cast<size_t>(n_keep) * ncol));
-        S_CUDA(sc.alloc(&t_round, n_keep));
-        S_CUDA(sc.alloc(&t_walker, n_keep));
-        S_CUDA(sc.alloc(&t_slot, n_keep));
-        S_CUDA(sc.alloc(&t_rec, 3 * n_keep));
-        if (n_keep) {
-            const int64_t row0 = s->last_row0;
-            move_rows_kernel<<<blocks_for(n_keep * 32, kThreads), kThreads, 0, st>>>(
-                n_keep, d_src, row0, s->d_store + row0 * ncol, ncol, s->d_st_round, s->d_st_walker, s->d_st_slot, s->d_records,
-                t_store, t_round, t_walker, t_slot, t_rec);
-            S_CUDA(cudaGetLastError());
-            S_CUDA(cudaMemcpyAsync(s->d_store + row0 * ncol, t_store, sizeof(int32_t) * static_cast<size_t>(n_keep) * ncol, cudaMemcpyDeviceToDevice, st));
-            S_CUDA(cudaMemcpyAsync(s->d_st_round + row0, t_round, sizeof(int32_t) * n_keep, cudaMemcpyDeviceToDevice, st));
-            S_CUDA(cudaMemcpyAsync(s->d_st_walker + row0, t_walker, sizeof(int64_t) * n_keep, cudaMemcpyDeviceToDevice, st));
-            S_CUDA(cudaMemcpyAsync(s->d_st_slot + row0, t_slot, sizeof(int32_t) * n_keep, cudaMemcpyDeviceToDevice, st));
-            S_CUDA(cudaMemcpyAsync(s->d_records, t_rec, sizeof(uint64_t) * 3 * n_keep, cudaMemcpyDeviceToDevice, st));
-        }
-        S_CUDA(cudaStreamSynchronize(st));
-        s->store_rows = s->last_row0 + n_keep;
-        s->n_records = n_keep;
-    }
     S_CUDA(cudaStreamSynchronize(st));
     *n_dropped = m - n_keep;
     return CYP_OK;

@@ -135,6 +135,7 @@ typedef struct cyp_round_stats {
     int32_t dedup_passes;     /* hash passes used (1 unless a 128-bit hash collided) */
     float ms_walk;            /* step kernel, CUDA events */
     float ms_filter;          /* filter + dedup + compaction kernels */
+    int32_t n_chunks;         /* pieces the round was walked in (1 unless it did not fit the free HBM) */
 } cyp_round_stats;
 
 /* Walkers [walker_begin, walker_end) of round `round` with sims_per_root walkers per root.
@@ -155,6 +156,11 @@ int cyp_session_fetch_rows(const cyp_session *s, const int64_t *h_rows, int64_t 
  * was also produced by a lower walker id on another rank. */
 int cyp_session_round_records(const cyp_session *s, uint64_t **d_records, int64_t *n_records);
 int cyp_session_round_prune(cyp_session *s, const uint64_t *d_all_records, int64_t n_all, int64_t *n_dropped);
+
+/* Walkers per chunk of a round (0 = as many as the free HBM allows).  A round larger than a chunk is
+ * walked piecewise; the first-occurrence de-duplication is then completed across the chunks, so the
+ * result does not depend on the chunk size. */
+int cyp_session_set_chunk_walkers(cyp_session *s, int64_t walkers);
 
 /* test hook: keep only the low `bits` bits of the 128-bit sequence hash (forces collisions) */
 int cyp_session_set_hash_bits(cyp_session *s, int bits);

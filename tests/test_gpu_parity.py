@@ -302,9 +302,10 @@ def oracle_round(C, cdf, roots, sims, max_steps, seed, rnd, code, min_clusters, 
     return seq, ok, cand
 
 
+@pytest.mark.parametrize("chunk", [0, 97])
 @pytest.mark.parametrize("hash_bits", [128, 6, 0])
 @pytest.mark.parametrize("n_codes", [1, 40, 200, 700])
-def test_k3_round_filters_and_dedup_vs_oracle(hash_bits, n_codes):
+def test_k3_round_filters_and_dedup_vs_oracle(hash_bits, n_codes, chunk):
     """Short walks on a tiny graph produce many duplicate sequences; truncating the hash to a
     few bits forces collisions so the verify / re-hash path is exercised too."""
     C = sp.canonical_csr(synth.branching_graph(n=80, k=4, n_branches=2, seed=5, workers=1, scale=2.0, noise=0.05).T)
@@ -320,6 +321,7 @@ def test_k3_round_filters_and_dedup_vs_oracle(hash_bits, n_codes):
     cdf = cwalk.build_cdf(C, 0)
     s, slot = make_session(C, g, roots, code, min_clusters, end_cells, 6, True, 77)
     s.set_hash_bits(hash_bits)
+    s.set_chunk_walkers(chunk)              # 97 walkers per chunk: duplicates must also be found across chunks
     total = 0
     for rnd, sims in enumerate((50, 400)):
         st = s.round(rnd, sims, 0, len(roots) * sims)
@@ -329,6 +331,7 @@ def test_k3_round_filters_and_dedup_vs_oracle(hash_bits, n_codes):
         assert st["n_kept"] == len(cand), (st, len(cand))
         if hash_bits < 128 and st["n_terminal"] > st["n_kept"] + 5:
             assert st["dedup_passes"] >= 2
+        assert st["n_chunks"] == (1 if chunk == 0 else -(-len(seq) // chunk))
         r, w, sl = s.fetch_index(total)
         np.testing.assert_array_equal(w, cand)
         np.testing.assert_array_equal(sl, slot[seq[cand, -1]])
