@@ -32,7 +32,7 @@ WORKLOADS = {
     "c1": dict(n=3_696, k=30, branches=4, stems=1, walkers=444_000, max_steps=108, desc="configs[0] graph: 3,696 cells k=30"),
     "c2": dict(n=5_780, k=30, branches=5, stems=2, walkers=710_000, max_steps=200, desc="configs[1] graph: 5,780 cells k=30, 200 steps"),
     "c3": dict(n=100_000, k=30, branches=8, stems=1, walkers=1_000_000, max_steps=200, desc="configs[2]: 100k cells k=30, 1M walkers x 200 steps (L2-resident)"),
-    "c4": dict(n=1_000_000, k=50, branches=16, stems=1, walkers=1_250_000, max_steps=500,
+    "c4": dict(n=1_000_000, k=50, branches=8, stems=1, layers=16, walkers=1_250_000, max_steps=500,
                desc="configs[3]: 1M cells k=50 (51M nnz), 10M walkers x 500 steps / 8 GPUs = 1.25M walkers per GPU (HBM-bound)"),
     "c5": dict(n=250_000, k=200, branches=0, stems=1, walkers=1_250_000, max_steps=200,
                desc="configs[4]-shaped: cycling + convergent graph, 250k cells k=200 (50M nnz, long rows), 1.25M walkers x 200 steps per GPU"),
@@ -59,7 +59,8 @@ def make_graph(w, world):
         g = synth.cycling_graph(n=w["n"], k=w["k"], seed=0, workers=workers)
         roots = np.where(g.root_prob >= 0.99)[0].astype(np.int32)        # unsupervised roots (markov_chain_sampler.py:226)
     else:
-        g = synth.branching_graph(n=w["n"], k=w["k"], n_branches=w["branches"], n_root_stems=w["stems"], seed=0, workers=workers)
+        g = synth.branching_graph(n=w["n"], k=w["k"], n_branches=w["branches"], n_root_stems=w["stems"], seed=0, workers=workers,
+                                  n_layers=w.get("layers", 1))
         roots = np.where(np.isin(g.clusters, g.root_clusters))[0].astype(np.int32)
     C = _canonical_csr(g.T)
     return g, C, roots

@@ -20,6 +20,7 @@ from __future__ import annotations
 
 import math
 import os
+import sys
 import warnings
 
 import numpy as np
@@ -129,6 +130,8 @@ class _World:
         self.rank, self.size, self.dist, self.torch = 0, 1, None, None
         if use_dist is False:
             return
+        if use_dist == "auto" and "torch.distributed" not in sys.modules:
+            return                      # nobody initialised a process group: do not pay `import torch` (seconds)
         try:
             import torch
             import torch.distributed as dist

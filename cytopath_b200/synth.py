@@ -66,11 +66,21 @@ class SynthGraph:
         return ad
 
 
-def _knn_transition(pos, vel, k, scale=10.0, self_loops=True, workers=-1):
-    """kNN graph with scvelo-like exp(scale * cos(velocity, displacement)) weights."""
+def _knn_transition(pos, vel, k, scale=10.0, self_loops=True, workers=-1, layer=None):
+    """kNN graph with scvelo-like exp(scale * cos(velocity, displacement)) weights.  With `layer`
+    (an integer per cell) neighbours are searched within the cell's layer only: L interleaved,
+    independent sub-graphs whose hop length is ~sqrt(L) times longer, so that terminal regions stay
+    reachable in a few hundred steps at atlas scale while every row of the big matrix is still used."""
     n = pos.shape[0]
-    tree = cKDTree(pos)
-    _, nbr = tree.query(pos, k=k + 1, workers=workers)       # column 0 is the cell itself
+    if layer is None:
+        tree = cKDTree(pos)
+        _, nbr = tree.query(pos, k=k + 1, workers=workers)       # column 0 is the cell itself
+    else:
+        nbr = np.empty((n, k + 1), dtype=np.int64)
+        for l in np.unique(layer):
+            idx = np.flatnonzero(layer == l)
+            _, loc = cKDTree(pos[idx]).query(pos[idx], k=k + 1, workers=workers)
+            nbr[idx] = idx[loc]
     nbr = nbr.astype(np.int64)
     disp = pos[nbr] - pos[:, None, :]
     norm = np.linalg.norm(disp, axis=2)
@@ -89,7 +99,7 @@ def _knn_transition(pos, vel, k, scale=10.0, self_loops=True, workers=-1):
 
 
 def branching_graph(n=3696, k=30, n_branches=4, seed=0, n_root_stems=1, self_loops=True,
-                    shuffle=True, workers=-1, scale=10.0, noise=0.01) -> SynthGraph:
+                    shuffle=True, workers=-1, scale=10.0, noise=0.01, n_layers=1) -> SynthGraph:
     """Stem that splits into `n_branches` rays; velocity points along pseudotime.
 
     `n_root_stems=2` adds a second stem (offset in y) that joins the first at the
@@ -117,7 +127,8 @@ def branching_graph(n=3696, k=30, n_branches=4, seed=0, n_root_stems=1, self_loo
     if not shuffle:                                   # optional locality-preserving order
         order = np.argsort(t, kind="stable")
         t, b, stem_id, on_stem, pos, vel = (a[order] for a in (t, b, stem_id, on_stem, pos, vel))
-    T = _knn_transition(pos, vel, k, scale=scale, self_loops=self_loops, workers=workers)
+    layer = rng.integers(n_layers, size=n) if n_layers > 1 else None
+    T = _knn_transition(pos, vel, k, scale=scale, self_loops=self_loops, workers=workers, layer=layer)
 
     stem_bin = np.minimum((t / 0.3 * 5).astype(int), 4)
     br_bin = np.minimum(((t - 0.3) / 0.7 * 5).astype(int), 4)
