@@ -67,7 +67,7 @@ def make_graph(w, world):
 
 
 class ClockSampler:
-    """nvidia-smi clocks line of B200_PROFILING.md, sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks line of B200_PROFILING.md, sampled every 50 ms during the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -77,7 +77,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -366,6 +366,7 @@ def run_b200(args, w):
                      "mean_visited_row_nnz": kbar, "ms_per_launch": ms_launch,
                      "layout_bytes_per_walker_step": layout_bytes,
                      "layout_achieved": W * nt * layout_bytes / (ms_launch * 1e-3) / 1e9,
+                     "layout_frac": W * nt * layout_bytes / (ms_launch * 1e-3) / 1e9 / peak,
                      "note": "achieved uses SURVEY 8d's algorithmic bytes (full float64/float32 CDF row + 16 B); the default kernel "
                              "stages 2-byte CDF codes (exact by construction, DESIGN.md 5), so it requests layout_bytes per step "
                              "and frac can exceed 1; traffic = dram read+write bytes of one launch from the committed ncu capture"},

@@ -218,6 +218,14 @@ def main():
                       dict(auto_adjust=False, max_steps=80, traj_number=30, sim_number=100,
                            root_cells=[root_cell], end_points=ends.tolist(), num_cores=1),
                       seed=14, np_seed=8)
+    dup_ends = np.where(np.isin(small.clusters, small.end_clusters))[0]
+    dup_ends = np.concatenate([dup_ends[::-1][:25], dup_ends[:10], dup_ends[::-1][:5]])         # unsorted, with repeats
+    run_sampling_case(ref, "sampling_small_dup_endpoints", small,
+                      dict(auto_adjust=False, max_steps=70, traj_number=40, sim_number=300,
+                           root_clusters=small.root_clusters, end_points=dup_ends.tolist(), num_cores=1),
+                      seed=18, np_seed=14)
+    if "--dup-only" in sys.argv:
+        return
     run_sampling_case(ref, "sampling_small_auto", small, dict(auto_adjust=True, traj_number=20, num_cores=1),
                       seed=15, np_seed=9)
     two = synth.branching_graph(n=900, k=16, n_branches=3, seed=4, n_root_stems=2, workers=1, scale=4.0, noise=0.03)

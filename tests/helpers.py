@@ -13,7 +13,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 SAMPLING_CASES = [
     "sampling_small_clusters", "sampling_small_probs_f32", "sampling_small_notunique",
     "sampling_small_single_root", "sampling_small_auto", "sampling_two_stems_normalize",
-    "sampling_tiny_dups", "sampling_config1_auto",
+    "sampling_tiny_dups", "sampling_small_dup_endpoints", "sampling_config1_auto",
 ]
 
 

@@ -153,6 +153,22 @@ def test_undirected_simulations_host_logic_matches_reference(name):
     check_undirected(name, _backend=oracle_backend, dist=False)
 
 
+def test_duplicate_and_unsorted_end_points_follow_the_reference_scan_order():
+    """The reference scans `end_points` in list order and counts a cell listed twice twice (:343-354, :386-394)."""
+    from oracle import sampler_port as sp
+    g, ad = small_adata()
+    ends = np.where(np.isin(g.clusters, g.end_clusters))[0]
+    ends = np.concatenate([ends[::-1][:25], ends[:10], ends[::-1][:5]]).tolist()        # unsorted, with repeats
+    kw = dict(auto_adjust=False, max_steps=60, traj_number=40, sim_number=300, root_clusters=g.root_clusters, end_points=ends)
+    a, b = ad.copy(), ad.copy()
+    np.random.seed(3)
+    run_quiet(cytopath_b200.sampling, a, **kw, seed=5, _backend=oracle_backend, dist=False)
+    np.random.seed(3)
+    run_quiet(sp.sampling_port, b, **kw, seed=5)
+    np.testing.assert_array_equal(a.uns["samples"]["cell_sequences"], b.uns["samples"]["cell_sequences"])
+    np.testing.assert_array_equal(a.uns["samples"]["cluster_sequences"], b.uns["samples"]["cluster_sequences"])
+
+
 def test_canonical_csr_equals_densify_resparsify():
     M = synth.random_sparse_rows(n=150, max_nnz=9, seed=11, messy=True, dtype=np.float32)
     want = sparse.csr_matrix(np.float64(np.asarray(M.toarray())))
