@@ -131,11 +131,10 @@ def power_iteration(T, init, stationary, max_iter: int, device: int = 0, return_
     T: scipy sparse or dense n x n matrix as stored in adata.uns[matrix_key] (not normalised, like :73)."""
     from scipy import sparse
     require_device(device)
-    M = sparse.csc_matrix(T)
-    M.sort_indices()
+    M = T if sparse.isspmatrix_csr(T) or isinstance(T, sparse.csr_array) else sparse.csr_matrix(T)
     n = M.shape[0]
-    col_ptr = np.ascontiguousarray(M.indptr, dtype=np.int64)
-    row_idx = np.ascontiguousarray(M.indices, dtype=np.int32)
+    col_ptr = np.ascontiguousarray(M.indptr, dtype=np.int64)          # CSR row pointers / column indices:
+    row_idx = np.ascontiguousarray(M.indices, dtype=np.int32)         # the library transposes on the device
     val = np.ascontiguousarray(M.data, dtype=np.float64)
     init = np.ascontiguousarray(init, dtype=np.float64)
     stationary = np.ascontiguousarray(stationary, dtype=np.float64)

@@ -70,12 +70,13 @@ int cyp_graph_fetch_cdf(const cyp_graph *g, void *h_cdf);
 int cyp_graph_build_ms(const cyp_graph *g, float *ms);
 
 /* ---- a5: iterate_state_probability (markov_chain_sampler.py:62-87) --------------------
- * max_iter iterations of p <- p @ T from h_init, with T given as CSC (columns of T, row indices
- * ascending); h_eps_history[i] = cosine distance between p after iteration i+1 and h_stationary
- * (:73-76).  The caller derives max_steps with check_convergence_criteria (:54-60).
+ * max_iter iterations of p <- p @ T from h_init, with T given as CSR exactly as stored in
+ * adata.uns[matrix_key] (any column order; it is transposed on the device);
+ * h_eps_history[i] = cosine distance between p after iteration i+1 and h_stationary (:73-76).
+ * The caller derives max_steps with check_convergence_criteria (:54-60).
  * h_final_state (may be NULL) receives p after the last iteration. */
-int cyp_power_iteration(int device, int64_t n_cells, int64_t nnz, const int64_t *h_col_ptr,
-                        const int32_t *h_row_idx, const double *h_val, const double *h_init,
+int cyp_power_iteration(int device, int64_t n_cells, int64_t nnz, const int64_t *h_row_ptr,
+                        const int32_t *h_col, const double *h_val, const double *h_init,
                         const double *h_stationary, int32_t max_iter, double *h_eps_history,
                         double *h_final_state);
 
