@@ -10,7 +10,8 @@ The compute lives in a CUDA C-ABI library (include/cytopath_b200.h); there is no
 fallback: without the library or a CUDA device, `sampling` raises.
 """
 from .sampler import check_convergence_criteria, iterate_state_probability, sampling
+from .trajectory_distances import coordinate_assigner, distance_matrix
 from .undirected import undirected_simulations
 
 __version__ = "0.1.0"
-__all__ = ["sampling", "undirected_simulations", "iterate_state_probability", "check_convergence_criteria", "__version__"]
+__all__ = ["sampling", "undirected_simulations", "distance_matrix", "coordinate_assigner", "iterate_state_probability", "check_convergence_criteria", "__version__"]

@@ -25,6 +25,7 @@ EXPORTS = [
     "cyp_session_create", "cyp_session_destroy", "cyp_session_round", "cyp_session_rows",
     "cyp_session_fetch_index", "cyp_session_fetch_rows", "cyp_session_round_records",
     "cyp_session_round_prune", "cyp_session_set_hash_bits", "cyp_session_set_chunk_walkers",
+    "cyp_hausdorff_matrix",
 ]
 
 
@@ -87,6 +88,7 @@ def load():
     L.cyp_session_round_prune.argtypes = [vp, vp, i64, P(i64)]
     L.cyp_session_set_hash_bits.argtypes = [vp, ci]
     L.cyp_session_set_chunk_walkers.argtypes = [vp, i64]
+    L.cyp_hausdorff_matrix.argtypes = [ci, vp, i64, i32, i32, ci, vp, P(ctypes.c_float)]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("cyp_last_error", "cyp_walk_variant_name"):
@@ -143,6 +145,25 @@ def power_iteration(T, init, stationary, max_iter: int, device: int = 0, return_
     check(load().cyp_power_iteration(device, n, val.shape[0], ptr(col_ptr), ptr(row_idx), ptr(val), ptr(init),
                                      ptr(stationary), max_iter, ptr(eps), ptr(state)))
     return (eps, state) if return_state else eps
+
+
+HAUSDORFF_METRICS = {"euclidean": 0, "manhattan": 1, "chebyshev": 2, "cosine": 3}
+
+
+def hausdorff_matrix(coords, metric: str = "euclidean", device: int = 0, return_ms: bool = False):
+    """[S, S] Hausdorff distances between the S chains of `coords` [S, L, d] (K5, cyp_hausdorff_matrix)."""
+    require_device(device)
+    if metric not in HAUSDORFF_METRICS:
+        raise ValueError("distance must be one of %s" % sorted(HAUSDORFF_METRICS))
+    c = np.ascontiguousarray(coords, dtype=np.float64)
+    if c.ndim != 3:
+        raise ValueError("sequence_coordinates must have shape [n_sequences, n_steps, n_dims]")
+    out = np.empty((c.shape[0], c.shape[0]), dtype=np.float64)
+    ms = ctypes.c_float(0)
+    if c.shape[0]:
+        check(load().cyp_hausdorff_matrix(device, ptr(c), c.shape[0], c.shape[1], c.shape[2], HAUSDORFF_METRICS[metric],
+                                          ptr(out), ctypes.byref(ms)))
+    return (out, ms.value) if return_ms else out
 
 
 class Graph:

@@ -163,6 +163,14 @@ int cyp_session_round_prune(cyp_session *s, const uint64_t *d_all_records, int64
  * result does not depend on the chunk size. */
 int cyp_session_set_chunk_walkers(cyp_session *s, int64_t walkers);
 
+/* ---- f2: distance_matrix (trajectory_estimation/sample_clustering.py:57-71) -------------
+ * Symmetric [n_chains, n_chains] matrix of Hausdorff distances between chains of chain_len points in
+ * `dim` dimensions (h_coords is double [n_chains, chain_len, dim], what coordinate_assigner :38-55
+ * returns).  metric: 0 euclidean (the reference's default, :135), 1 manhattan, 2 chebyshev, 3 cosine,
+ * as in the `hausdorff` package the reference calls.  kernel_ms (may be NULL): device time. */
+int cyp_hausdorff_matrix(int device, const double *h_coords, int64_t n_chains, int32_t chain_len, int32_t dim,
+                         int metric, double *h_out, float *kernel_ms);
+
 /* test hook: keep only the low `bits` bits of the 128-bit sequence hash (forces collisions) */
 int cyp_session_set_hash_bits(cyp_session *s, int bits);
 

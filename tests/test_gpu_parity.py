@@ -425,3 +425,39 @@ def test_native_rng_one_step_frequencies_chi_square():
             chi2, p = stats.chisquare(counts[keep], exp)
             assert p > 1e-4 / len(rows), (mode, r, chi2, p)
         g.close()
+
+
+# ---- f2: Hausdorff distance matrix ---------------------------------------------------------
+@pytest.mark.parametrize("S,L,d", [(40, 37, 5), (12, 200, 50), (25, 129, 2), (3, 1, 7)])
+@pytest.mark.parametrize("metric", ["euclidean", "manhattan", "chebyshev", "cosine"])
+def test_f2_hausdorff_matrix_vs_oracle(S, L, d, metric):
+    """distance_matrix (sample_clustering.py:57-71) against the numpy restatement; float64, rtol 1e-12
+    (sums of d terms in a different association).  The `hausdorff` package itself is absent: parity unpinned."""
+    from oracle import hausdorff_port as hp
+    rng = np.random.default_rng(S * 1000 + L + d)
+    base = rng.normal(size=(S, 1, d)) * 0.3
+    coords = (base + np.cumsum(rng.normal(scale=0.05, size=(S, L, d)), axis=1) + 1.0).astype(np.float32)
+    with contextlib.redirect_stdout(io.StringIO()):
+        got = cytopath_b200.distance_matrix(coords, distance=metric)
+    want = hp.distance_matrix(coords, distance=metric)
+    assert got.shape == (S, S) and got.dtype == np.float64
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-14)
+    np.testing.assert_array_equal(got, got.T)
+    assert (np.diag(got) == 0).all()
+
+
+def test_f2_runs_on_sampler_output():
+    """sampling() -> coordinate_assigner -> distance_matrix, the first three calls of cytopath.trajectories
+    (trajectory_inference.py:57 -> sample_clustering.py:21-71), on a golden case."""
+    from oracle import hausdorff_port as hp
+    z = load("sampling_small_clusters")
+    ad, kw = adata_from_case(z)
+    rng = np.random.default_rng(0)
+    ad.obsm["X_pca"] = rng.normal(size=(ad.shape[0], 10)).astype(np.float32)
+    np.random.seed(int(z["np_seed"]))
+    run_quiet(cytopath_b200.sampling, ad, **kw, seed=int(z["seed"]))
+    seqs = ad.uns["samples"]["cell_sequences"][:60]
+    coords = cytopath_b200.coordinate_assigner(ad, seqs, basis="pca")
+    np.testing.assert_array_equal(coords, hp.coordinate_assigner(ad.obsm["X_pca"], seqs))
+    D = run_quiet(cytopath_b200.distance_matrix, coords)
+    np.testing.assert_allclose(D, hp.distance_matrix(coords), rtol=1e-12, atol=1e-14)
