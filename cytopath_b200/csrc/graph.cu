@@ -298,7 +298,10 @@ extern "C" int cyp_graph_create(int device, int64_t n_cells, int64_t nnz, const 
 
     G_CUDA(cudaEventCreate(&e0));
     G_CUDA(cudaEventCreate(&e1));
-    const int smem_elems = 20 * 1024;                  // 160 KB of staged float64 values per CTA
+    // staging buffer: 1.5x a typical 128-row slice (so several CTAs fit an SM), at most 160 KB
+    int smem_elems = static_cast<int>(1.5 * kK1Threads * g->mean_len) + 256;
+    if (smem_elems < 2048) smem_elems = 2048;
+    if (smem_elems > 20 * 1024) smem_elems = 20 * 1024;
     const int smem_bytes = smem_elems * static_cast<int>(sizeof(double));
     const unsigned grid = static_cast<unsigned>((n_cells + kK1Threads - 1) / kK1Threads);
     G_CUDA(cudaEventRecord(e0));

@@ -401,6 +401,50 @@ def test_partition_independence_and_edge_validity_large():
     g.close()
 
 
+def test_full_size_c4_properties():
+    """BASELINE.json configs[3] at full size (1M cells, k=50, 1.25M walkers x 500 steps on one GPU): the default
+    kernel and the rows-as-stored kernel produce identical trajectories (checksum over all 625M entries), a
+    sub-range of the walkers reproduces its rows, every sampled step is an edge of T, and the C oracle agrees
+    on a sample of walkers."""
+    import ctypes
+    import torch
+    import bench
+    w = bench.WORKLOADS["c4"]
+    gph, C, roots = bench.make_graph(w, 1)
+    W, nt = w["walkers"], w["max_steps"] - 1
+    sims = -(-W // len(roots))
+    L = _lib.load()
+    g = _lib.Graph(C, _lib.CDF_EXACT)
+    d_roots = torch.tensor(roots, dtype=torch.int32, device="cuda")
+    sptr = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    outs = []
+    for variant in (0, 9016):
+        out = torch.empty((W, nt + 1), dtype=torch.int32, device="cuda")
+        miss = torch.zeros(1, dtype=torch.int64, device="cuda")
+        _lib.check(L.cyp_walk_device(g.handle, d_roots.data_ptr(), len(roots), sims, 0, W, nt, 1234, 0, None, out.data_ptr(),
+                                     miss.data_ptr(), variant, sptr))
+        torch.cuda.synchronize()
+        assert int(miss.item()) == 0
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])                                  # 16-bit-code kernel == float64-row kernel, all entries
+    weights = torch.arange(1, nt + 2, device="cuda", dtype=torch.int64)
+    checksum = (outs[0].to(torch.int64) * weights).sum(dim=1)             # per-walker checksum
+    part = torch.empty((1000, nt + 1), dtype=torch.int32, device="cuda")
+    _lib.check(L.cyp_walk_device(g.handle, d_roots.data_ptr(), len(roots), sims, 777_000, 1000, nt, 1234, 0, None, part.data_ptr(),
+                                 None, 0, sptr))
+    torch.cuda.synchronize()
+    assert torch.equal((part.to(torch.int64) * weights).sum(dim=1), checksum[777_000:778_000])
+    sample = outs[0][::2500].cpu().numpy()                                # 500 walkers
+    src, dst = sample[:, :-1].ravel(), sample[:, 1:].ravel()
+    assert (np.asarray(C[src, dst]).ravel() > 0).all()
+    np.testing.assert_array_equal(sample[:, 0], roots[(np.arange(0, W, 2500)) // sims])
+    cdf = cwalk.build_cdf(C, 1)
+    for w_id in (0, 2500, 1_247_500):
+        want = cwalk.walk(C, cdf, roots[w_id // sims:w_id // sims + 1], nt, seed=1234, walker_begin=w_id)[0]
+        np.testing.assert_array_equal(sample[w_id // 2500], want)
+    g.close()
+
+
 def test_native_rng_one_step_frequencies_chi_square():
     """With the native Philox stream the empirical one-step transition frequencies match the
     effective probabilities (bin widths of the CDF actually sampled) at p > 1e-4 per row
