@@ -1,20 +1,20 @@
-// K2, TMA flavour: the Markov-chain step loop (reference cytopath/markov_chain_sampler.py:45-51)
-// with one walker per THREAD and the CDF rows staged in shared memory by the bulk-copy engine.
+// K2, staged-row flavour (default): the Markov-chain step loop (reference
+// cytopath/markov_chain_sampler.py:45-51) with one walker per THREAD, one persistent CTA per SM, and
+// the current row of every walker staged in a private shared-memory slot.
 //
-// Why: the register flavour (walk.cu) is latency bound — a walker-step is three dependent
-// loads (row descriptor -> CDF row -> column index) and the row bytes in flight are limited by
-// registers (ncu: long-scoreboard stalls, 35 % DRAM utilisation at 40 warps/SM).  Here a row
-// in flight costs no registers: each thread issues ONE cp.async.bulk (UBLKCP) that copies its
-// whole 32-byte-aligned row (up to `slot_elems` entries) from HBM into its private shared
-// memory slot and signals the warp's mbarrier with the byte count.  A 512-thread CTA keeps
-// 512 rows (~210 KB) in flight per SM.  The first-crossing search (`u <= cdf[j]`, ties to the
-// bin, :49) then runs on shared memory: binary search when the row is known to be
-// non-decreasing (all probabilities >= 0), otherwise the literal left-to-right scan.
+// Why: the register flavour (walk.cu) is latency bound — a walker-step is a chain of dependent loads
+// and the row bytes in flight are limited by registers (ncu: 85 % long-scoreboard stalls, 35 % DRAM
+// utilisation at 40 warps/SM).  Here a row in flight costs shared memory instead: a 512..1024-thread
+// CTA keeps 512..1024 rows in flight per SM.  Per step a thread
+//   1. gets its row into the slot: either its own cp.async.bulk (UBLKCP, completion on the warp's
+//      mbarrier with the byte count) or, for small rows, the warp's cooperative 16-byte cp.async copies;
+//   2. finds the first crossing `u <= cdf[j]` (ties to the bin, :49) in shared memory: binary search
+//      when the row is non-decreasing (all probabilities >= 0), else the literal left-to-right scan;
+//      the row is the CDF as stored or its 16-bit codes (exact by construction, see "row formats");
+//   3. loads ONE 16-byte edge record: next cell, its row descriptor and its label code (:48,:51), so
+//      there is no separate descriptor or label lookup;
+//   4. computes Philox once per two steps and stores the trajectory as one int4 per four steps.
 // Rows longer than a slot are streamed through it in chunks.
-//
-// Per step and thread: one bulk copy, ~log2(len) LDS, one 16-byte edge-record load (next cell +
-// its row descriptor, so no separate descriptor lookup), one Philox call every second step and
-// a 16-byte trajectory store every fourth step.
 #include <cstdio>
 #include <type_traits>
 
