@@ -276,7 +276,10 @@ __global__ void __launch_bounds__(1024, 1) walk_tma_kernel(const WalkParams p, c
 // stores evict_first through createpolicy descriptors): identical timings on every workload;
 // (2) two CTAs of 768 threads per SM for the cp.async flavour (needs <= 42 registers): slower than
 // one CTA of 1024 threads (29.9 vs 32.9 G walker-steps/s at C4);
-// (3) (profiles/r01_sweep4_pingpong_*.log) a ping-pong flavour with two walkers per
+// (3) rotating the 16-byte chunks of every slot per lane (cp.async flavour) and padding bulk slots to an
+// odd number of 16-byte units, to spread the binary-search probes over the shared-memory banks: no gain
+// (36.8 vs 38.0 G walker-steps/s at C4), so the shared-memory pipe is not the limit either;
+// (4) (profiles/r01_sweep4_pingpong_*.log) a ping-pong flavour with two walkers per
 // thread sharing one slot, so that one walker's row copy overlaps the other's edge-record load.
 // Same throughput as this kernel at equal thread counts (19.1 vs 19.0 G walker-steps/s at C4): the
 // memory system, not the per-thread dependency chain, is the limit at this point.
