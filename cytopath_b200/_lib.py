@@ -57,9 +57,15 @@ def load():
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
-        raise ImportError(
-            "cytopath_b200: %s not found. Build it with `python -m cytopath_b200.build` "
-            "(needs nvcc; sm_100a). There is no CPU fallback." % LIB_PATH)
+        # a source checkout without the built library: compile it in tree (nvcc, sm_100a) — a build
+        # step, not a fallback; if nvcc is missing this raises and so does every entry point
+        try:
+            from .build import build_library
+            build_library()
+        except Exception as exc:
+            raise ImportError(
+                "cytopath_b200: %s not found and building it failed (%s). Build it with "
+                "`python -m cytopath_b200.build` (needs nvcc; sm_100a). There is no CPU fallback." % (LIB_PATH, exc))
     L = ctypes.CDLL(LIB_PATH)
     i32, i64, u32, u64 = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_uint64
     vp, ci = ctypes.c_void_p, ctypes.c_int

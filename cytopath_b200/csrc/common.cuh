@@ -11,7 +11,6 @@
 namespace cyp {
 
 // ---- error plumbing ---------------------------------------------------------------
-void set_error(const std::string &msg);
 int fail(int code, const std::string &msg);
 
 #define CYP_CUDA(expr)                                                                        \

@@ -16,7 +16,6 @@ namespace cyp {
 
 static thread_local std::string g_last_error;
 
-void set_error(const std::string &msg) { g_last_error = msg; }
 int fail(int code, const std::string &msg) {
     g_last_error = msg;
     return code;

@@ -262,7 +262,6 @@ extern "C" int cyp_walk(const cyp_graph *g, const int32_t *h_root_cells, int64_t
     unsigned long long *d_miss = nullptr;
     const size_t seq_bytes = sizeof(int32_t) * static_cast<size_t>(n_walkers) * (n_transitions + 1);
     int rc = CYP_OK;
-    cudaError_t e = cudaSuccess;
     auto chk = [&](cudaError_t err, const char *what) {
         if (err != cudaSuccess && rc == CYP_OK)
             rc = fail(err == cudaErrorMemoryAllocation ? CYP_E_NOMEM : CYP_E_CUDA, std::string("cyp_walk: ") + what + ": " + cudaGetErrorString(err));
@@ -289,7 +288,6 @@ extern "C" int cyp_walk(const cyp_graph *g, const int32_t *h_root_cells, int64_t
             }
         }
     }
-    (void)e;
     dev_free(d_roots);
     dev_free(d_seq);
     dev_free(d_u);
