@@ -283,6 +283,42 @@ def test_undirected_simulations_cuda_matches_reference(name):
     check_undirected(name)
 
 
+def test_sampling_uniforms_hook_equals_native_stream():
+    """`uniforms=` (the hook that feeds the reference's numpy rule and this kernel the same numbers) with the
+    Philox stream as the source gives exactly what the in-kernel Philox gives."""
+    z = load("sampling_small_clusters")
+    seed = int(z["seed"])
+    outs = []
+    for hook in (None, lambda rnd, w0, n, nt: philox.walker_uniforms(seed, rnd, w0, n, nt)):
+        ad, kw = adata_from_case(z)
+        np.random.seed(int(z["np_seed"]))
+        run_quiet(cytopath_b200.sampling, ad, **kw, seed=seed, uniforms=hook)
+        outs.append(ad.uns["samples"]["cell_sequences"])
+    np.testing.assert_array_equal(outs[0], outs[1])
+    np.testing.assert_array_equal(outs[0], z["cell_sequences"])
+
+
+def test_k2_randomised_shapes_vs_oracle():
+    """40 random (graph, mode, roots, walkers, steps, seed, round, shard) combinations through the default kernel."""
+    rng = np.random.default_rng(2024)
+    for trial in range(40):
+        n = int(rng.integers(20, 600))
+        max_nnz = int(rng.integers(1, 90))
+        C = sp.canonical_csr(synth.random_sparse_rows(n=n, max_nnz=min(max_nnz, n - 2), seed=trial, messy=bool(trial % 2)))
+        mode = int(rng.integers(2))
+        g = _lib.Graph(C, mode)
+        cdf = cwalk.build_cdf(C, mode)
+        roots = rng.choice(n, size=int(rng.integers(1, 9)), replace=True)
+        sims, nt = int(rng.integers(1, 70)), int(rng.integers(0, 45))
+        seed, rnd = int(rng.integers(2**62)), int(rng.integers(100))
+        total = len(roots) * sims
+        a = int(rng.integers(0, total)); b = int(rng.integers(a, total + 1))
+        want = cwalk.walk(C, cdf, np.repeat(roots, sims)[a:b], nt, seed=seed, round_idx=rnd, walker_begin=a, strict=False)
+        got = g.walk(roots, sims, nt, seed=seed, round_idx=rnd, walker_begin=a, n_walkers=b - a, strict=False)
+        np.testing.assert_array_equal(got, want, err_msg="trial %d n=%d nnz<=%d mode=%d" % (trial, n, max_nnz, mode))
+        g.close()
+
+
 def make_session(C, g, roots, code, min_clusters, end_cells, max_steps, unique, seed):
     n = C.shape[0]
     slot = np.full(n, -1, dtype=np.int32)
