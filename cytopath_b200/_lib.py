@@ -20,7 +20,7 @@ E_NOCROSSING = -4
 
 EXPORTS = [
     "cyp_version", "cyp_last_error", "cyp_device_count",
-    "cyp_graph_create", "cyp_graph_destroy", "cyp_graph_info", "cyp_graph_fetch_cdf", "cyp_graph_build_ms",
+    "cyp_graph_create", "cyp_graph_create_f32", "cyp_graph_row_sum_range", "cyp_graph_destroy", "cyp_graph_info", "cyp_graph_fetch_cdf", "cyp_graph_build_ms",
     "cyp_power_iteration", "cyp_walk", "cyp_walk_device", "cyp_walk_variant_name", "cyp_transition_scores",
     "cyp_session_create", "cyp_session_destroy", "cyp_session_round", "cyp_session_rows",
     "cyp_session_fetch_index", "cyp_session_fetch_rows", "cyp_session_round_records",
@@ -74,6 +74,8 @@ def load():
     L.cyp_last_error.restype = ctypes.c_char_p
     L.cyp_device_count.argtypes = [P(ci)]
     L.cyp_graph_create.argtypes = [ci, i64, i64, vp, vp, vp, ci, P(vp)]
+    L.cyp_graph_create_f32.argtypes = [ci, i64, i64, vp, vp, vp, ci, P(vp)]
+    L.cyp_graph_row_sum_range.argtypes = [vp, P(ctypes.c_double), P(ctypes.c_double)]
     L.cyp_graph_destroy.argtypes = [vp]
     L.cyp_graph_info.argtypes = [vp, P(i64), P(i64), P(i32), P(ci), P(ci), P(i64)]
     L.cyp_graph_fetch_cdf.argtypes = [vp, vp]
@@ -177,15 +179,17 @@ class Graph:
     `matrix_prep` (markov_chain_sampler.py:11-31) returns, minus the ELL padding."""
 
     def __init__(self, C, cdf_mode: int = CDF_REFERENCE, device: int = 0):
-        """C: canonical scipy CSR (sorted columns, no duplicates, no explicit zeros), float64."""
+        """C: canonical scipy CSR (sorted columns, no duplicates, no explicit zeros), float64 or float32
+        (float32 values are uploaded as they are and widened on the device: no host copy)."""
         require_device(device)
         self._h = ctypes.c_void_p()
         self.indptr = np.ascontiguousarray(C.indptr, dtype=np.int64)
         indices = np.ascontiguousarray(C.indices, dtype=np.int32)
-        data = np.ascontiguousarray(C.data, dtype=np.float64)
+        f32 = C.data.dtype == np.float32
+        data = np.ascontiguousarray(C.data, dtype=np.float32 if f32 else np.float64)
         self.n, self.nnz, self.cdf_mode, self.device = int(C.shape[0]), int(data.shape[0]), cdf_mode, device
-        check(load().cyp_graph_create(device, self.n, self.nnz, ptr(self.indptr), ptr(indices), ptr(data),
-                                      cdf_mode, ctypes.byref(self._h)))
+        create = load().cyp_graph_create_f32 if f32 else load().cyp_graph_create
+        check(create(device, self.n, self.nnz, ptr(self.indptr), ptr(indices), ptr(data), cdf_mode, ctypes.byref(self._h)))
 
     @property
     def handle(self):
@@ -197,6 +201,11 @@ class Graph:
         check(load().cyp_graph_info(self._h, n, nnz, mx, mode, dev, b))
         return dict(n_cells=n.value, nnz=nnz.value, max_row_nnz=mx.value, cdf_mode=mode.value,
                     device=dev.value, device_bytes=b.value)
+
+    def row_sum_range(self):
+        lo, hi = ctypes.c_double(), ctypes.c_double()
+        check(load().cyp_graph_row_sum_range(self._h, ctypes.byref(lo), ctypes.byref(hi)))
+        return lo.value, hi.value
 
     def build_ms(self) -> float:
         ms = ctypes.c_float()

@@ -120,5 +120,6 @@ struct cyp_graph {
     int64_t *d_row_ptr = nullptr;    // [n+1] original CSR offsets (fetch_cdf un-pads with it)
     int64_t device_bytes = 0;
     float build_ms = 0.f;
+    double row_sum_min = 0.0, row_sum_max = 0.0;     // range of the float64 row sums (normalisation check)
     mutable uint64_t labels_owner = 0;   // id of the session whose label codes are in d_edge[].code (0 = none)
 };

@@ -6,6 +6,8 @@
 // Reference mode then narrows to float32 (:23,:28) and rounds to 3 decimals with
 // rintf(c*1000)/1000 in float32 (np.round(decimals=3), :31).  Output goes to the
 // sector-aligned row layout described in common.cuh.
+#include <algorithm>
+#include <cfloat>
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -77,12 +79,13 @@ __device__ __forceinline__ uint16_t cdf_code(double acc, int *flags) {
     }
 }
 
-template <typename CdfT>
+template <typename CdfT, typename ValT>
 __global__ void __launch_bounds__(kK1Threads)
 build_cdf_kernel(int64_t n, const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ raw_col,
-                 const double *__restrict__ raw_val, const RowInfo *__restrict__ rows, int align_elems,
+                 const ValT *__restrict__ raw_val, const RowInfo *__restrict__ rows, int align_elems,
                  int64_t total_units, CdfT *__restrict__ cdf, uint16_t *__restrict__ q16, int32_t *__restrict__ col,
-                 EdgeRec *__restrict__ edge, double *__restrict__ val, int smem_elems, int *__restrict__ negative_flag) {
+                 EdgeRec *__restrict__ edge, double *__restrict__ val, int smem_elems, int *__restrict__ negative_flag,
+                 double *__restrict__ block_sum_min, double *__restrict__ block_sum_max) {
     extern __shared__ double s_val[];                 // [smem_elems] raw values, then cumulative sums in place
     __shared__ int64_t s_src[kK1Threads + 1];         // CSR offsets of the CTA's rows
     __shared__ int64_t s_dst[kK1Threads + 1];         // padded offsets of the CTA's rows
@@ -97,10 +100,11 @@ build_cdf_kernel(int64_t n, const int64_t *__restrict__ row_ptr, const int32_t *
     __syncthreads();
     const int64_t src0 = s_src[0], cnt = s_src[nrows] - src0;
     const int64_t dst0 = s_dst[0], dcnt = s_dst[nrows] - dst0;
+    double row_sum = 0.0;                              // this thread's row: last CDF value before narrowing
     if (cnt <= smem_elems) {
         bool neg = false;
         for (int64_t i = threadIdx.x; i < cnt; i += kK1Threads) {
-            const double v = raw_val[src0 + i];
+            const double v = static_cast<double>(raw_val[src0 + i]);      // float32 input widens exactly
             neg |= v < 0.0;
             s_val[i] = v;
         }
@@ -113,6 +117,7 @@ build_cdf_kernel(int64_t n, const int64_t *__restrict__ row_ptr, const int32_t *
                 acc = __dadd_rn(acc, s_val[j]);        // sequential: no re-association, no FMA
                 s_val[j] = acc;
             }
+            row_sum = acc;
         }
         __syncthreads();
         for (int64_t p = threadIdx.x; p < dcnt; p += kK1Threads) {
@@ -131,7 +136,7 @@ build_cdf_kernel(int64_t n, const int64_t *__restrict__ row_ptr, const int32_t *
                 q16[dst0 + p] = cdf_code<CdfT>(s_val[q - src0], negative_flag);
                 col[dst0 + p] = c;
                 edge[dst0 + p] = EdgeRec{c, tr.off_units, tr.len, 0u};
-                val[dst0 + p] = raw_val[q];
+                val[dst0 + p] = static_cast<double>(raw_val[q]);
             } else {                                   // padding never matches: u >= 0 > -1
                 cdf[dst0 + p] = static_cast<CdfT>(-1);
                 q16[dst0 + p] = 0;
@@ -146,7 +151,7 @@ build_cdf_kernel(int64_t n, const int64_t *__restrict__ row_ptr, const int32_t *
         const int64_t len_pad = (len + align_elems - 1) / align_elems * align_elems;
         double acc = 0.0;
         for (int64_t j = 0; j < len; ++j) {
-            const double v = raw_val[a + j];
+            const double v = static_cast<double>(raw_val[a + j]);
             if (v < 0.0) atomicOr(negative_flag, 1);
             acc = __dadd_rn(acc, v);
             const int32_t c = raw_col[a + j];
@@ -157,6 +162,7 @@ build_cdf_kernel(int64_t n, const int64_t *__restrict__ row_ptr, const int32_t *
             edge[dst + j] = EdgeRec{c, tr.off_units, tr.len, 0u};
             val[dst + j] = v;
         }
+        row_sum = acc;
         for (int64_t j = len; j < len_pad; ++j) {
             cdf[dst + j] = static_cast<CdfT>(-1);
             q16[dst + j] = 0;
@@ -164,6 +170,21 @@ build_cdf_kernel(int64_t n, const int64_t *__restrict__ row_ptr, const int32_t *
             edge[dst + j] = EdgeRec{-1, 0u, 0u, 0u};
             val[dst + j] = 0.0;
         }
+    }
+    // range of the row sums of this CTA (the normalisation check of markov_chain_sampler.py:182-187 runs on them)
+    __shared__ double s_min[kK1Threads / 32], s_max[kK1Threads / 32];
+    __syncthreads();
+    double lo = (threadIdx.x < nrows) ? row_sum : DBL_MAX, hi = (threadIdx.x < nrows) ? row_sum : -DBL_MAX;
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) { s_min[threadIdx.x >> 5] = lo; s_max[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kK1Threads / 32; ++w) { lo = fmin(lo, s_min[w]); hi = fmax(hi, s_max[w]); }
+        block_sum_min[blockIdx.x] = lo;
+        block_sum_max[blockIdx.x] = hi;
     }
 }
 
@@ -205,8 +226,8 @@ static void graph_free(cyp_graph *g) {
     delete g;
 }
 
-extern "C" int cyp_graph_create(int device, int64_t n_cells, int64_t nnz, const int64_t *h_row_ptr,
-                                const int32_t *h_col, const double *h_val, int cdf_mode, cyp_graph **out) {
+static int graph_create_impl(int device, int64_t n_cells, int64_t nnz, const int64_t *h_row_ptr, const int32_t *h_col,
+                             const void *h_val, bool val_f32, int cdf_mode, cyp_graph **out) {
     CYP_REQUIRE(out != nullptr, "cyp_graph_create: out is NULL");
     *out = nullptr;
     CYP_REQUIRE(n_cells > 0 && nnz > 0, "cyp_graph_create: empty matrix");
@@ -252,13 +273,17 @@ extern "C" int cyp_graph_create(int device, int64_t n_cells, int64_t nnz, const 
     const size_t cdf_elem = (cdf_mode == CYP_CDF_EXACT) ? 8 : 4;
 
     int32_t *d_raw_col = nullptr;
-    double *d_raw_val = nullptr;
+    void *d_raw_val = nullptr;
+    double *d_block_min = nullptr, *d_block_max = nullptr;
     int *d_flag = nullptr;
+    const size_t val_elem = val_f32 ? sizeof(float) : sizeof(double);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     auto cleanup = [&](int code, const std::string &msg) {
         dev_free(d_raw_col);
         dev_free(d_raw_val);
         dev_free(d_flag);
+        dev_free(d_block_min);
+        dev_free(d_block_max);
         if (e0) cudaEventDestroy(e0);
         if (e1) cudaEventDestroy(e1);
         graph_free(g);
@@ -279,7 +304,7 @@ extern "C" int cyp_graph_create(int device, int64_t n_cells, int64_t nnz, const 
     G_CUDA(dev_alloc(&g->d_edge, sizeof(EdgeRec) * g->padded));
     G_CUDA(dev_alloc(&g->d_val, sizeof(double) * g->padded));
     G_CUDA(dev_alloc(&d_raw_col, sizeof(int32_t) * nnz));
-    G_CUDA(dev_alloc(&d_raw_val, sizeof(double) * nnz));
+    G_CUDA(dev_alloc(&d_raw_val, val_elem * nnz));
     G_CUDA(dev_alloc(&d_flag, sizeof(int)));
     G_CUDA(cudaMemset(d_flag, 0, sizeof(int)));
     g->device_bytes = sizeof(RowInfo) * n_cells + sizeof(int64_t) * (n_cells + 1) +
@@ -287,7 +312,7 @@ extern "C" int cyp_graph_create(int device, int64_t n_cells, int64_t nnz, const 
     G_CUDA(cudaMemcpy(g->d_row, rows.data(), sizeof(RowInfo) * n_cells, cudaMemcpyHostToDevice));
     G_CUDA(cudaMemcpy(g->d_row_ptr, h_row_ptr, sizeof(int64_t) * (n_cells + 1), cudaMemcpyHostToDevice));
     G_CUDA(cudaMemcpy(d_raw_col, h_col, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice));
-    G_CUDA(cudaMemcpy(d_raw_val, h_val, sizeof(double) * nnz, cudaMemcpyHostToDevice));
+    G_CUDA(cudaMemcpy(d_raw_val, h_val, val_elem * nnz, cudaMemcpyHostToDevice));
     // slack region: never-matching padding
     G_CUDA(cudaMemset(static_cast<char *>(g->d_cdf) + cdf_elem * units * A, 0xFF, cdf_elem * 4 * A));   // NaN: u <= NaN is false
     G_CUDA(cudaMemset(g->d_q16 + units * A, 0, sizeof(uint16_t) * 4 * A));
@@ -303,18 +328,22 @@ extern "C" int cyp_graph_create(int device, int64_t n_cells, int64_t nnz, const 
     if (smem_elems > 20 * 1024) smem_elems = 20 * 1024;
     const int smem_bytes = smem_elems * static_cast<int>(sizeof(double));
     const unsigned grid = static_cast<unsigned>((n_cells + kK1Threads - 1) / kK1Threads);
+    G_CUDA(dev_alloc(&d_block_min, sizeof(double) * grid));
+    G_CUDA(dev_alloc(&d_block_max, sizeof(double) * grid));
     G_CUDA(cudaEventRecord(e0));
+#define K1_LAUNCH(CDFT, VALT)                                                                                               \
+    do {                                                                                                                    \
+        G_CUDA(cudaFuncSetAttribute(build_cdf_kernel<CDFT, VALT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); \
+        build_cdf_kernel<CDFT, VALT><<<grid, kK1Threads, smem_bytes>>>(                                                     \
+            n_cells, g->d_row_ptr, d_raw_col, static_cast<const VALT *>(d_raw_val), g->d_row, A, units,                     \
+            static_cast<CDFT *>(g->d_cdf), g->d_q16, g->d_col, g->d_edge, g->d_val, smem_elems, d_flag, d_block_min, d_block_max); \
+    } while (0)
     if (cdf_mode == CYP_CDF_EXACT) {
-        G_CUDA(cudaFuncSetAttribute(build_cdf_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        build_cdf_kernel<double><<<grid, kK1Threads, smem_bytes>>>(n_cells, g->d_row_ptr, d_raw_col, d_raw_val, g->d_row, A,
-                                                                   units, static_cast<double *>(g->d_cdf), g->d_q16,
-                                                                   g->d_col, g->d_edge, g->d_val, smem_elems, d_flag);
+        if (val_f32) K1_LAUNCH(double, float); else K1_LAUNCH(double, double);
     } else {
-        G_CUDA(cudaFuncSetAttribute(build_cdf_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        build_cdf_kernel<float><<<grid, kK1Threads, smem_bytes>>>(n_cells, g->d_row_ptr, d_raw_col, d_raw_val, g->d_row, A,
-                                                                  units, static_cast<float *>(g->d_cdf), g->d_q16,
-                                                                  g->d_col, g->d_edge, g->d_val, smem_elems, d_flag);
+        if (val_f32) K1_LAUNCH(float, float); else K1_LAUNCH(float, double);
     }
+#undef K1_LAUNCH
     G_CUDA(cudaGetLastError());
     G_CUDA(cudaEventRecord(e1));
     G_CUDA(cudaEventSynchronize(e1));
@@ -325,12 +354,43 @@ extern "C" int cyp_graph_create(int device, int64_t n_cells, int64_t nnz, const 
     g->q16_ok = (negative == 0) ? 1 : 0;
     dev_free(d_flag);
     d_flag = nullptr;
+    {
+        std::vector<double> bmin(grid), bmax(grid);
+        G_CUDA(cudaMemcpy(bmin.data(), d_block_min, sizeof(double) * grid, cudaMemcpyDeviceToHost));
+        G_CUDA(cudaMemcpy(bmax.data(), d_block_max, sizeof(double) * grid, cudaMemcpyDeviceToHost));
+        g->row_sum_min = bmin[0];
+        g->row_sum_max = bmax[0];
+        for (unsigned b = 1; b < grid; ++b) {
+            g->row_sum_min = std::min(g->row_sum_min, bmin[b]);
+            g->row_sum_max = std::max(g->row_sum_max, bmax[b]);
+        }
+    }
+    dev_free(d_block_min);
+    dev_free(d_block_max);
+    d_block_min = d_block_max = nullptr;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     dev_free(d_raw_col);
     dev_free(d_raw_val);
 #undef G_CUDA
     *out = g;
+    return CYP_OK;
+}
+
+extern "C" int cyp_graph_create(int device, int64_t n_cells, int64_t nnz, const int64_t *h_row_ptr,
+                                const int32_t *h_col, const double *h_val, int cdf_mode, cyp_graph **out) {
+    return graph_create_impl(device, n_cells, nnz, h_row_ptr, h_col, h_val, false, cdf_mode, out);
+}
+
+extern "C" int cyp_graph_create_f32(int device, int64_t n_cells, int64_t nnz, const int64_t *h_row_ptr,
+                                    const int32_t *h_col, const float *h_val, int cdf_mode, cyp_graph **out) {
+    return graph_create_impl(device, n_cells, nnz, h_row_ptr, h_col, h_val, true, cdf_mode, out);
+}
+
+extern "C" int cyp_graph_row_sum_range(const cyp_graph *g, double *min_sum, double *max_sum) {
+    CYP_REQUIRE(g != nullptr && min_sum != nullptr && max_sum != nullptr, "cyp_graph_row_sum_range: NULL argument");
+    *min_sum = g->row_sum_min;
+    *max_sum = g->row_sum_max;
     return CYP_OK;
 }
 

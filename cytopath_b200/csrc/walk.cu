@@ -200,6 +200,11 @@ WalkVariant pick_walk_variant(const cyp_graph *g, int variant) {
 }
 
 int launch_walk(const cyp_graph *g, const WalkParams &p, WalkMode mode, int variant, cudaStream_t stream) {
+    if (variant >= 9400) {        // paired flavour: on request only (same throughput as the default: K2 is bound by the memory system)
+        const int rc = launch_walk_pp(g, p, mode, variant, stream);
+        if (rc != kPpNotApplicable) return rc;
+        return fail(CYP_E_INVALID, "launch_walk: the paired kernel (variant 94xx) does not apply to this graph");
+    }
     if (variant == 0 || variant >= 9000) return launch_walk_tma(g, p, mode, variant, stream);
     const WalkVariant v = pick_walk_variant(g, variant);
     if (g->cdf_mode == CYP_CDF_EXACT) return launch_variant<double>(p, v, mode, stream);
@@ -213,7 +218,11 @@ using namespace cyp;
 extern "C" const char *cyp_walk_variant_name(const cyp_graph *g, int variant) {
     static thread_local char buf[96];
     if (!g) return "";
-    if (variant == 0 || variant >= 9000) return walk_tma_name(g, variant);
+    if (variant >= 9400) {
+        const char *name = walk_pp_name(g, variant);
+        return name ? name : "not applicable";
+    }
+    if (variant >= 9000 || variant == 0) return walk_tma_name(g, variant);
     const WalkVariant v = pick_walk_variant(g, variant);
     snprintf(buf, sizeof(buf), "walk_kernel<%s,lanes=%d,unroll=%d>", g->cdf_mode == CYP_CDF_EXACT ? "f64" : "f32", v.lanes,
              v.unroll);

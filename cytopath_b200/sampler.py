@@ -93,6 +93,9 @@ def _canonical_csr(M) -> sparse.csr_matrix:
     re-sparsifies (:14), which sorts columns, sums duplicates (in the input dtype) and drops
     explicit zeros.  Same result here without the n x n array."""
     if sparse.issparse(M):
+        if (M.format == "csr" and M.dtype in (np.float32, np.float64) and M.has_canonical_format
+                and np.count_nonzero(M.data) == M.nnz):
+            return M            # already canonical: used in place, never modified (float32 is widened on the device)
         C = sparse.csr_matrix(M, copy=True)
         if not C.has_canonical_format:
             C.sum_duplicates()
@@ -108,7 +111,7 @@ def _row_sums(C) -> np.ndarray:
     out = np.zeros(C.shape[0], dtype=np.float64)
     nz = np.flatnonzero(np.diff(C.indptr))
     if nz.size:
-        out[nz] = np.add.reduceat(C.data, C.indptr[nz])
+        out[nz] = np.add.reduceat(C.data.astype(np.float64, copy=False), C.indptr[nz])
     return out
 
 
@@ -212,16 +215,41 @@ def sampling(data, auto_adjust=True, matrix_key="T_forward", cluster_key="louvai
     except Exception:
         raise ValueError("Transition matrix must be of shape num_cells x num_cells")
 
+    world = _World(dist)
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0")) if world.size > 1 else 0
+    backend = _backend if _backend is not None else _lib
+
     C = _canonical_csr(M)
     n = C.shape[0]
-    row_sums = _row_sums(C)
-    if normalize:
+    if normalize:                                                          # :176-180
+        row_sums = _row_sums(C)
         with np.errstate(divide="ignore", invalid="ignore"):
-            C = sparse.csr_matrix((C.data / np.repeat(row_sums, np.diff(C.indptr)), C.indices, C.indptr), shape=C.shape)
+            C = sparse.csr_matrix((C.data.astype(np.float64, copy=False) / np.repeat(row_sums, np.diff(C.indptr)),
+                                   C.indices, C.indptr), shape=C.shape)
         C.eliminate_zeros()
-    elif not (row_sums.max() <= 1.0 + 1e-3 and row_sums.min() >= 1.0 - 1e-3):
-        raise ValueError("Transition matrix has not been normalized. Either pass normalize==True or provide a row sum normalized matrix.")
+    # a1 (K1): upload + CDF build.  The row sums of the normalisation check (:181-187) come back from the
+    # same kernel, so the host never walks the 50M-entry value array.
+    graph = backend.Graph(C, _CDF_MODES[cdf_mode], device)
+    session = None
+    try:
+        if not normalize:
+            lo, hi = graph.row_sum_range() if hasattr(graph, "row_sum_range") else (lambda r: (r.min(), r.max()))(_row_sums(C))
+            if not (hi <= 1.0 + 1e-3 and lo >= 1.0 - 1e-3):
+                raise ValueError("Transition matrix has not been normalized. Either pass normalize==True or provide a row sum normalized matrix.")
+        return _sampling_on_graph(adata, copy, world, backend, graph, C, device, auto_adjust, matrix_key, cluster_key, max_steps,
+                                  min_sim_ratio, rounds_limit, traj_number, sim_number, end_point_probability,
+                                  root_cell_probability, end_points, root_cells, end_clusters, root_clusters, min_clusters,
+                                  max_iter, tol, unique, seed, uniforms)
+    finally:
+        graph.close()
 
+
+def _sampling_on_graph(adata, copy, world, backend, graph, C, device, auto_adjust, matrix_key, cluster_key, max_steps,
+                       min_sim_ratio, rounds_limit, traj_number, sim_number, end_point_probability, root_cell_probability,
+                       end_points, root_cells, end_clusters, root_clusters, min_clusters, max_iter, tol, unique, seed, uniforms):
+    """Everything of `sampling` after the transition matrix has been accepted (:189-412)."""
+    n = C.shape[0]
     try:
         adata.obs[cluster_key]
         assert adata.obs[cluster_key].dtype == "category"
@@ -271,18 +299,14 @@ def sampling(data, auto_adjust=True, matrix_key="T_forward", cluster_key="louvai
         print("Number of required simulations per end point (traj_number) set to {}".format(traj_number))
         sim_number = math.ceil(traj_number * len(end_clusters_) * np.log2(n_roots + 1))
         print("Number of initial simulations (sim_number) set to {}".format(sim_number))
-        auto_device = device if device is not None else int(os.environ.get("LOCAL_RANK", "0"))
         max_steps = _auto_max_steps(adata.uns[matrix_key],
                                     (adata.obs["root_cells"] / adata.obs["root_cells"].sum()).values,
                                     (adata.obs["end_points"] / adata.obs["end_points"].sum()).values, max_iter, tol,
-                                    _backend if _backend is not None else _lib, auto_device)
+                                    backend, device)
         print("Number of initial simulation steps (max_steps) set to {}".format(max_steps))
     max_steps = int(max_steps)
 
     # -- device-side state
-    world = _World(dist)
-    if device is None:
-        device = int(os.environ.get("LOCAL_RANK", "0")) if world.size > 1 else 0
     trunc = np.array([c[:8] for c in clusters], dtype="U8")     # labels are stored into a U8 array (:39,:51)
     code_names, cell_code = np.unique(trunc, return_inverse=True)
     # end-point slots: one slot per distinct end-point cell; the reference scans end points in
@@ -291,8 +315,6 @@ def sampling(data, auto_adjust=True, matrix_key="T_forward", cluster_key="louvai
     end_slot_of_cell = np.full(n, -1, dtype=np.int32)
     end_slot_of_cell[slot_cells] = np.arange(len(slot_cells), dtype=np.int32)
 
-    backend = _backend if _backend is not None else _lib
-    graph = backend.Graph(C, _CDF_MODES[cdf_mode], device)
     session = backend.Session(graph, roots, cell_code, len(code_names), int(min_clusters), end_slot_of_cell,
                               len(slot_cells), max_steps, bool(unique), int(seed))
     try:
@@ -301,7 +323,6 @@ def sampling(data, auto_adjust=True, matrix_key="T_forward", cluster_key="louvai
                            unique, uniforms, device)
     finally:
         session.close()
-        graph.close()
 
 
 def _run_rounds(adata, copy, world, graph, session, roots, end_cells, end_slot_of_point, end_point_clusters,

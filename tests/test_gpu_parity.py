@@ -71,6 +71,48 @@ def test_k1_ragged_rows_with_staging_overflow():
         g.close()
 
 
+@pytest.mark.parametrize("mode,omode", MODES)
+def test_k1_float32_values_equal_the_widened_matrix(mode, omode):
+    """scvelo stores T_forward as float32; the reference widens it with np.float64(toarray()) (:168).
+    cyp_graph_create_f32 uploads the float32 values and widens on the device: same CDF bits, and the
+    row-sum range the kernel reports equals the left-to-right float64 sums."""
+    g32 = synth.branching_graph(n=1500, k=20, n_branches=3, seed=9, workers=1).T.astype(np.float32)
+    C32 = sp.canonical_csr(g32).astype(np.float32)
+    assert C32.dtype == np.float32
+    C64 = C32.astype(np.float64)
+    a, b = _lib.Graph(C32, mode), _lib.Graph(C64, mode)
+    np.testing.assert_array_equal(a.cdf(), b.cdf())
+    np.testing.assert_array_equal(a.cdf(), cwalk.build_cdf(C64, omode))
+    sums = np.array([np.cumsum(C64.data[s:e])[-1] for s, e in zip(C64.indptr[:-1], C64.indptr[1:])])
+    assert a.row_sum_range() == b.row_sum_range() == (sums.min(), sums.max())
+    roots = np.arange(40)
+    np.testing.assert_array_equal(a.walk(roots, 20, 30, seed=3), b.walk(roots, 20, 30, seed=3))
+    a.close(); b.close()
+
+
+def test_sampling_accepts_float32_matrix_in_place_and_checks_normalisation_on_device():
+    z = load("sampling_small_clusters")
+    ad, kw = adata_from_case(z)
+    T32 = sp.canonical_csr(ad.uns[kw.get("matrix_key", "T_forward")]).astype(np.float32)
+    T32.sort_indices()
+    before = T32.data.copy()
+    ad.uns[kw.get("matrix_key", "T_forward")] = T32
+    ad2, _ = adata_from_case(z)
+    ad2.uns[kw.get("matrix_key", "T_forward")] = T32.astype(np.float64)
+    for a in (ad, ad2):
+        np.random.seed(1)
+        run_quiet(cytopath_b200.sampling, a, **kw, seed=5)
+    np.testing.assert_array_equal(ad.uns["samples"]["cell_sequences"], ad2.uns["samples"]["cell_sequences"])
+    np.testing.assert_array_equal(T32.data, before)                       # the caller's matrix is never modified
+    bad = T32.copy()
+    bad.data[bad.indptr[7]:bad.indptr[8]] *= 1.01
+    ad.uns[kw.get("matrix_key", "T_forward")] = bad
+    with pytest.raises(ValueError, match="has not been normalized"):
+        run_quiet(cytopath_b200.sampling, ad, **kw, seed=5)
+    kw2 = dict(kw, normalize=True)
+    run_quiet(cytopath_b200.sampling, ad, **kw2, seed=5)
+
+
 # ---- K4 ---------------------------------------------------------------------------------
 def test_k4_power_iteration_matches_scipy():
     """eps history of iterate_state_probability (:62-87): the state vector is bit-equal to scipy's
@@ -144,6 +186,21 @@ def test_k2_bit_exact_vs_oracle_all_variants(gname, mode, omode):
     # TMA flavour: 128 / 256 / 512 / 1024 threads per CTA (1024 forces rows to stream through small slots)
     for variant in (9004, 9008, 9016, 9032, 9204, 9216, 9232, 9304, 9316, 9332):     # 90xx: CDF rows as stored; 92xx: 16-bit CDF codes
         for n_t in (nt, 62):                                  # 63 columns: scalar stores; 64 columns: int4 stores
+            wnt = want if n_t == nt else cwalk.walk(C, cdf, np.repeat(roots, sims), n_t, seed=seed, round_idx=rnd, strict=False)
+            out = torch.full((len(roots) * sims, n_t + 1), -7, dtype=torch.int32, device="cuda")
+            miss = torch.zeros(1, dtype=torch.int64, device="cuda")
+            _lib.check(L.cyp_walk_device(g.handle, d_roots.data_ptr(), len(roots), sims, 0, len(roots) * sims, n_t, seed, rnd,
+                                         None, out.data_ptr(), miss.data_ptr(), variant,
+                                         ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            torch.cuda.synchronize()
+            np.testing.assert_array_equal(out.cpu().numpy(), wnt, err_msg="%s nt=%d" % (g.variant_name(variant), n_t))
+    # paired flavour (two walkers per thread): 32 / 128 / 512 / 1024 threads per CTA; 62, 63 and 64 columns
+    for variant in (9401, 9404, 9416, 9432):
+        if g.variant_name(variant) == "not applicable":
+            assert gname == "ragged"                          # negative probabilities: no 16-bit codes
+            continue
+        assert "walk_pp_kernel" in g.variant_name(variant)
+        for n_t in (nt, 62, 63):
             wnt = want if n_t == nt else cwalk.walk(C, cdf, np.repeat(roots, sims), n_t, seed=seed, round_idx=rnd, strict=False)
             out = torch.full((len(roots) * sims, n_t + 1), -7, dtype=torch.int32, device="cuda")
             miss = torch.zeros(1, dtype=torch.int64, device="cuda")
