@@ -98,6 +98,28 @@ struct EdgeRec {
     uint32_t code;        // target's cluster-label code for the session that last labelled the graph
 };
 
+// ---- fused rows ("v2" layout, what the default step kernel walk_v2.cu reads) --------------------
+// One block of 32-byte sectors per cell holding everything a step needs except, sometimes, the target:
+//   +0  int32  cell            the cell id (trajectory column; the walker learns it when the row arrives)
+//   +4  uint16 len             entries in the row
+//   +6  uint8  label           code of the cell's truncated cluster label (written per session)
+//   +7  uint8  m               number of inlined targets
+//   +8  uint64 inline_mask     bit j set: the target of entry j is inlined (only entries j < 64 qualify)
+//   +16 uint32 edge_base       the row's targets start at edge4[edge_base * 4]
+//   +20 uint8  hi[len]         upper 8 bits of the 12-bit CDF codes
+//   ..  uint8  lo[(len+1)/2]   lower 4 bits, two per byte (entry j in nibble j & 1 of byte j >> 1)
+//   ..  (pad to 4 bytes) uint32 inl[m]   targets of the m most probable entries, in entry order
+// A target is a ROW WORD: (sectors of the target's block) << kWordOffBits | first sector of the block --
+// exactly what a warp needs to start copying the next row, so for the inlined entries (the most
+// probable ones: the slack of the block's last sector is filled with them) a step is ONE gather.
+// 12-bit codes: exact mode q = min(4095, floor(cdf * 4096)) (undecided compares are settled against the
+// float64 CDF, as for the 16-bit codes); reference mode q = m with cdf = fl32(m / 1000), lossless.
+constexpr int kWordOffBits = 27;
+constexpr uint32_t kWordOffMask = (1u << kWordOffBits) - 1u;
+constexpr int kV2Header = 20;
+constexpr int kV2MaxSectors = 31;          // 5 bits of a row word
+__host__ __device__ inline int v2_used_bytes(int len) { return (kV2Header + len + (len + 1) / 2 + 3) & ~3; }
+
 }  // namespace cyp
 
 struct cyp_graph {
@@ -122,4 +144,19 @@ struct cyp_graph {
     float build_ms = 0.f;
     double row_sum_min = 0.0, row_sum_max = 0.0;     // range of the float64 row sums (normalisation check)
     mutable uint64_t labels_owner = 0;   // id of the session whose label codes are in d_edge[].code (0 = none)
+    // fused rows (see above); v2_ok = 0 when a row needs more than kV2MaxSectors sectors, the codes are unusable
+    // (q16_ok / monotone) or the blocks exceed 2^27 sectors
+    int v2_ok = 0;
+    int v2_max_sectors = 0;              // largest block, in sectors (shared-memory slot size of the step kernel)
+    int64_t v2_sectors = 0;              // total sectors of d_rows2
+    unsigned char *d_rows2 = nullptr;    // [v2_sectors * 32]
+    uint32_t *d_edge4 = nullptr;         // [v2_edge_units * 4] row words of all targets, rows padded to 4 words
+    int64_t v2_edge_units = 0;
+    uint32_t *d_word = nullptr;          // [n] row word of every cell (the roots start from it)
+    mutable uint64_t labels2_owner = 0;  // id of the session whose label codes are in the fused rows' headers
 };
+
+namespace cyp {
+// K1b (rows_v2.cu): builds the fused rows from K1's output; sets g->v2_ok.
+int build_rows_v2(cyp_graph *g, const int64_t *h_row_ptr);
+}

@@ -223,6 +223,9 @@ static void graph_free(cyp_graph *g) {
     dev_free(g->d_edge);
     dev_free(g->d_val);
     dev_free(g->d_row_ptr);
+    dev_free(g->d_rows2);
+    dev_free(g->d_edge4);
+    dev_free(g->d_word);
     delete g;
 }
 
@@ -373,6 +376,11 @@ static int graph_create_impl(int device, int64_t n_cells, int64_t nnz, const int
     dev_free(d_raw_col);
     dev_free(d_raw_val);
 #undef G_CUDA
+    const int rc2 = build_rows_v2(g, h_row_ptr);        // K1b: fused rows for the default step kernel (rows_v2.cu)
+    if (rc2 != CYP_OK) {
+        graph_free(g);
+        return rc2;
+    }
     *out = g;
     return CYP_OK;
 }

@@ -1,0 +1,185 @@
+// K1b: the fused-row layout of common.cuh ("v2"), built from K1's output.
+//
+// Why this layout (profiles/r01_gather_ceilings.log, r01_footprint_sweep_*.log): at atlas scale K2 is bound
+// by DRAM random accesses -- per step one 128-byte row of 16-bit codes (L2 hit rate ~55 %) plus one 32-byte
+// sector holding a 16-byte edge record out of a 1 GB array (hit rate ~15 %); the edge-record gathers alone
+// are ~30 G/s against a measured ceiling of ~40 G random sector reads/s.  Transition probabilities are
+// skewed (scvelo: exp(cosine * scale)), so a row's few most probable entries take most of the steps: their
+// targets are stored in the slack of the row's own block and those steps need no second gather at all.
+// 12-bit codes (two planes: 8 + 4 bits) make room for that without growing the block; the remaining
+// targets shrink from 16-byte records to 4-byte row words.
+//
+// The kernel is one warp per row: codes from the CDF K1 wrote (bit-equal to matrix_prep, :11-31), targets
+// translated to row words, the m most probable entries selected by m warp-argmax rounds.
+#include <cstdlib>
+#include <vector>
+
+#include "common.cuh"
+
+namespace cyp {
+
+namespace {
+
+template <typename CdfT>
+__device__ __forceinline__ int code12(CdfT c, int *bad) {
+    if constexpr (sizeof(CdfT) == 8) {
+        if (!(c >= 0.0)) { *bad = 1; return 0; }
+        const double x = floor(c * 4096.0);
+        return static_cast<int>(x > 4095.0 ? 4095.0 : x);
+    } else {
+        const float m = rintf(__fmul_rn(c, 1000.0f));       // the stored value is fl32(m / 1000) exactly (:31)
+        if (!(m >= 0.0f && m <= 4095.0f)) { *bad = 1; return 0; }
+        return static_cast<int>(m);
+    }
+}
+
+template <typename CdfT>
+__global__ void __launch_bounds__(256)
+build_rows_v2_kernel(int64_t n, const RowInfo *__restrict__ rows, const CdfT *__restrict__ cdf, const double *__restrict__ val,
+                     const int32_t *__restrict__ col, const uint32_t *__restrict__ word, const uint32_t *__restrict__ ebase,
+                     unsigned char *__restrict__ rows2, uint32_t *__restrict__ edge4, int *__restrict__ bad_flag) {
+    const int64_t r = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= n) return;
+    const RowInfo ri = rows[r];
+    const int len = static_cast<int>(ri.len);
+    const int64_t off = static_cast<int64_t>(ri.off_units) * kRowAlign;
+    const uint32_t w = word[r];
+    unsigned char *blk = rows2 + static_cast<size_t>(w & kWordOffMask) * 32;
+    const int nsect = static_cast<int>(w >> kWordOffBits);
+    const int used = v2_used_bytes(len);
+    int m = (nsect * 32 - used) / 4;
+    if (m > len) m = len;
+    if (m > 64) m = 64;
+    uint32_t *e4 = edge4 + static_cast<size_t>(ebase[r]) * 4;
+    int bad = 0;
+    // codes and targets
+    for (int j0 = 0; j0 < len; j0 += 32) {
+        const int j = j0 + lane;
+        int code = 0;
+        if (j < len) {
+            code = code12<CdfT>(cdf[off + j], &bad);
+            blk[kV2Header + j] = static_cast<unsigned char>(code >> 4);
+            e4[j] = word[col[off + j]];
+        }
+        const int lo = code & 15;
+        const int lo_next = __shfl_down_sync(0xffffffffu, lo, 1);       // lane parity == entry parity (j0 is a multiple of 32)
+        if ((lane & 1) == 0 && j < len) blk[kV2Header + len + (j >> 1)] = static_cast<unsigned char>(lo | ((j + 1 < len ? lo_next : 0) << 4));
+    }
+    // the m most probable entries among the first 64 (ties: the earlier entry)
+    double p0 = (lane < len) ? val[off + lane] : -1.0;
+    double p1 = (lane + 32 < len) ? val[off + lane + 32] : -1.0;
+    unsigned long long mask = 0ull;
+    for (int k = 0; k < m; ++k) {
+        double best = p0 >= p1 ? p0 : p1;
+        int bj = p0 >= p1 ? lane : lane + 32;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+            if (ob > best || (ob == best && oj < bj)) { best = ob; bj = oj; }
+        }
+        mask |= 1ull << bj;
+        if (bj == lane) p0 = -2.0;
+        if (bj == lane + 32) p1 = -2.0;
+    }
+    uint32_t *inl = reinterpret_cast<uint32_t *>(blk + used);
+    for (int j = lane; j < 64 && j < len; j += 32)
+        if ((mask >> j) & 1ull) inl[__popcll(mask & ((1ull << j) - 1ull))] = word[col[off + j]];
+    if (lane == 0) {
+        *reinterpret_cast<int32_t *>(blk) = static_cast<int32_t>(r);
+        *reinterpret_cast<uint16_t *>(blk + 4) = static_cast<uint16_t>(len);
+        blk[6] = 0;
+        blk[7] = static_cast<unsigned char>(m);
+        *reinterpret_cast<unsigned long long *>(blk + 8) = mask;
+        *reinterpret_cast<uint32_t *>(blk + 16) = ebase[r];
+    }
+    if (bad) atomicOr(bad_flag, 1);
+}
+
+}  // namespace
+
+// Called at the end of cyp_graph_create.  Leaves g->v2_ok = 0 (and no v2 arrays) when the layout does not apply.
+int build_rows_v2(cyp_graph *g, const int64_t *h_row_ptr) {
+    g->v2_ok = 0;
+    if (!(g->q16_ok && g->monotone)) return CYP_OK;
+    if (g->max_len > 65535) return CYP_OK;
+    if (const char *off = getenv("CYP_NO_V2")) if (off[0] == '1') return CYP_OK;
+    int extra = 0;                                       // whole extra sectors of inlined targets per row (experiments)
+    if (const char *e = getenv("CYP_V2_EXTRA")) extra = atoi(e);
+    const int64_t n = g->n;
+    std::vector<uint32_t> word(static_cast<size_t>(n)), ebase(static_cast<size_t>(n));
+    int64_t sectors = 0, units = 0;
+    int max_sectors = 0;
+    for (int64_t r = 0; r < n; ++r) {
+        const int len = static_cast<int>(h_row_ptr[r + 1] - h_row_ptr[r]);
+        int nsect = (v2_used_bytes(len) + 31) / 32;
+        if (len > 0) nsect += extra;
+        if (nsect > kV2MaxSectors) return CYP_OK;
+        if (sectors > static_cast<int64_t>(kWordOffMask) - nsect || units >= (1ll << 32) - 1) return CYP_OK;
+        word[r] = (static_cast<uint32_t>(nsect) << kWordOffBits) | static_cast<uint32_t>(sectors);
+        ebase[r] = static_cast<uint32_t>(units);
+        sectors += nsect;
+        units += (len + 3) / 4;
+        if (nsect > max_sectors) max_sectors = nsect;
+    }
+    uint32_t *d_ebase = nullptr;
+    int *d_bad = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    auto bail = [&](cudaError_t e, const char *what) {
+        dev_free(d_ebase); dev_free(d_bad);
+        dev_free(g->d_rows2); dev_free(g->d_edge4); dev_free(g->d_word);
+        g->d_rows2 = nullptr; g->d_edge4 = nullptr; g->d_word = nullptr;
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        return fail(e == cudaErrorMemoryAllocation ? CYP_E_NOMEM : CYP_E_CUDA, std::string("build_rows_v2: ") + what + ": " + cudaGetErrorString(e));
+    };
+#define V_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return bail(_e, #expr); } while (0)
+    const size_t rows_bytes = static_cast<size_t>(sectors + kV2MaxSectors + 1) * 32;     // slack: a warp may copy a full slot past the last block
+    V_CUDA(dev_alloc(&g->d_rows2, rows_bytes));
+    V_CUDA(dev_alloc(&g->d_edge4, sizeof(uint32_t) * 4 * static_cast<size_t>(units + 1)));
+    V_CUDA(dev_alloc(&g->d_word, sizeof(uint32_t) * n));
+    V_CUDA(dev_alloc(&d_ebase, sizeof(uint32_t) * n));
+    V_CUDA(dev_alloc(&d_bad, sizeof(int)));
+    V_CUDA(cudaMemset(d_bad, 0, sizeof(int)));
+    V_CUDA(cudaMemset(g->d_rows2, 0, rows_bytes));
+    V_CUDA(cudaMemcpy(g->d_word, word.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice));
+    V_CUDA(cudaMemcpy(d_ebase, ebase.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice));
+    V_CUDA(cudaEventCreate(&e0));
+    V_CUDA(cudaEventCreate(&e1));
+    const int threads = 256;
+    const unsigned grid = static_cast<unsigned>((n * 32 + threads - 1) / threads);
+    V_CUDA(cudaEventRecord(e0));
+    if (g->cdf_mode == CYP_CDF_EXACT)
+        build_rows_v2_kernel<double><<<grid, threads>>>(n, g->d_row, static_cast<const double *>(g->d_cdf), g->d_val, g->d_col, g->d_word,
+                                                        d_ebase, g->d_rows2, g->d_edge4, d_bad);
+    else
+        build_rows_v2_kernel<float><<<grid, threads>>>(n, g->d_row, static_cast<const float *>(g->d_cdf), g->d_val, g->d_col, g->d_word,
+                                                       d_ebase, g->d_rows2, g->d_edge4, d_bad);
+    V_CUDA(cudaGetLastError());
+    V_CUDA(cudaEventRecord(e1));
+    V_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    V_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    int bad = 0;
+    V_CUDA(cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost));
+#undef V_CUDA
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    dev_free(d_ebase);
+    dev_free(d_bad);
+    if (bad) {                                           // a CDF value the 12-bit codes cannot hold: keep the old layout only
+        dev_free(g->d_rows2); dev_free(g->d_edge4); dev_free(g->d_word);
+        g->d_rows2 = nullptr; g->d_edge4 = nullptr; g->d_word = nullptr;
+        return CYP_OK;
+    }
+    g->build_ms += ms;
+    g->v2_sectors = sectors;
+    g->v2_edge_units = units;
+    g->v2_max_sectors = max_sectors;
+    g->device_bytes += static_cast<int64_t>(rows_bytes + sizeof(uint32_t) * 4 * (units + 1) + sizeof(uint32_t) * n);
+    g->v2_ok = 1;
+    return CYP_OK;
+}
+
+}  // namespace cyp

@@ -263,6 +263,13 @@ fetch_rows_kernel(int64_t n_rows, const int64_t *__restrict__ rows, const int32_
     for (int i = lane; i < n_cols; i += 32) dst[i] = src[i];
 }
 
+// same for the fused rows (walk_v2.cu): the label code lives in byte 6 of every row block's header
+__global__ void __launch_bounds__(256)
+label_rows2_kernel(int64_t n, const uint32_t *__restrict__ word, unsigned char *__restrict__ rows2, const uint8_t *__restrict__ code8) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) rows2[static_cast<size_t>(word[i] & kWordOffMask) * 32 + 6] = code8[i];
+}
+
 // generic min_clusters filter for label sets too large for the in-kernel bitmap (n_codes > 256):
 // one warp per walker, bitmap of n_codes bits in shared memory.
 __global__ void __launch_bounds__(128)
@@ -695,7 +702,13 @@ int run_chunk(cyp_session *s, uint32_t round, int64_t sims_per_root, int64_t wb,
     struct EvGuard { cudaEvent_t *e; ~EvGuard() { for (int i = 0; i < 3; ++i) cudaEventDestroy(e[i]); } } evg{ev};
 
     // ---- K2
-    if (s->d_code8 && s->g->labels_owner != s->id) {     // label the edge records for this session (once)
+    if (s->d_code8 && walk_auto_is_v2(s->g)) {           // label the fused rows' headers for this session (once)
+        if (s->g->labels2_owner != s->id) {
+            label_rows2_kernel<<<blocks_for(s->g->n, kThreads), kThreads, 0, st>>>(s->g->n, s->g->d_word, s->g->d_rows2, s->d_code8);
+            S_CUDA(cudaGetLastError());
+            s->g->labels2_owner = s->id;
+        }
+    } else if (s->d_code8 && s->g->labels_owner != s->id) {     // label the edge records for this session (once)
         label_edges_kernel<<<blocks_for(s->g->padded, kThreads), kThreads, 0, st>>>(s->g->padded, s->g->d_edge, s->d_code8);
         S_CUDA(cudaGetLastError());
         s->g->labels_owner = s->id;

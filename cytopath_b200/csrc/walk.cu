@@ -188,6 +188,9 @@ static int launch_variant(const WalkParams &p, WalkVariant v, WalkMode mode, cud
     return fail(CYP_E_INVALID, "launch_walk: unknown kernel variant (lanes*100+unroll)");
 }
 
+// long rows (C5, k = 200: 352-byte blocks in 512-byte slots) are faster through walk_tma.cu's bulk copies (24.4 vs 21.2 G walker-steps/s)
+bool walk_auto_is_v2(const cyp_graph *g) { return g->v2_ok && g->v2_max_sectors * 32 <= 256; }
+
 WalkVariant pick_walk_variant(const cyp_graph *g, int variant) {
     if (variant > 0) return WalkVariant{variant / 100, variant % 100};
     // one chunk (lanes * unroll * 16 bytes) should cover a typical row
@@ -200,6 +203,11 @@ WalkVariant pick_walk_variant(const cyp_graph *g, int variant) {
 }
 
 int launch_walk(const cyp_graph *g, const WalkParams &p, WalkMode mode, int variant, cudaStream_t stream) {
+    if (variant >= 9500 || (variant == 0 && walk_auto_is_v2(g))) {
+        const int rc = launch_walk_v2(g, p, mode, variant, stream);
+        if (rc != kNotApplicable) return rc;
+        return fail(CYP_E_INVALID, "launch_walk: the fused-row kernel (variant 95xx) does not apply to this graph");
+    }
     if (variant >= 9400) {        // paired flavour: on request only (same throughput as the default: K2 is bound by the memory system)
         const int rc = launch_walk_pp(g, p, mode, variant, stream);
         if (rc != kPpNotApplicable) return rc;
@@ -218,6 +226,10 @@ using namespace cyp;
 extern "C" const char *cyp_walk_variant_name(const cyp_graph *g, int variant) {
     static thread_local char buf[96];
     if (!g) return "";
+    if (variant >= 9500 || (variant == 0 && walk_auto_is_v2(g))) {
+        const char *name = walk_v2_name(g, variant);
+        return name ? name : "not applicable";
+    }
     if (variant >= 9400) {
         const char *name = walk_pp_name(g, variant);
         return name ? name : "not applicable";

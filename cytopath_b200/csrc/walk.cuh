@@ -27,6 +27,10 @@ struct WalkParams {
     const int32_t *end_slot;        // [n_cells] end-point slot or -1
     int32_t *out_slot;              // [n_walkers]: -2 fails min_clusters, -1 not terminal, else end slot
     uint64_t *out_hash;             // [n_walkers, 2] 128-bit sequence hash
+    // fused rows (walk_v2.cu; filled in by launch_walk_v2 from the graph)
+    const unsigned char *rows2 = nullptr;
+    const uint32_t *edge4 = nullptr;
+    const uint32_t *word = nullptr;
 };
 
 // Kernel modes: what is fused into the step loop besides the walk itself.
@@ -117,8 +121,17 @@ const char *walk_tma_name(const cyp_graph *g, int variant);
 // K2, paired flavour (walk_pp.cu): two walkers per thread sharing one shared-memory slot of 16-bit CDF
 // codes.  `variant` = 9400 + threads per CTA / 32; 0 = auto.  Returns kPpNotApplicable (nothing launched)
 // when the graph does not qualify; walk_pp_name returns nullptr then.
-constexpr int kPpNotApplicable = 1;
+constexpr int kNotApplicable = 1;
+constexpr int kPpNotApplicable = kNotApplicable;
 int launch_walk_pp(const cyp_graph *g, const WalkParams &p, WalkMode mode, int variant, cudaStream_t stream);
 const char *walk_pp_name(const cyp_graph *g, int variant);
+
+
+// K2, fused-row flavour (walk_v2.cu, the default where cyp_graph::v2_ok): `variant` = 9500 + threads per
+// CTA / 32; 0 = auto.  Returns kNotApplicable (nothing launched) when the graph has no fused rows.
+int launch_walk_v2(const cyp_graph *g, const WalkParams &p, WalkMode mode, int variant, cudaStream_t stream);
+const char *walk_v2_name(const cyp_graph *g, int variant);
+// true when launch_walk(variant 0) runs the fused-row kernel on this graph
+bool walk_auto_is_v2(const cyp_graph *g);
 
 }  // namespace cyp

@@ -1,0 +1,273 @@
+// K2, fused-row flavour (default where the layout applies): the Markov-chain step loop (reference
+// cytopath/markov_chain_sampler.py:45-51) over the "v2" rows of common.cuh / rows_v2.cu.
+//
+// One walker per thread, one persistent CTA per SM, one shared-memory slot per thread.  Per step:
+//   1. the warp copies its 32 row blocks into the slots with cooperative 16-byte cp.async (LDGSTS): a walker
+//      is represented by its ROW WORD (sectors << 27 | first sector), which is all a copy needs, so one
+//      width-limited shuffle per copy instruction moves it between lanes;
+//   2. the header tells the cell id (-> trajectory column, hash, label bitmap), the row length and which
+//      entries have their target inlined;
+//   3. first crossing `min j : u <= cdf[j]` (ties to the bin, :49): fixed-depth branchless lower bound over
+//      the upper-8-bit plane, then the 12-bit codes decide; a compare the code cannot decide (code ==
+//      floor(u*4096)-ish, ~k/4096 of the steps) is settled against the float64 CDF, so the selected entry
+//      is ALWAYS the one the reference's comparison selects;
+//   4. the next row word: from the slot if the entry is inlined (the row's most probable entries: most
+//      steps), else one 4-byte gather from edge4.
+// The uniform stream, the comparisons and therefore the trajectories are bit-identical to walk.cu /
+// walk_tma.cu / walk_pp.cu and to the oracle.
+#include <cstdio>
+
+#include "walk.cuh"
+
+namespace cyp {
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+}
+
+__device__ __forceinline__ uint32_t ldg_word(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+constexpr int kModeExact = 0, kModeRef = 1;
+
+}  // namespace
+
+// CPR = 16-byte chunks per slot; CDFM = kModeExact / kModeRef.
+template <int CPR, int CDFM, int MODE>
+__global__ void __launch_bounds__(1024, 1) walk_v2_kernel(const WalkParams p, const int log_n /* search depth: 2^log_n >= longest row */) {
+    constexpr int SLOT_STRIDE = 16 * CPR + 32;           // +32 spreads same-position probes over 4 bank groups and keeps slots sector aligned
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int nthreads = blockDim.x;
+    const unsigned char *const slot = smem_raw + static_cast<size_t>(threadIdx.x) * SLOT_STRIDE;
+    // cooperative copy geometry: lane = (group, chunk); instruction i moves chunk `chunk` of the block of lane (lane & ~(CPR-1)) + i
+    const int chunk = lane & (CPR - 1);
+    const uint32_t dst0 = smem_u32(slot) - static_cast<uint32_t>(chunk) * SLOT_STRIDE + static_cast<uint32_t>(chunk) * 16u;
+    const unsigned char *const src_c = p.rows2 + chunk * 16;
+    const uint32_t need_thr = (static_cast<uint32_t>(chunk >> 1) + 1u) << kWordOffBits;     // word >= need_thr <=> sectors > chunk / 2
+
+    const int nt = p.nt;
+    const bool vec_store = (p.ld & 3) == 0;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * nthreads;
+
+    auto issue_copy = [&](uint32_t word) {
+#pragma unroll
+        for (int i = 0; i < CPR; ++i) {
+            const uint32_t wd = __shfl_sync(0xffffffffu, word, i, CPR);
+            const unsigned char *src = src_c + static_cast<uint64_t>(wd & kWordOffMask) * 32u;
+            if (wd >= need_thr) cp_async16(dst0 + static_cast<uint32_t>(i) * SLOT_STRIDE, src);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    for (int64_t wbase = static_cast<int64_t>(blockIdx.x) * nthreads + (threadIdx.x & ~31); wbase < p.n_walkers; wbase += stride) {
+        const int64_t w = wbase + lane;
+        const bool active = w < p.n_walkers;
+        const uint64_t gw = static_cast<uint64_t>(p.walker_begin + w);
+        uint32_t word = 0u;                               // inactive lanes copy nothing
+        if (active) word = p.word[p.roots[gw / static_cast<uint64_t>(p.sims_per_root)]];
+        int32_t *__restrict__ out_row = p.out_seq + (active ? w : 0) * p.ld;
+        const double *__restrict__ urow = (p.uniforms && active) ? p.uniforms + w * static_cast<int64_t>(nt) : nullptr;
+        int32_t b0 = 0, b1 = 0, b2 = 0;
+        int32_t cell = 0;
+        WalkerDigest<MODE> dg;
+        double u_even = 0.0, u_odd = 0.0;
+        issue_copy(word);
+        if (!p.uniforms && nt > 0) walker_uniform_pair(p.seed, p.round, gw, 0u, u_even, u_odd);
+
+        for (int t = 0; t <= nt; ++t) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            uint32_t next = word;
+            if (active) {
+                const uint4 h = *reinterpret_cast<const uint4 *>(slot);          // cell | len, label, m | inline mask
+                cell = static_cast<int32_t>(h.x);
+                const int len = static_cast<int>(h.y & 0xffffu);
+                // ---- trajectory column t, hash, label bitmap
+                if (vec_store) {
+                    const int q = t & 3;
+                    if (q == 3) {
+                        *reinterpret_cast<int4 *>(out_row + (t & ~3)) = make_int4(b0, b1, b2, cell);
+                    } else {
+                        if (q == 0) b0 = cell; else if (q == 1) b1 = cell; else b2 = cell;
+                        if (t == nt) {
+                            out_row[t & ~3] = b0;
+                            if (q >= 1) out_row[(t & ~3) + 1] = b1;
+                            if (q >= 2) out_row[(t & ~3) + 2] = b2;
+                        }
+                    }
+                } else {
+                    out_row[t] = cell;
+                }
+                dg.visit(cell, (h.y >> 16) & 0xffu);
+                if (t < nt) {
+                    // ---- first crossing
+                    const double u = urow ? urow[t] : ((t & 1) ? u_odd : u_even);
+                    int key, t_def = 0;
+                    if constexpr (CDFM == kModeExact) {
+                        t_def = static_cast<int>(ceil(u * 4096.0));            // q >= t_def      <=>  u <= q / 4096
+                        key = t_def - 1;                                         // q >= t_def - 1  <=>  u <= (q + 1) / 4096
+                    } else {
+                        key = static_cast<int>(ceil(u * 1000.0));               // smallest integer m with u <= (double)fl32(m / 1000)
+                        while (key > 0 && u <= static_cast<double>(__fdiv_rn(static_cast<float>(key - 1), 1000.0f))) --key;
+                        while (u > static_cast<double>(__fdiv_rn(static_cast<float>(key), 1000.0f))) ++key;
+                    }
+                    const unsigned char *hi = slot + kV2Header;
+                    const unsigned char *lo = hi + len;
+                    const int key_hi = key >> 4;
+                    int j = 0;
+                    for (int step = 1 << (log_n - 1); step >= 1; step >>= 1) {
+                        const int probe = j + step - 1;
+                        if (probe < len && static_cast<int>(hi[probe]) < key_hi) j += step;
+                    }
+                    auto code_at = [&](int jj) { return (static_cast<int>(hi[jj]) << 4) | ((static_cast<int>(lo[jj >> 1]) >> ((jj & 1) * 4)) & 15); };
+                    if constexpr (CDFM == kModeExact) {
+                        while (j < len) {
+                            const int q = code_at(j);
+                            if (q >= t_def) break;                               // certain crossing
+                            if (q == key) {                                      // undecided by the code: float64 compare (:49)
+                                const RowInfo ri = p.rows[cell];
+                                if (u <= __ldg(static_cast<const double *>(p.cdf) + static_cast<int64_t>(ri.off_units) * kRowAlign + j)) break;
+                            }
+                            ++j;
+                        }
+                    } else {
+                        while (j < len && code_at(j) < key) ++j;
+                    }
+                    // ---- next row word
+                    if (j < len) {
+                        const unsigned long long mask = (static_cast<unsigned long long>(h.w) << 32) | h.z;
+                        if (j < 64 && ((mask >> j) & 1ull)) {
+                            const int rank = __popcll(mask & ((1ull << j) - 1ull));
+                            next = *reinterpret_cast<const uint32_t *>(slot + v2_used_bytes(len) + 4 * rank);
+                        } else {
+                            const uint32_t ebase = *reinterpret_cast<const uint32_t *>(slot + 16);
+                            next = ldg_word(p.edge4 + static_cast<size_t>(ebase) * 4 + j);
+                        }
+                    } else if (p.nocross) {
+                        atomicAdd(p.nocross, 1ull);                              // stays where it is (reference: IndexError at :49)
+                    }
+                }
+            }
+            if (t == nt) break;
+            word = next;
+            __syncwarp();                                                         // every lane is done with its slot
+            issue_copy(word);
+            if (!p.uniforms && (t & 1)) walker_uniform_pair(p.seed, p.round, gw, static_cast<uint32_t>((t + 1) >> 1), u_even, u_odd);
+        }
+        if (active) dg.finish(p, w, cell);
+    }
+}
+
+struct V2Config {
+    int cpr;
+    int threads;
+    int log_n;
+    size_t smem;
+};
+
+// variant: 0 = auto; 9500 + T/32 = T threads per CTA.
+static bool v2_config(const cyp_graph *g, int variant, int64_t n_walkers, int sm_count, V2Config *out) {
+    if (!g->v2_ok) return false;
+    int cpr = 2;
+    while (cpr * 16 < g->v2_max_sectors * 32) cpr <<= 1;
+    if (cpr > 32) return false;
+    const size_t stride = 16 * cpr + 32;
+    int threads = static_cast<int>((226 * 1024) / stride) / 32 * 32;
+    if (threads > 1024) threads = 1024;
+    if (variant > 9500) {
+        threads = (variant - 9500) * 32 < threads ? (variant - 9500) * 32 : threads;
+    } else if (n_walkers > 0 && sm_count > 0) {
+        // wave balancing: every warp runs as many 32-walker batches as with the largest CTA, with no more warps than that needs
+        const int64_t batches = (n_walkers + 31) / 32;
+        const int64_t per_round = static_cast<int64_t>(sm_count) * (threads / 32);
+        const int64_t rounds = (batches + per_round - 1) / per_round;
+        const int64_t warps = (batches + static_cast<int64_t>(sm_count) * rounds - 1) / (static_cast<int64_t>(sm_count) * rounds);
+        if (warps * 32 < threads) threads = static_cast<int>(warps) * 32;
+    }
+    if (threads < 32) threads = 32;
+    int log_n = 1;
+    while ((1 << log_n) < g->max_len) ++log_n;
+    *out = V2Config{cpr, threads, log_n, static_cast<size_t>(threads) * stride};
+    return true;
+}
+
+static int v2_sm_count() {
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (dev != cached_dev) {
+        if (cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+template <int CPR, int CDFM, int MODE>
+static int launch_v2_one(const WalkParams &p, const V2Config &c, int sm_count, cudaStream_t stream) {
+    auto kernel = walk_v2_kernel<CPR, CDFM, MODE>;
+    static size_t smem_set = 0;
+    if (c.smem > smem_set) {
+        CYP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c.smem)));
+        smem_set = c.smem;
+    }
+    const int64_t need = (p.n_walkers + c.threads - 1) / c.threads;
+    const unsigned grid = static_cast<unsigned>(need < sm_count ? need : sm_count);     // persistent: one CTA per SM
+    if (grid == 0) return CYP_OK;
+    kernel<<<grid, c.threads, c.smem, stream>>>(p, c.log_n);
+    CYP_CUDA(cudaGetLastError());
+    return CYP_OK;
+}
+
+template <int CPR, int CDFM>
+static int launch_v2_mode(const WalkParams &p, WalkMode mode, const V2Config &c, int sm_count, cudaStream_t stream) {
+    switch (mode) {
+        case kModePlain: return launch_v2_one<CPR, CDFM, kModePlain>(p, c, sm_count, stream);
+        case kModeFilter0: return launch_v2_one<CPR, CDFM, kModeFilter0>(p, c, sm_count, stream);
+        case kModeFilter1: return launch_v2_one<CPR, CDFM, kModeFilter1>(p, c, sm_count, stream);
+        case kModeFilter4: return launch_v2_one<CPR, CDFM, kModeFilter4>(p, c, sm_count, stream);
+    }
+    return fail(CYP_E_INVALID, "launch_walk_v2: bad mode");
+}
+
+template <int CPR>
+static int launch_v2_cdf(const cyp_graph *g, const WalkParams &p, WalkMode mode, const V2Config &c, int sm_count, cudaStream_t stream) {
+    return g->cdf_mode == CYP_CDF_EXACT ? launch_v2_mode<CPR, kModeExact>(p, mode, c, sm_count, stream)
+                                        : launch_v2_mode<CPR, kModeRef>(p, mode, c, sm_count, stream);
+}
+
+int launch_walk_v2(const cyp_graph *g, const WalkParams &p_in, WalkMode mode, int variant, cudaStream_t stream) {
+    const int sm_count = v2_sm_count();
+    V2Config c;
+    if (sm_count <= 0 || !v2_config(g, variant, p_in.n_walkers, sm_count, &c)) return kNotApplicable;
+    WalkParams p = p_in;
+    p.rows2 = g->d_rows2;
+    p.edge4 = g->d_edge4;
+    p.word = g->d_word;
+    switch (c.cpr) {
+        case 2: return launch_v2_cdf<2>(g, p, mode, c, sm_count, stream);
+        case 4: return launch_v2_cdf<4>(g, p, mode, c, sm_count, stream);
+        case 8: return launch_v2_cdf<8>(g, p, mode, c, sm_count, stream);
+        case 16: return launch_v2_cdf<16>(g, p, mode, c, sm_count, stream);
+        case 32: return launch_v2_cdf<32>(g, p, mode, c, sm_count, stream);
+    }
+    return kNotApplicable;
+}
+
+const char *walk_v2_name(const cyp_graph *g, int variant) {
+    static thread_local char buf[128];
+    V2Config c;
+    if (!v2_config(g, variant, 0, 0, &c)) return nullptr;
+    snprintf(buf, sizeof(buf), "walk_v2_kernel<%s,fused rows,threads<=%d,slot=%dB>", g->cdf_mode == CYP_CDF_EXACT ? "q12/f64" : "q12/f32",
+             c.threads, 16 * c.cpr);
+    return buf;
+}
+
+}  // namespace cyp

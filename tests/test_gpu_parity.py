@@ -209,6 +209,19 @@ def test_k2_bit_exact_vs_oracle_all_variants(gname, mode, omode):
                                          ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
             torch.cuda.synchronize()
             np.testing.assert_array_equal(out.cpu().numpy(), wnt, err_msg="%s nt=%d" % (g.variant_name(variant), n_t))
+    # fused-row flavour (12-bit codes, inlined targets): 32 / 128 / 512 / 1024 threads per CTA; 62, 63 and 64 columns
+    for variant in (9501, 9504, 9516, 9532):
+        assert "walk_v2_kernel" in g.variant_name(variant), g.variant_name(variant)
+        for n_t in (nt, 62, 63):
+            wnt = want if n_t == nt else cwalk.walk(C, cdf, np.repeat(roots, sims), n_t, seed=seed, round_idx=rnd, strict=False)
+            out = torch.full((len(roots) * sims, n_t + 1), -7, dtype=torch.int32, device="cuda")
+            miss = torch.zeros(1, dtype=torch.int64, device="cuda")
+            _lib.check(L.cyp_walk_device(g.handle, d_roots.data_ptr(), len(roots), sims, 0, len(roots) * sims, n_t, seed, rnd,
+                                         None, out.data_ptr(), miss.data_ptr(), variant,
+                                         ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            torch.cuda.synchronize()
+            np.testing.assert_array_equal(out.cpu().numpy(), wnt, err_msg="%s nt=%d" % (g.variant_name(variant), n_t))
+    assert "walk_v2_kernel" in g.variant_name(0)              # and it is what the auto variant picks
     # auto variant through the host entry point, a shard in the middle of the round
     got = g.walk(roots, sims, nt, seed=seed, round_idx=rnd, walker_begin=100, n_walkers=211, strict=False)
     np.testing.assert_array_equal(got, want[100:311])
@@ -271,8 +284,8 @@ def test_k2_under_normalised_row_raises_like_the_reference():
 
 
 def test_k2_q16_ambiguous_codes_are_resolved_in_float64():
-    """Rows whose CDF values crowd into single 1/65536 buckets, and uniforms aimed exactly at and next to
-    those values: the 16-bit flavour must still return what the float64 comparison returns."""
+    """Rows whose CDF values crowd into single 1/65536 (and 1/4096) buckets, and uniforms aimed exactly at and
+    next to those values: the 16-bit and 12-bit code flavours must still return what the float64 comparison returns."""
     from scipy import sparse
     rng = np.random.default_rng(3)
     n, k = 64, 40
@@ -289,7 +302,7 @@ def test_k2_q16_ambiguous_codes_are_resolved_in_float64():
     L = _lib.load()
     for mode, omode in MODES:
         g = _lib.Graph(C, mode)
-        assert "q16" in g.variant_name(0)
+        assert "q12" in g.variant_name(0) and "q16" in g.variant_name(9204) and "q16" in g.variant_name(9404)
         cdf = cwalk.build_cdf(C, omode)
         cdf64 = cdf.astype(np.float64)
         roots = np.arange(n)
@@ -303,7 +316,7 @@ def test_k2_q16_ambiguous_codes_are_resolved_in_float64():
         want = cwalk.walk(C, cdf, np.repeat(roots, 8), nt, uniforms=u, strict=False)
         d_roots = torch.tensor(roots, dtype=torch.int32, device="cuda")
         d_u = torch.tensor(u, dtype=torch.float64, device="cuda")
-        for variant in (0, 9204, 9304, 9008, 404):
+        for variant in (0, 9504, 9404, 9204, 9304, 9008, 404):
             out = torch.zeros((n * 8, nt + 1), dtype=torch.int32, device="cuda")
             miss = torch.zeros(1, dtype=torch.int64, device="cuda")
             _lib.check(L.cyp_walk_device(g.handle, d_roots.data_ptr(), n, 8, 0, n * 8, nt, 0, 0, d_u.data_ptr(), out.data_ptr(),
