@@ -115,6 +115,29 @@ def mean_visited_row_len(C, seq_sample):
     return float(lens[seq_sample[:, :-1].ravel()].mean())
 
 
+def fused_layout_stats(C, seq_sample, row_block_bytes, n_probe=20000):
+    """What the fused-row kernel requests per walker-step on the sampled trajectories: mean bytes of the visited
+    row blocks and the share of transitions whose target was inlined (include/cytopath_b200.h, DESIGN.md 4:
+    block = 20-byte header + 12-bit codes + the m most probable targets that fit the block's last sector)."""
+    lens = np.diff(C.indptr)
+    used = (20 + lens + (lens + 1) // 2 + 3) & ~3
+    nsect0 = (used + 31) // 32
+    extra = 1 if row_block_bytes > int(nsect0.sum()) * 32 else 0                # the library's choice (rows_v2.cu)
+    nsect = nsect0 + extra * (lens > 0)
+    m = np.minimum(np.minimum(lens, 64), (nsect * 32 - used) // 4)
+    cur, nxt = seq_sample[:, :-1].ravel(), seq_sample[:, 1:].ravel()
+    pick = np.random.default_rng(0).choice(len(cur), size=min(n_probe, len(cur)), replace=False)
+    inlined = 0
+    for c, x in zip(cur[pick], nxt[pick]):
+        a, b = C.indptr[c], C.indptr[c + 1]
+        j = int(np.searchsorted(C.indices[a:b], x))
+        if j < 64:
+            cand = C.data[a:min(b, a + 64)]
+            rank = int(np.sum((cand > cand[j]) | ((cand == cand[j]) & (np.arange(len(cand)) < j))))
+            inlined += rank < m[c]
+    return float((nsect[cur] * 32).mean()), float(inlined) / len(pick)
+
+
 def timed_port_sample(cb, prep, pool, roots, clusters, max_steps, cores, budget_s):
     """Size one joblib call (one task per root cell, 2 tasks per core, like :306-308) to about
     `budget_s` of wall time.  The per-walker cost is measured in-process first so that each task
@@ -266,8 +289,13 @@ def run_b200(args, w):
         peak, peak_src = 6650.0, "fallback of B200_PROFILING.md"
     achieved = W * nt * bytes_per_step / (ms_launch * 1e-3) / 1e9
     # bytes the default kernel actually requests per walker-step (sector granular): the staged row + one edge-record sector + the store
-    row_elem = 2 if "q16" in kernel_name else elem
-    layout_bytes = np.ceil(row_elem * kbar / 32.0) * 32.0 + 32.0 + 4.0
+    inline_cov = None
+    if "fused rows" in kernel_name:
+        block_bytes, inline_cov = fused_layout_stats(C, sample, graph.layout()["row_block_bytes"])
+        layout_bytes = block_bytes + (1.0 - inline_cov) * 32.0 + 4.0      # row block + a target-word sector when not inlined + the store
+    else:
+        row_elem = 2 if "q16" in kernel_name else elem
+        layout_bytes = np.ceil(row_elem * kbar / 32.0) * 32.0 + 32.0 + 4.0
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
@@ -367,9 +395,11 @@ def run_b200(args, w):
                      "layout_bytes_per_walker_step": layout_bytes,
                      "layout_achieved": W * nt * layout_bytes / (ms_launch * 1e-3) / 1e9,
                      "layout_frac": W * nt * layout_bytes / (ms_launch * 1e-3) / 1e9 / peak,
+                     "inlined_target_share": inline_cov,
                      "note": "achieved uses SURVEY 8d's algorithmic bytes (full float64/float32 CDF row + 16 B); the default kernel "
-                             "stages 2-byte CDF codes (exact by construction, DESIGN.md 5), so it requests layout_bytes per step "
-                             "and frac can exceed 1; traffic = dram read+write bytes of one launch from the committed ncu capture"},
+                             "reads fused rows (12-bit CDF codes, exact by construction, + the most probable targets inlined; "
+                             "DESIGN.md 4-5), so it requests layout_bytes per step and frac can exceed 1; traffic = dram read+write "
+                             "bytes of one launch from the committed ncu capture"},
     }
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu, cpu_c = cpu_baseline_sample(C, g, roots, max_steps, 1 if mode == _lib.CDF_EXACT else 0)

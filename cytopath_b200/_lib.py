@@ -13,6 +13,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libcytopath_b200.so")
+if os.environ.get("CYP_LIB_PATH"):          # developer A/B runs of two builds on one GPU box
+    LIB_PATH = os.environ["CYP_LIB_PATH"]
 
 CDF_REFERENCE = 0
 CDF_EXACT = 1
@@ -20,7 +22,7 @@ E_NOCROSSING = -4
 
 EXPORTS = [
     "cyp_version", "cyp_last_error", "cyp_device_count",
-    "cyp_graph_create", "cyp_graph_create_f32", "cyp_graph_row_sum_range", "cyp_graph_destroy", "cyp_graph_info", "cyp_graph_fetch_cdf", "cyp_graph_build_ms",
+    "cyp_graph_create", "cyp_graph_create_f32", "cyp_graph_row_sum_range", "cyp_graph_destroy", "cyp_graph_info", "cyp_graph_layout", "cyp_graph_fetch_cdf", "cyp_graph_build_ms",
     "cyp_power_iteration", "cyp_walk", "cyp_walk_device", "cyp_walk_variant_name", "cyp_transition_scores",
     "cyp_session_create", "cyp_session_destroy", "cyp_session_round", "cyp_session_rows",
     "cyp_session_fetch_index", "cyp_session_fetch_rows", "cyp_session_round_records",
@@ -78,6 +80,7 @@ def load():
     L.cyp_graph_row_sum_range.argtypes = [vp, P(ctypes.c_double), P(ctypes.c_double)]
     L.cyp_graph_destroy.argtypes = [vp]
     L.cyp_graph_info.argtypes = [vp, P(i64), P(i64), P(i32), P(ci), P(ci), P(i64)]
+    L.cyp_graph_layout.argtypes = [vp, P(ci), P(i64), P(i64), P(i32)]
     L.cyp_graph_fetch_cdf.argtypes = [vp, vp]
     L.cyp_graph_build_ms.argtypes = [vp, P(ctypes.c_float)]
     L.cyp_power_iteration.argtypes = [ci, i64, i64, vp, vp, vp, vp, vp, i32, vp, vp]
@@ -201,6 +204,12 @@ class Graph:
         check(load().cyp_graph_info(self._h, n, nnz, mx, mode, dev, b))
         return dict(n_cells=n.value, nnz=nnz.value, max_row_nnz=mx.value, cdf_mode=mode.value,
                     device=dev.value, device_bytes=b.value)
+
+    def layout(self):
+        """Fused-row layout: dict(fused, row_block_bytes, target_word_bytes, max_block_bytes)."""
+        f, rb, tb, mb = ctypes.c_int(), ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int32()
+        check(load().cyp_graph_layout(self._h, ctypes.byref(f), ctypes.byref(rb), ctypes.byref(tb), ctypes.byref(mb)))
+        return dict(fused=bool(f.value), row_block_bytes=rb.value, target_word_bytes=tb.value, max_block_bytes=mb.value)
 
     def row_sum_range(self):
         lo, hi = ctypes.c_double(), ctypes.c_double()

@@ -159,4 +159,7 @@ struct cyp_graph {
 namespace cyp {
 // K1b (rows_v2.cu): builds the fused rows from K1's output; sets g->v2_ok.
 int build_rows_v2(cyp_graph *g, const int64_t *h_row_ptr);
+// graph.cu: builds d_q16 and d_edge (the arrays of the step kernels other than walk_v2.cu) if they do not exist yet.
+// Synchronous, default stream; call before launching one of those kernels.
+int ensure_edge_records(const cyp_graph *g);
 }

@@ -131,17 +131,22 @@ build_cdf_kernel(int64_t n, const int64_t *__restrict__ row_ptr, const int32_t *
             if (j < len) {
                 const int64_t q = s_src[lo] + j;
                 const int32_t c = raw_col[q];
-                const RowInfo tr = rows[c];
                 cdf[dst0 + p] = finish_cdf<CdfT>(s_val[q - src0]);
-                q16[dst0 + p] = cdf_code<CdfT>(s_val[q - src0], negative_flag);
+                const uint16_t code = cdf_code<CdfT>(s_val[q - src0], negative_flag);     // also checks the code range
                 col[dst0 + p] = c;
-                edge[dst0 + p] = EdgeRec{c, tr.off_units, tr.len, 0u};
+                if (q16) {
+                    const RowInfo tr = rows[c];
+                    q16[dst0 + p] = code;
+                    edge[dst0 + p] = EdgeRec{c, tr.off_units, tr.len, 0u};
+                }
                 val[dst0 + p] = static_cast<double>(raw_val[q]);
             } else {                                   // padding never matches: u >= 0 > -1
                 cdf[dst0 + p] = static_cast<CdfT>(-1);
-                q16[dst0 + p] = 0;
                 col[dst0 + p] = -1;
-                edge[dst0 + p] = EdgeRec{-1, 0u, 0u, 0u};
+                if (q16) {
+                    q16[dst0 + p] = 0;
+                    edge[dst0 + p] = EdgeRec{-1, 0u, 0u, 0u};
+                }
                 val[dst0 + p] = 0.0;
             }
         }
@@ -155,19 +160,24 @@ build_cdf_kernel(int64_t n, const int64_t *__restrict__ row_ptr, const int32_t *
             if (v < 0.0) atomicOr(negative_flag, 1);
             acc = __dadd_rn(acc, v);
             const int32_t c = raw_col[a + j];
-            const RowInfo tr = rows[c];
             cdf[dst + j] = finish_cdf<CdfT>(acc);
-            q16[dst + j] = cdf_code<CdfT>(acc, negative_flag);
+            const uint16_t code = cdf_code<CdfT>(acc, negative_flag);
             col[dst + j] = c;
-            edge[dst + j] = EdgeRec{c, tr.off_units, tr.len, 0u};
+            if (q16) {
+                const RowInfo tr = rows[c];
+                q16[dst + j] = code;
+                edge[dst + j] = EdgeRec{c, tr.off_units, tr.len, 0u};
+            }
             val[dst + j] = v;
         }
         row_sum = acc;
         for (int64_t j = len; j < len_pad; ++j) {
             cdf[dst + j] = static_cast<CdfT>(-1);
-            q16[dst + j] = 0;
             col[dst + j] = -1;
-            edge[dst + j] = EdgeRec{-1, 0u, 0u, 0u};
+            if (q16) {
+                q16[dst + j] = 0;
+                edge[dst + j] = EdgeRec{-1, 0u, 0u, 0u};
+            }
             val[dst + j] = 0.0;
         }
     }
@@ -198,6 +208,58 @@ __global__ void unpad_cdf_kernel(int64_t n, const int64_t *__restrict__ row_ptr,
     const int64_t a = row_ptr[r], len = row_ptr[r + 1] - a;
     const int64_t src = static_cast<int64_t>(rows[r].off_units) * align_elems;
     for (int64_t j = lane; j < len; j += 32) out[a + j] = cdf[src + j];
+}
+
+// 16-bit CDF codes + edge records (what walk.cu / walk_tma.cu / walk_pp.cu read), derived from K1's output.
+template <typename CdfT>
+__global__ void __launch_bounds__(256)
+build_edge_records_kernel(int64_t padded, const RowInfo *__restrict__ rows, const CdfT *__restrict__ cdf, const int32_t *__restrict__ col,
+                          uint16_t *__restrict__ q16, EdgeRec *__restrict__ edge) {
+    const int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (p >= padded) return;
+    const int32_t c = col[p];
+    if (c >= 0) {
+        int unused = 0;
+        const RowInfo tr = rows[c];
+        if constexpr (sizeof(CdfT) == 8) {
+            q16[p] = cdf_code<double>(cdf[p], &unused);
+        } else {
+            const float m = rintf(__fmul_rn(cdf[p], 1000.0f));          // the stored value is fl32(m / 1000)
+            q16[p] = (m >= 0.0f && m <= 65535.0f) ? static_cast<uint16_t>(m) : 0;
+        }
+        edge[p] = EdgeRec{c, tr.off_units, tr.len, 0u};
+    } else {
+        q16[p] = 0;
+        edge[p] = EdgeRec{-1, 0u, 0u, 0u};
+    }
+}
+
+int ensure_edge_records(const cyp_graph *cg) {
+    cyp_graph *g = const_cast<cyp_graph *>(cg);
+    if (g->d_edge) return CYP_OK;
+    DeviceGuard guard(g->device);
+    uint16_t *q16 = nullptr;
+    EdgeRec *edge = nullptr;
+    cudaError_t e = dev_alloc(&q16, sizeof(uint16_t) * g->padded);
+    if (e == cudaSuccess) e = dev_alloc(&edge, sizeof(EdgeRec) * g->padded);
+    if (e == cudaSuccess) {
+        const unsigned grid = static_cast<unsigned>((g->padded + 255) / 256);
+        if (g->cdf_mode == CYP_CDF_EXACT)
+            build_edge_records_kernel<double><<<grid, 256>>>(g->padded, g->d_row, static_cast<const double *>(g->d_cdf), g->d_col, q16, edge);
+        else
+            build_edge_records_kernel<float><<<grid, 256>>>(g->padded, g->d_row, static_cast<const float *>(g->d_cdf), g->d_col, q16, edge);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
+    }
+    if (e != cudaSuccess) {
+        dev_free(q16);
+        dev_free(edge);
+        return fail(e == cudaErrorMemoryAllocation ? CYP_E_NOMEM : CYP_E_CUDA, std::string("ensure_edge_records: ") + cudaGetErrorString(e));
+    }
+    g->d_q16 = q16;
+    g->d_edge = edge;
+    g->device_bytes += static_cast<int64_t>((sizeof(uint16_t) + sizeof(EdgeRec)) * g->padded);
+    return CYP_OK;
 }
 
 }  // namespace cyp
@@ -302,25 +364,21 @@ static int graph_create_impl(int device, int64_t n_cells, int64_t nnz, const int
     G_CUDA(dev_alloc(&g->d_row, sizeof(RowInfo) * n_cells));
     G_CUDA(dev_alloc(&g->d_row_ptr, sizeof(int64_t) * (n_cells + 1)));
     G_CUDA(dev_alloc(&g->d_cdf, cdf_elem * g->padded));
-    G_CUDA(dev_alloc(&g->d_q16, sizeof(uint16_t) * g->padded));
     G_CUDA(dev_alloc(&g->d_col, sizeof(int32_t) * g->padded));
-    G_CUDA(dev_alloc(&g->d_edge, sizeof(EdgeRec) * g->padded));
     G_CUDA(dev_alloc(&g->d_val, sizeof(double) * g->padded));
     G_CUDA(dev_alloc(&d_raw_col, sizeof(int32_t) * nnz));
     G_CUDA(dev_alloc(&d_raw_val, val_elem * nnz));
     G_CUDA(dev_alloc(&d_flag, sizeof(int)));
     G_CUDA(cudaMemset(d_flag, 0, sizeof(int)));
     g->device_bytes = sizeof(RowInfo) * n_cells + sizeof(int64_t) * (n_cells + 1) +
-                      (cdf_elem + sizeof(uint16_t) + sizeof(int32_t) + sizeof(EdgeRec) + sizeof(double)) * g->padded;
+                      (cdf_elem + sizeof(int32_t) + sizeof(double)) * g->padded;
     G_CUDA(cudaMemcpy(g->d_row, rows.data(), sizeof(RowInfo) * n_cells, cudaMemcpyHostToDevice));
     G_CUDA(cudaMemcpy(g->d_row_ptr, h_row_ptr, sizeof(int64_t) * (n_cells + 1), cudaMemcpyHostToDevice));
     G_CUDA(cudaMemcpy(d_raw_col, h_col, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice));
     G_CUDA(cudaMemcpy(d_raw_val, h_val, val_elem * nnz, cudaMemcpyHostToDevice));
     // slack region: never-matching padding
     G_CUDA(cudaMemset(static_cast<char *>(g->d_cdf) + cdf_elem * units * A, 0xFF, cdf_elem * 4 * A));   // NaN: u <= NaN is false
-    G_CUDA(cudaMemset(g->d_q16 + units * A, 0, sizeof(uint16_t) * 4 * A));
     G_CUDA(cudaMemset(g->d_col + units * A, 0xFF, sizeof(int32_t) * 4 * A));
-    G_CUDA(cudaMemset(g->d_edge + units * A, 0, sizeof(EdgeRec) * 4 * A));
     G_CUDA(cudaMemset(g->d_val + units * A, 0, sizeof(double) * 4 * A));
 
     G_CUDA(cudaEventCreate(&e0));
@@ -339,7 +397,7 @@ static int graph_create_impl(int device, int64_t n_cells, int64_t nnz, const int
         G_CUDA(cudaFuncSetAttribute(build_cdf_kernel<CDFT, VALT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); \
         build_cdf_kernel<CDFT, VALT><<<grid, kK1Threads, smem_bytes>>>(                                                     \
             n_cells, g->d_row_ptr, d_raw_col, static_cast<const VALT *>(d_raw_val), g->d_row, A, units,                     \
-            static_cast<CDFT *>(g->d_cdf), g->d_q16, g->d_col, g->d_edge, g->d_val, smem_elems, d_flag, d_block_min, d_block_max); \
+            static_cast<CDFT *>(g->d_cdf), nullptr, g->d_col, nullptr, g->d_val, smem_elems, d_flag, d_block_min, d_block_max); \
     } while (0)
     if (cdf_mode == CYP_CDF_EXACT) {
         if (val_f32) K1_LAUNCH(double, float); else K1_LAUNCH(double, double);
@@ -376,7 +434,10 @@ static int graph_create_impl(int device, int64_t n_cells, int64_t nnz, const int
     dev_free(d_raw_col);
     dev_free(d_raw_val);
 #undef G_CUDA
-    const int rc2 = build_rows_v2(g, h_row_ptr);        // K1b: fused rows for the default step kernel (rows_v2.cu)
+    int rc2 = build_rows_v2(g, h_row_ptr);              // K1b: fused rows for the default step kernel (rows_v2.cu)
+    // the 16-bit codes and 16-byte edge records of the other step kernels: now if they are the default for this
+    // graph, else on first use (ensure_edge_records)
+    if (rc2 == CYP_OK && !g->v2_ok) rc2 = ensure_edge_records(g);
     if (rc2 != CYP_OK) {
         graph_free(g);
         return rc2;
@@ -416,6 +477,16 @@ extern "C" int cyp_graph_info(const cyp_graph *g, int64_t *n_cells, int64_t *nnz
     if (cdf_mode) *cdf_mode = g->cdf_mode;
     if (device) *device = g->device;
     if (device_bytes) *device_bytes = g->device_bytes;
+    return CYP_OK;
+}
+
+extern "C" int cyp_graph_layout(const cyp_graph *g, int *fused, int64_t *row_block_bytes, int64_t *target_word_bytes,
+                                int32_t *max_block_bytes) {
+    CYP_REQUIRE(g != nullptr, "cyp_graph_layout: NULL graph");
+    if (fused) *fused = g->v2_ok;
+    if (row_block_bytes) *row_block_bytes = g->v2_ok ? g->v2_sectors * 32 : 0;
+    if (target_word_bytes) *target_word_bytes = g->v2_ok ? g->v2_edge_units * 16 : 0;
+    if (max_block_bytes) *max_block_bytes = g->v2_ok ? g->v2_max_sectors * 32 : 0;
     return CYP_OK;
 }
 

@@ -105,18 +105,26 @@ int build_rows_v2(cyp_graph *g, const int64_t *h_row_ptr) {
     if (!(g->q16_ok && g->monotone)) return CYP_OK;
     if (g->max_len > 65535) return CYP_OK;
     if (const char *off = getenv("CYP_NO_V2")) if (off[0] == '1') return CYP_OK;
-    int extra = 0;                                       // whole extra sectors of inlined targets per row (experiments)
-    if (const char *e = getenv("CYP_V2_EXTRA")) extra = atoi(e);
     const int64_t n = g->n;
+    // Extra sectors of inlined targets per row.  More inlining means fewer second gathers but more bytes per step:
+    // on B200 it pays while the fused rows stay L2 resident (C3, 100k cells: 87 vs 79 G walker-steps/s) and costs
+    // at atlas scale, where DRAM bytes per step are what counts (C4: 51 vs 57 G).  CYP_V2_EXTRA overrides.
+    int extra = -1;
+    if (const char *e = getenv("CYP_V2_EXTRA")) extra = atoi(e);
+    if (extra < 0) {
+        int64_t sectors0 = 0;
+        for (int64_t r = 0; r < n; ++r) sectors0 += (v2_used_bytes(static_cast<int>(h_row_ptr[r + 1] - h_row_ptr[r])) + 31) / 32;
+        extra = ((sectors0 + n) * 32 <= (32ll << 20)) ? 1 : 0;
+    }
     std::vector<uint32_t> word(static_cast<size_t>(n)), ebase(static_cast<size_t>(n));
     int64_t sectors = 0, units = 0;
     int max_sectors = 0;
     for (int64_t r = 0; r < n; ++r) {
         const int len = static_cast<int>(h_row_ptr[r + 1] - h_row_ptr[r]);
         int nsect = (v2_used_bytes(len) + 31) / 32;
-        if (len > 0) nsect += extra;
+        if (len > 0 && nsect + extra <= kV2MaxSectors) nsect += extra;
         if (nsect > kV2MaxSectors) return CYP_OK;
-        if (sectors > static_cast<int64_t>(kWordOffMask) - nsect || units >= (1ll << 32) - 1) return CYP_OK;
+        if (sectors > static_cast<int64_t>(kWordOffMask) - nsect - kV2MaxSectors || units >= (1ll << 32) - 1) return CYP_OK;
         word[r] = (static_cast<uint32_t>(nsect) << kWordOffBits) | static_cast<uint32_t>(sectors);
         ebase[r] = static_cast<uint32_t>(units);
         sectors += nsect;

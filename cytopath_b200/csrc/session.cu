@@ -709,6 +709,8 @@ int run_chunk(cyp_session *s, uint32_t round, int64_t sims_per_root, int64_t wb,
             s->g->labels2_owner = s->id;
         }
     } else if (s->d_code8 && s->g->labels_owner != s->id) {     // label the edge records for this session (once)
+        const int rce = ensure_edge_records(s->g);
+        if (rce != CYP_OK) return rce;
         label_edges_kernel<<<blocks_for(s->g->padded, kThreads), kThreads, 0, st>>>(s->g->padded, s->g->d_edge, s->d_code8);
         S_CUDA(cudaGetLastError());
         s->g->labels_owner = s->id;

@@ -202,12 +202,18 @@ WalkVariant pick_walk_variant(const cyp_graph *g, int variant) {
     return WalkVariant{32, 4};
 }
 
-int launch_walk(const cyp_graph *g, const WalkParams &p, WalkMode mode, int variant, cudaStream_t stream) {
+int launch_walk(const cyp_graph *g, const WalkParams &p_in, WalkMode mode, int variant, cudaStream_t stream) {
     if (variant >= 9500 || (variant == 0 && walk_auto_is_v2(g))) {
-        const int rc = launch_walk_v2(g, p, mode, variant, stream);
+        const int rc = launch_walk_v2(g, p_in, mode, variant, stream);
         if (rc != kNotApplicable) return rc;
         return fail(CYP_E_INVALID, "launch_walk: the fused-row kernel (variant 95xx) does not apply to this graph");
     }
+    {                              // every other flavour reads the 16-byte edge records (and the 16-bit codes)
+        const int rc = ensure_edge_records(g);
+        if (rc != CYP_OK) return rc;
+    }
+    WalkParams p = p_in;
+    p.edge = g->d_edge;
     if (variant >= 9400) {        // paired flavour: on request only (same throughput as the default: K2 is bound by the memory system)
         const int rc = launch_walk_pp(g, p, mode, variant, stream);
         if (rc != kPpNotApplicable) return rc;

@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(1024, 1) walk_v2_kernel(const WalkParams p, co
     // cooperative copy geometry: lane = (group, chunk); instruction i moves chunk `chunk` of the block of lane (lane & ~(CPR-1)) + i
     const int chunk = lane & (CPR - 1);
     const uint32_t dst0 = smem_u32(slot) - static_cast<uint32_t>(chunk) * SLOT_STRIDE + static_cast<uint32_t>(chunk) * 16u;
-    const unsigned char *const src_c = p.rows2 + chunk * 16;
+    const uint32_t src_c = static_cast<uint32_t>(chunk) * 16u;     // byte offsets into rows2 fit 32 bits (< 2^27 sectors)
     const uint32_t need_thr = (static_cast<uint32_t>(chunk >> 1) + 1u) << kWordOffBits;     // word >= need_thr <=> sectors > chunk / 2
 
     const int nt = p.nt;
@@ -61,8 +61,8 @@ __global__ void __launch_bounds__(1024, 1) walk_v2_kernel(const WalkParams p, co
 #pragma unroll
         for (int i = 0; i < CPR; ++i) {
             const uint32_t wd = __shfl_sync(0xffffffffu, word, i, CPR);
-            const unsigned char *src = src_c + static_cast<uint64_t>(wd & kWordOffMask) * 32u;
-            if (wd >= need_thr) cp_async16(dst0 + static_cast<uint32_t>(i) * SLOT_STRIDE, src);
+            const uint32_t off = (wd << 5) + src_c;                  // the shift drops the sector count
+            if (wd >= need_thr) cp_async16(dst0 + static_cast<uint32_t>(i) * SLOT_STRIDE, p.rows2 + off);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(1024, 1) walk_v2_kernel(const WalkParams p, co
 
 struct V2Config {
     int cpr;
+    int ctas_per_sm;
     int threads;
     int log_n;
     size_t smem;
@@ -180,7 +181,9 @@ static bool v2_config(const cyp_graph *g, int variant, int64_t n_walkers, int sm
     while (cpr * 16 < g->v2_max_sectors * 32) cpr <<= 1;
     if (cpr > 32) return false;
     const size_t stride = 16 * cpr + 32;
-    int threads = static_cast<int>((226 * 1024) / stride) / 32 * 32;
+    int ctas = 1;
+    if (variant > 9600) { ctas = 2; variant -= 100; }     // 96xx: two CTAs per SM (experiment)
+    int threads = static_cast<int>((226 * 1024 / ctas - 1024) / stride) / 32 * 32;
     if (threads > 1024) threads = 1024;
     if (variant > 9500) {
         threads = (variant - 9500) * 32 < threads ? (variant - 9500) * 32 : threads;
@@ -195,7 +198,7 @@ static bool v2_config(const cyp_graph *g, int variant, int64_t n_walkers, int sm
     if (threads < 32) threads = 32;
     int log_n = 1;
     while ((1 << log_n) < g->max_len) ++log_n;
-    *out = V2Config{cpr, threads, log_n, static_cast<size_t>(threads) * stride};
+    *out = V2Config{cpr, ctas, threads, log_n, static_cast<size_t>(threads) * stride};
     return true;
 }
 
@@ -219,7 +222,8 @@ static int launch_v2_one(const WalkParams &p, const V2Config &c, int sm_count, c
         smem_set = c.smem;
     }
     const int64_t need = (p.n_walkers + c.threads - 1) / c.threads;
-    const unsigned grid = static_cast<unsigned>(need < sm_count ? need : sm_count);     // persistent: one CTA per SM
+    const int64_t resident = static_cast<int64_t>(sm_count) * c.ctas_per_sm;
+    const unsigned grid = static_cast<unsigned>(need < resident ? need : resident);       // persistent CTAs
     if (grid == 0) return CYP_OK;
     kernel<<<grid, c.threads, c.smem, stream>>>(p, c.log_n);
     CYP_CUDA(cudaGetLastError());

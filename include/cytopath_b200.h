@@ -73,6 +73,10 @@ int cyp_graph_info(const cyp_graph *g, int64_t *n_cells, int64_t *nnz, int32_t *
                    int *cdf_mode, int *device, int64_t *device_bytes);
 /* CDF values in CSR order: float[nnz] (reference mode) or double[nnz] (exact mode). */
 int cyp_graph_fetch_cdf(const cyp_graph *g, void *h_cdf);
+/* Fused-row layout of the default step kernel: *fused = 1 when the graph has it (else the
+ * other outputs are 0), bytes of the row blocks, bytes of the 4-byte target words, largest block in bytes. */
+int cyp_graph_layout(const cyp_graph *g, int *fused, int64_t *row_block_bytes, int64_t *target_word_bytes,
+                     int32_t *max_block_bytes);
 /* Milliseconds the K1 prefix-sum kernel took when the graph was created (CUDA events). */
 int cyp_graph_build_ms(const cyp_graph *g, float *ms);
 

@@ -221,7 +221,7 @@ def test_k2_bit_exact_vs_oracle_all_variants(gname, mode, omode):
                                          ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
             torch.cuda.synchronize()
             np.testing.assert_array_equal(out.cpu().numpy(), wnt, err_msg="%s nt=%d" % (g.variant_name(variant), n_t))
-    assert "walk_v2_kernel" in g.variant_name(0)              # and it is what the auto variant picks
+    assert ("walk_v2_kernel" in g.variant_name(0)) == (gname != "k200")     # the auto variant picks it, except for long rows
     # auto variant through the host entry point, a shard in the middle of the round
     got = g.walk(roots, sims, nt, seed=seed, round_idx=rnd, walker_begin=100, n_walkers=211, strict=False)
     np.testing.assert_array_equal(got, want[100:311])
