@@ -166,6 +166,15 @@ __global__ void __launch_bounds__(1024, 1) walk_v2_kernel(const WalkParams p, co
     }
 }
 
+// Tried on C4 and dropped (gpurun_out/flags.log, profiles/r01_v2_experiments.md): L2 cache hints (streaming
+// trajectory stores, evict-first target gathers, evict-last row copies: 52.2-52.3 G walker-steps/s with any
+// combination, i.e. no effect), a persisting-L2 access-policy window on the fused rows (hitRatio 0.3..1.0: 24-34 G,
+// much worse), two CTAs of 512..640 threads per SM (57.7-58.6 vs 57.0 G: no gain from more walkers in flight), a
+// fully unrolled 7-level search with a separate refine loop (3-6 % slower: two more dependent shared-memory round
+// trips per step), one or two extra sectors of inlined targets per row (51 / 48 vs 57 G at C4; +10 % at C3, where it
+// is now the default).  ncu (profiles/r01_ncu_walk_v2_fused_c4_exact.csv): L2 hit rate 73 %, the misses are ~20 G
+// random 32..128-byte DRAM gathers per second against a measured ceiling of 22-29 G/s for 128-byte gathers
+// (profiles/r01_gather_ceilings.log): the kernel is at the DRAM random-access rate of this graph.
 struct V2Config {
     int cpr;
     int ctas_per_sm;
