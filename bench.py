@@ -326,8 +326,13 @@ def run_b200(args, w):
 
     e2e_ms = {}
 
+    trace = bool(os.environ.get("CYP_E2E_TRACE"))
+
     def lap(name, t0):
-        e2e_ms[name] = e2e_ms.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
+        dt = (time.perf_counter() - t0) * 1e3
+        e2e_ms[name] = e2e_ms.get(name, 0.0) + dt
+        if trace:
+            print("e2e %-14s %7.2f ms" % (name, dt), file=sys.stderr)
         return time.perf_counter()
 
     def e2e_step(i):

@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/cytopath_b200.h"
 
@@ -157,8 +158,22 @@ struct cyp_graph {
 };
 
 namespace cyp {
-// K1b (rows_v2.cu): builds the fused rows from K1's output; sets g->v2_ok.
-int build_rows_v2(cyp_graph *g, const int64_t *h_row_ptr);
+// K1b (rows_v2.cu): the fused rows, built from K1's output chunk by chunk; v2_finish sets g->v2_ok.
+struct V2Build {
+    bool planned = false;
+    std::vector<uint32_t> word, ebase;       // per cell: row word; start of its targets in edge4 (units of 4 words)
+    int64_t sectors = 0, units = 0;
+    int max_sectors = 0;
+    size_t rows_bytes = 0;
+    uint32_t *d_ebase = nullptr;
+    int *d_bad = nullptr;
+};
+bool v2_plan(const cyp_graph *g, const int64_t *h_row_ptr, V2Build *b);
+cudaError_t v2_alloc(cyp_graph *g, V2Build *b);
+cudaError_t v2_upload(cyp_graph *g, V2Build *b, cudaStream_t stream);
+cudaError_t v2_launch(cyp_graph *g, V2Build *b, int64_t row_begin, int64_t row_end, cudaStream_t stream);
+cudaError_t v2_finish(cyp_graph *g, V2Build *b, bool codes_ok);
+void v2_release(cyp_graph *g, V2Build *b);
 // graph.cu: builds d_q16 and d_edge (the arrays of the step kernels other than walk_v2.cu) if they do not exist yet.
 // Synchronous, default stream; call before launching one of those kernels.
 int ensure_edge_records(const cyp_graph *g);

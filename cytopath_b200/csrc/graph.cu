@@ -81,7 +81,7 @@ __device__ __forceinline__ uint16_t cdf_code(double acc, int *flags) {
 
 template <typename CdfT, typename ValT>
 __global__ void __launch_bounds__(kK1Threads)
-build_cdf_kernel(int64_t n, const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ raw_col,
+build_cdf_kernel(int64_t row_begin, int64_t n, const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ raw_col,
                  const ValT *__restrict__ raw_val, const RowInfo *__restrict__ rows, int align_elems,
                  int64_t total_units, CdfT *__restrict__ cdf, uint16_t *__restrict__ q16, int32_t *__restrict__ col,
                  EdgeRec *__restrict__ edge, double *__restrict__ val, int smem_elems, int *__restrict__ negative_flag,
@@ -89,8 +89,9 @@ build_cdf_kernel(int64_t n, const int64_t *__restrict__ row_ptr, const int32_t *
     extern __shared__ double s_val[];                 // [smem_elems] raw values, then cumulative sums in place
     __shared__ int64_t s_src[kK1Threads + 1];         // CSR offsets of the CTA's rows
     __shared__ int64_t s_dst[kK1Threads + 1];         // padded offsets of the CTA's rows
-    const int64_t r0 = static_cast<int64_t>(blockIdx.x) * kK1Threads;
+    const int64_t r0 = row_begin + static_cast<int64_t>(blockIdx.x) * kK1Threads;     // row_begin is a multiple of kK1Threads
     const int64_t r1 = min(r0 + kK1Threads, n);
+    const int64_t block_id = r0 / kK1Threads;
     const int nrows = static_cast<int>(r1 - r0);
     for (int i = threadIdx.x; i <= nrows; i += kK1Threads) {
         const int64_t r = r0 + i;
@@ -193,8 +194,8 @@ build_cdf_kernel(int64_t n, const int64_t *__restrict__ row_ptr, const int32_t *
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int w = 1; w < kK1Threads / 32; ++w) { lo = fmin(lo, s_min[w]); hi = fmax(hi, s_max[w]); }
-        block_sum_min[blockIdx.x] = lo;
-        block_sum_max[blockIdx.x] = hi;
+        block_sum_min[block_id] = lo;
+        block_sum_max[block_id] = hi;
     }
 }
 
@@ -291,6 +292,9 @@ static void graph_free(cyp_graph *g) {
     delete g;
 }
 
+// cyp_graph_create: upload + K1 + K1b as a pipeline.  The CSR arrays travel in chunks of rows on a copy stream; the
+// host lays out the rows meanwhile; K1 and K1b of a chunk start as soon as the chunk has landed, so at atlas scale
+// (628 MB of CSR over PCIe) the kernels and the host work hide behind the upload.
 static int graph_create_impl(int device, int64_t n_cells, int64_t nnz, const int64_t *h_row_ptr, const int32_t *h_col,
                              const void *h_val, bool val_f32, int cdf_mode, cyp_graph **out) {
     CYP_REQUIRE(out != nullptr, "cyp_graph_create: out is NULL");
@@ -312,45 +316,38 @@ static int graph_create_impl(int device, int64_t n_cells, int64_t nnz, const int
     g->nnz = nnz;
     g->align_elems = kRowAlign;
     const int A = g->align_elems;
-
-    // host: padded row offsets (O(n))
-    std::vector<RowInfo> rows(static_cast<size_t>(n_cells));
-    int64_t units = 0;
-    int32_t max_len = 0;
-    for (int64_t r = 0; r < n_cells; ++r) {
-        const int64_t len = h_row_ptr[r + 1] - h_row_ptr[r];
-        if (len < 0 || len > (1ll << 30)) {
-            delete g;
-            return fail(CYP_E_INVALID, "cyp_graph_create: row_ptr not monotone");
-        }
-        rows[r].off_units = static_cast<uint32_t>(units);
-        rows[r].len = static_cast<uint32_t>(len);
-        units += (len + A - 1) / A;
-        if (len > max_len) max_len = static_cast<int32_t>(len);
-    }
-    if (units >= (1ll << 32)) {
-        delete g;
-        return fail(CYP_E_INVALID, "cyp_graph_create: matrix too large for 32-bit row units");
-    }
-    g->padded = units * A + 4 * A;                     // slack so vector loads of a last partial chunk stay in bounds
-    g->max_len = max_len;
-    g->mean_len = static_cast<double>(nnz) / static_cast<double>(n_cells);
     const size_t cdf_elem = (cdf_mode == CYP_CDF_EXACT) ? 8 : 4;
+    const size_t val_elem = val_f32 ? sizeof(float) : sizeof(double);
 
+    constexpr int kMaxChunks = 8;
     int32_t *d_raw_col = nullptr;
     void *d_raw_val = nullptr;
     double *d_block_min = nullptr, *d_block_max = nullptr;
     int *d_flag = nullptr;
-    const size_t val_elem = val_f32 ? sizeof(float) : sizeof(double);
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaStream_t s_copy = nullptr, s_aux = nullptr, s_comp = nullptr;
+    cudaEvent_t ev_alloc = nullptr, ev_small = nullptr, ev_chunk[kMaxChunks] = {}, ev_t[kMaxChunks][2] = {};
+    V2Build v2;
+    auto release_tmp = [&]() {
+        if (s_copy) cudaStreamSynchronize(s_copy);
+        if (s_aux) cudaStreamSynchronize(s_aux);
+        if (s_comp) cudaStreamSynchronize(s_comp);
+        dev_free(d_raw_col); dev_free(d_raw_val); dev_free(d_flag); dev_free(d_block_min); dev_free(d_block_max);
+        d_raw_col = nullptr; d_raw_val = nullptr; d_flag = nullptr; d_block_min = d_block_max = nullptr;
+        if (ev_alloc) cudaEventDestroy(ev_alloc);
+        if (ev_small) cudaEventDestroy(ev_small);
+        for (int c = 0; c < kMaxChunks; ++c) {
+            if (ev_chunk[c]) cudaEventDestroy(ev_chunk[c]);
+            if (ev_t[c][0]) cudaEventDestroy(ev_t[c][0]);
+            if (ev_t[c][1]) cudaEventDestroy(ev_t[c][1]);
+        }
+        if (s_copy) cudaStreamDestroy(s_copy);
+        if (s_aux) cudaStreamDestroy(s_aux);
+        if (s_comp) cudaStreamDestroy(s_comp);
+        ev_alloc = ev_small = nullptr; s_copy = s_aux = s_comp = nullptr;
+    };
     auto cleanup = [&](int code, const std::string &msg) {
-        dev_free(d_raw_col);
-        dev_free(d_raw_val);
-        dev_free(d_flag);
-        dev_free(d_block_min);
-        dev_free(d_block_max);
-        if (e0) cudaEventDestroy(e0);
-        if (e1) cudaEventDestroy(e1);
+        release_tmp();
+        v2_release(g, &v2);
         graph_free(g);
         return fail(code, msg);
     };
@@ -361,86 +358,145 @@ static int graph_create_impl(int device, int64_t n_cells, int64_t nnz, const int
                                               std::string(#expr) + ": " + cudaGetErrorString(_e));    \
     } while (0)
 
-    G_CUDA(dev_alloc(&g->d_row, sizeof(RowInfo) * n_cells));
+    // ---- 1. raw CSR on its way: chunks of rows (multiples of kK1Threads rows, so K1's CTAs never straddle a chunk)
+    const int n_chunks = nnz < (4 << 20) ? 1 : kMaxChunks;
+    int64_t chunk_rows = (n_cells + n_chunks - 1) / n_chunks;
+    chunk_rows = (chunk_rows + kK1Threads - 1) / kK1Threads * kK1Threads;
+    G_CUDA(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
+    G_CUDA(cudaStreamCreateWithFlags(&s_aux, cudaStreamNonBlocking));
+    G_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
+    G_CUDA(cudaEventCreateWithFlags(&ev_alloc, cudaEventDisableTiming));
+    G_CUDA(cudaEventCreateWithFlags(&ev_small, cudaEventDisableTiming));
     G_CUDA(dev_alloc(&g->d_row_ptr, sizeof(int64_t) * (n_cells + 1)));
+    G_CUDA(dev_alloc(&d_raw_col, sizeof(int32_t) * nnz));
+    G_CUDA(dev_alloc(&d_raw_val, val_elem * nnz));
+    G_CUDA(cudaEventRecord(ev_alloc, nullptr));                  // device memory comes from the default stream's pool
+    G_CUDA(cudaStreamWaitEvent(s_copy, ev_alloc, 0));
+    G_CUDA(cudaMemcpyAsync(g->d_row_ptr, h_row_ptr, sizeof(int64_t) * (n_cells + 1), cudaMemcpyHostToDevice, s_copy));
+    int used_chunks = 0;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int64_t rb = std::min<int64_t>(static_cast<int64_t>(c) * chunk_rows, n_cells), re = std::min<int64_t>(rb + chunk_rows, n_cells);
+        if (rb >= re) break;
+        const int64_t a = h_row_ptr[rb], b = h_row_ptr[re];
+        if (!(a >= 0 && b >= a && b <= nnz)) return cleanup(CYP_E_INVALID, "cyp_graph_create: row_ptr not monotone");
+        if (b > a) {
+            G_CUDA(cudaMemcpyAsync(d_raw_col + a, h_col + a, sizeof(int32_t) * (b - a), cudaMemcpyHostToDevice, s_copy));
+            G_CUDA(cudaMemcpyAsync(static_cast<char *>(d_raw_val) + val_elem * a, static_cast<const char *>(h_val) + val_elem * a, val_elem * (b - a),
+                                   cudaMemcpyHostToDevice, s_copy));
+        }
+        G_CUDA(cudaEventCreateWithFlags(&ev_chunk[c], cudaEventDisableTiming));
+        G_CUDA(cudaEventRecord(ev_chunk[c], s_copy));
+        used_chunks = c + 1;
+    }
+    // ---- 2. host, while the copies run: padded row offsets and the fused-row layout (O(n))
+    std::vector<RowInfo> rows(static_cast<size_t>(n_cells));
+    int64_t units = 0;
+    int32_t max_len = 0;
+    for (int64_t r = 0; r < n_cells; ++r) {
+        const int64_t len = h_row_ptr[r + 1] - h_row_ptr[r];
+        if (len < 0 || len > (1ll << 30)) return cleanup(CYP_E_INVALID, "cyp_graph_create: row_ptr not monotone");
+        rows[r].off_units = static_cast<uint32_t>(units);
+        rows[r].len = static_cast<uint32_t>(len);
+        units += (len + A - 1) / A;
+        if (len > max_len) max_len = static_cast<int32_t>(len);
+    }
+    if (units >= (1ll << 32)) return cleanup(CYP_E_INVALID, "cyp_graph_create: matrix too large for 32-bit row units");
+    g->padded = units * A + 4 * A;                     // slack so vector loads of a last partial chunk stay in bounds
+    g->max_len = max_len;
+    g->mean_len = static_cast<double>(nnz) / static_cast<double>(n_cells);
+    const bool want_v2 = v2_plan(g, h_row_ptr, &v2);
+
+    // ---- 3. the other device arrays (default stream)
+    G_CUDA(dev_alloc(&g->d_row, sizeof(RowInfo) * n_cells));
     G_CUDA(dev_alloc(&g->d_cdf, cdf_elem * g->padded));
     G_CUDA(dev_alloc(&g->d_col, sizeof(int32_t) * g->padded));
     G_CUDA(dev_alloc(&g->d_val, sizeof(double) * g->padded));
-    G_CUDA(dev_alloc(&d_raw_col, sizeof(int32_t) * nnz));
-    G_CUDA(dev_alloc(&d_raw_val, val_elem * nnz));
     G_CUDA(dev_alloc(&d_flag, sizeof(int)));
-    G_CUDA(cudaMemset(d_flag, 0, sizeof(int)));
-    g->device_bytes = sizeof(RowInfo) * n_cells + sizeof(int64_t) * (n_cells + 1) +
-                      (cdf_elem + sizeof(int32_t) + sizeof(double)) * g->padded;
-    G_CUDA(cudaMemcpy(g->d_row, rows.data(), sizeof(RowInfo) * n_cells, cudaMemcpyHostToDevice));
-    G_CUDA(cudaMemcpy(g->d_row_ptr, h_row_ptr, sizeof(int64_t) * (n_cells + 1), cudaMemcpyHostToDevice));
-    G_CUDA(cudaMemcpy(d_raw_col, h_col, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice));
-    G_CUDA(cudaMemcpy(d_raw_val, h_val, val_elem * nnz, cudaMemcpyHostToDevice));
+    const unsigned total_blocks = static_cast<unsigned>((n_cells + kK1Threads - 1) / kK1Threads);
+    G_CUDA(dev_alloc(&d_block_min, sizeof(double) * total_blocks));
+    G_CUDA(dev_alloc(&d_block_max, sizeof(double) * total_blocks));
+    G_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), nullptr));
+    g->device_bytes = sizeof(RowInfo) * n_cells + sizeof(int64_t) * (n_cells + 1) + (cdf_elem + sizeof(int32_t) + sizeof(double)) * g->padded;
     // slack region: never-matching padding
-    G_CUDA(cudaMemset(static_cast<char *>(g->d_cdf) + cdf_elem * units * A, 0xFF, cdf_elem * 4 * A));   // NaN: u <= NaN is false
-    G_CUDA(cudaMemset(g->d_col + units * A, 0xFF, sizeof(int32_t) * 4 * A));
-    G_CUDA(cudaMemset(g->d_val + units * A, 0, sizeof(double) * 4 * A));
+    G_CUDA(cudaMemsetAsync(static_cast<char *>(g->d_cdf) + cdf_elem * units * A, 0xFF, cdf_elem * 4 * A, nullptr));   // NaN: u <= NaN is false
+    G_CUDA(cudaMemsetAsync(g->d_col + units * A, 0xFF, sizeof(int32_t) * 4 * A, nullptr));
+    G_CUDA(cudaMemsetAsync(g->d_val + units * A, 0, sizeof(double) * 4 * A, nullptr));
+    if (want_v2) G_CUDA(v2_alloc(g, &v2));
+    G_CUDA(cudaEventRecord(ev_alloc, nullptr));                  // device memory comes from the default stream's pool
 
-    G_CUDA(cudaEventCreate(&e0));
-    G_CUDA(cudaEventCreate(&e1));
+    // the small host-made tables travel on their own stream (pageable: the call blocks until they are staged)
+    G_CUDA(cudaStreamWaitEvent(s_aux, ev_alloc, 0));
+    G_CUDA(cudaMemcpyAsync(g->d_row, rows.data(), sizeof(RowInfo) * n_cells, cudaMemcpyHostToDevice, s_aux));
+    if (want_v2) G_CUDA(v2_upload(g, &v2, s_aux));
+    G_CUDA(cudaEventRecord(ev_small, s_aux));
+
+    // ---- 4. K1 (+ K1b) per chunk
     // staging buffer: 1.5x a typical 128-row slice (so several CTAs fit an SM), at most 160 KB
     int smem_elems = static_cast<int>(1.5 * kK1Threads * g->mean_len) + 256;
     if (smem_elems < 2048) smem_elems = 2048;
     if (smem_elems > 20 * 1024) smem_elems = 20 * 1024;
     const int smem_bytes = smem_elems * static_cast<int>(sizeof(double));
-    const unsigned grid = static_cast<unsigned>((n_cells + kK1Threads - 1) / kK1Threads);
-    G_CUDA(dev_alloc(&d_block_min, sizeof(double) * grid));
-    G_CUDA(dev_alloc(&d_block_max, sizeof(double) * grid));
-    G_CUDA(cudaEventRecord(e0));
+    G_CUDA(cudaStreamWaitEvent(s_comp, ev_alloc, 0));
+    G_CUDA(cudaStreamWaitEvent(s_comp, ev_small, 0));
 #define K1_LAUNCH(CDFT, VALT)                                                                                               \
     do {                                                                                                                    \
         G_CUDA(cudaFuncSetAttribute(build_cdf_kernel<CDFT, VALT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); \
-        build_cdf_kernel<CDFT, VALT><<<grid, kK1Threads, smem_bytes>>>(                                                     \
-            n_cells, g->d_row_ptr, d_raw_col, static_cast<const VALT *>(d_raw_val), g->d_row, A, units,                     \
+        build_cdf_kernel<CDFT, VALT><<<grid, kK1Threads, smem_bytes, s_comp>>>(                                             \
+            rb, n_cells, g->d_row_ptr, d_raw_col, static_cast<const VALT *>(d_raw_val), g->d_row, A, units,                 \
             static_cast<CDFT *>(g->d_cdf), nullptr, g->d_col, nullptr, g->d_val, smem_elems, d_flag, d_block_min, d_block_max); \
     } while (0)
-    if (cdf_mode == CYP_CDF_EXACT) {
-        if (val_f32) K1_LAUNCH(double, float); else K1_LAUNCH(double, double);
-    } else {
-        if (val_f32) K1_LAUNCH(float, float); else K1_LAUNCH(float, double);
+    for (int c = 0; c < used_chunks; ++c) {
+        const int64_t rb = static_cast<int64_t>(c) * chunk_rows, re = std::min<int64_t>(rb + chunk_rows, n_cells);
+        const unsigned grid = static_cast<unsigned>((re - rb + kK1Threads - 1) / kK1Threads);
+        G_CUDA(cudaEventCreate(&ev_t[c][0]));
+        G_CUDA(cudaEventCreate(&ev_t[c][1]));
+        G_CUDA(cudaStreamWaitEvent(s_comp, ev_chunk[c], 0));
+        G_CUDA(cudaEventRecord(ev_t[c][0], s_comp));
+        if (cdf_mode == CYP_CDF_EXACT) {
+            if (val_f32) K1_LAUNCH(double, float); else K1_LAUNCH(double, double);
+        } else {
+            if (val_f32) K1_LAUNCH(float, float); else K1_LAUNCH(float, double);
+        }
+        G_CUDA(cudaGetLastError());
+        if (want_v2) G_CUDA(v2_launch(g, &v2, rb, re, s_comp));
+        G_CUDA(cudaEventRecord(ev_t[c][1], s_comp));
     }
 #undef K1_LAUNCH
-    G_CUDA(cudaGetLastError());
-    G_CUDA(cudaEventRecord(e1));
-    G_CUDA(cudaEventSynchronize(e1));
-    G_CUDA(cudaEventElapsedTime(&g->build_ms, e0, e1));
+    G_CUDA(cudaStreamSynchronize(s_comp));
+    g->build_ms = 0.f;
+    for (int c = 0; c < used_chunks; ++c) {
+        float ms = 0.f;
+        G_CUDA(cudaEventElapsedTime(&ms, ev_t[c][0], ev_t[c][1]));
+        g->build_ms += ms;
+    }
+
+    // ---- 5. what K1 found out
     int negative = 0;
     G_CUDA(cudaMemcpy(&negative, d_flag, sizeof(int), cudaMemcpyDeviceToHost));
     g->monotone = (negative & 1) ? 0 : 1;
     g->q16_ok = (negative == 0) ? 1 : 0;
-    dev_free(d_flag);
-    d_flag = nullptr;
     {
-        std::vector<double> bmin(grid), bmax(grid);
-        G_CUDA(cudaMemcpy(bmin.data(), d_block_min, sizeof(double) * grid, cudaMemcpyDeviceToHost));
-        G_CUDA(cudaMemcpy(bmax.data(), d_block_max, sizeof(double) * grid, cudaMemcpyDeviceToHost));
+        std::vector<double> bmin(total_blocks), bmax(total_blocks);
+        G_CUDA(cudaMemcpy(bmin.data(), d_block_min, sizeof(double) * total_blocks, cudaMemcpyDeviceToHost));
+        G_CUDA(cudaMemcpy(bmax.data(), d_block_max, sizeof(double) * total_blocks, cudaMemcpyDeviceToHost));
         g->row_sum_min = bmin[0];
         g->row_sum_max = bmax[0];
-        for (unsigned b = 1; b < grid; ++b) {
+        for (unsigned b = 1; b < total_blocks; ++b) {
             g->row_sum_min = std::min(g->row_sum_min, bmin[b]);
             g->row_sum_max = std::max(g->row_sum_max, bmax[b]);
         }
     }
-    dev_free(d_block_min);
-    dev_free(d_block_max);
-    d_block_min = d_block_max = nullptr;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    dev_free(d_raw_col);
-    dev_free(d_raw_val);
+    if (want_v2) G_CUDA(v2_finish(g, &v2, g->q16_ok && g->monotone));
+    release_tmp();
 #undef G_CUDA
-    int rc2 = build_rows_v2(g, h_row_ptr);              // K1b: fused rows for the default step kernel (rows_v2.cu)
     // the 16-bit codes and 16-byte edge records of the other step kernels: now if they are the default for this
     // graph, else on first use (ensure_edge_records)
-    if (rc2 == CYP_OK && !g->v2_ok) rc2 = ensure_edge_records(g);
-    if (rc2 != CYP_OK) {
-        graph_free(g);
-        return rc2;
+    if (!g->v2_ok) {
+        const int rc2 = ensure_edge_records(g);
+        if (rc2 != CYP_OK) {
+            graph_free(g);
+            return rc2;
+        }
     }
     *out = g;
     return CYP_OK;

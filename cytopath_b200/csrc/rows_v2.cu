@@ -35,12 +35,12 @@ __device__ __forceinline__ int code12(CdfT c, int *bad) {
 
 template <typename CdfT>
 __global__ void __launch_bounds__(256)
-build_rows_v2_kernel(int64_t n, const RowInfo *__restrict__ rows, const CdfT *__restrict__ cdf, const double *__restrict__ val,
+build_rows_v2_kernel(int64_t row_begin, int64_t row_end, const RowInfo *__restrict__ rows, const CdfT *__restrict__ cdf, const double *__restrict__ val,
                      const int32_t *__restrict__ col, const uint32_t *__restrict__ word, const uint32_t *__restrict__ ebase,
                      unsigned char *__restrict__ rows2, uint32_t *__restrict__ edge4, int *__restrict__ bad_flag) {
-    const int64_t r = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t r = row_begin + ((static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
-    if (r >= n) return;
+    if (r >= row_end) return;
     const RowInfo ri = rows[r];
     const int len = static_cast<int>(ri.len);
     const int64_t off = static_cast<int64_t>(ri.off_units) * kRowAlign;
@@ -99,12 +99,13 @@ build_rows_v2_kernel(int64_t n, const RowInfo *__restrict__ rows, const CdfT *__
 
 }  // namespace
 
-// Called at the end of cyp_graph_create.  Leaves g->v2_ok = 0 (and no v2 arrays) when the layout does not apply.
-int build_rows_v2(cyp_graph *g, const int64_t *h_row_ptr) {
-    g->v2_ok = 0;
-    if (!(g->q16_ok && g->monotone)) return CYP_OK;
-    if (g->max_len > 65535) return CYP_OK;
-    if (const char *off = getenv("CYP_NO_V2")) if (off[0] == '1') return CYP_OK;
+// ---- host side: cyp_graph_create drives these (graph.cu), chunk by chunk behind the CSR upload ----
+
+// Host-only layout of the fused rows.  Returns false when the layout does not apply to this matrix.
+bool v2_plan(const cyp_graph *g, const int64_t *h_row_ptr, V2Build *b) {
+    b->planned = false;
+    if (g->max_len > 65535) return false;
+    if (const char *off = getenv("CYP_NO_V2")) if (off[0] == '1') return false;
     const int64_t n = g->n;
     // Extra sectors of inlined targets per row.  More inlining means fewer second gathers but more bytes per step:
     // on B200 it pays while the fused rows stay L2 resident (C3, 100k cells: 87 vs 79 G walker-steps/s) and costs
@@ -116,78 +117,88 @@ int build_rows_v2(cyp_graph *g, const int64_t *h_row_ptr) {
         for (int64_t r = 0; r < n; ++r) sectors0 += (v2_used_bytes(static_cast<int>(h_row_ptr[r + 1] - h_row_ptr[r])) + 31) / 32;
         extra = ((sectors0 + n) * 32 <= (32ll << 20)) ? 1 : 0;
     }
-    std::vector<uint32_t> word(static_cast<size_t>(n)), ebase(static_cast<size_t>(n));
+    b->word.resize(static_cast<size_t>(n));
+    b->ebase.resize(static_cast<size_t>(n));
     int64_t sectors = 0, units = 0;
     int max_sectors = 0;
     for (int64_t r = 0; r < n; ++r) {
         const int len = static_cast<int>(h_row_ptr[r + 1] - h_row_ptr[r]);
         int nsect = (v2_used_bytes(len) + 31) / 32;
         if (len > 0 && nsect + extra <= kV2MaxSectors) nsect += extra;
-        if (nsect > kV2MaxSectors) return CYP_OK;
-        if (sectors > static_cast<int64_t>(kWordOffMask) - nsect - kV2MaxSectors || units >= (1ll << 32) - 1) return CYP_OK;
-        word[r] = (static_cast<uint32_t>(nsect) << kWordOffBits) | static_cast<uint32_t>(sectors);
-        ebase[r] = static_cast<uint32_t>(units);
+        if (nsect > kV2MaxSectors) return false;
+        if (sectors > static_cast<int64_t>(kWordOffMask) - nsect - kV2MaxSectors || units >= (1ll << 32) - 1) return false;
+        b->word[r] = (static_cast<uint32_t>(nsect) << kWordOffBits) | static_cast<uint32_t>(sectors);
+        b->ebase[r] = static_cast<uint32_t>(units);
         sectors += nsect;
         units += (len + 3) / 4;
         if (nsect > max_sectors) max_sectors = nsect;
     }
-    uint32_t *d_ebase = nullptr;
-    int *d_bad = nullptr;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    auto bail = [&](cudaError_t e, const char *what) {
-        dev_free(d_ebase); dev_free(d_bad);
+    b->sectors = sectors;
+    b->units = units;
+    b->max_sectors = max_sectors;
+    b->rows_bytes = static_cast<size_t>(sectors + kV2MaxSectors + 1) * 32;     // slack: a warp may copy a full slot past the last block
+    b->planned = true;
+    return true;
+}
+
+void v2_release(cyp_graph *g, V2Build *b) {
+    dev_free(b->d_ebase);
+    dev_free(b->d_bad);
+    b->d_ebase = nullptr;
+    b->d_bad = nullptr;
+    if (!g->v2_ok) {
         dev_free(g->d_rows2); dev_free(g->d_edge4); dev_free(g->d_word);
         g->d_rows2 = nullptr; g->d_edge4 = nullptr; g->d_word = nullptr;
-        if (e0) cudaEventDestroy(e0);
-        if (e1) cudaEventDestroy(e1);
-        return fail(e == cudaErrorMemoryAllocation ? CYP_E_NOMEM : CYP_E_CUDA, std::string("build_rows_v2: ") + what + ": " + cudaGetErrorString(e));
-    };
-#define V_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return bail(_e, #expr); } while (0)
-    const size_t rows_bytes = static_cast<size_t>(sectors + kV2MaxSectors + 1) * 32;     // slack: a warp may copy a full slot past the last block
-    V_CUDA(dev_alloc(&g->d_rows2, rows_bytes));
-    V_CUDA(dev_alloc(&g->d_edge4, sizeof(uint32_t) * 4 * static_cast<size_t>(units + 1)));
-    V_CUDA(dev_alloc(&g->d_word, sizeof(uint32_t) * n));
-    V_CUDA(dev_alloc(&d_ebase, sizeof(uint32_t) * n));
-    V_CUDA(dev_alloc(&d_bad, sizeof(int)));
-    V_CUDA(cudaMemset(d_bad, 0, sizeof(int)));
-    V_CUDA(cudaMemset(g->d_rows2, 0, rows_bytes));
-    V_CUDA(cudaMemcpy(g->d_word, word.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice));
-    V_CUDA(cudaMemcpy(d_ebase, ebase.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice));
-    V_CUDA(cudaEventCreate(&e0));
-    V_CUDA(cudaEventCreate(&e1));
-    const int threads = 256;
-    const unsigned grid = static_cast<unsigned>((n * 32 + threads - 1) / threads);
-    V_CUDA(cudaEventRecord(e0));
-    if (g->cdf_mode == CYP_CDF_EXACT)
-        build_rows_v2_kernel<double><<<grid, threads>>>(n, g->d_row, static_cast<const double *>(g->d_cdf), g->d_val, g->d_col, g->d_word,
-                                                        d_ebase, g->d_rows2, g->d_edge4, d_bad);
-    else
-        build_rows_v2_kernel<float><<<grid, threads>>>(n, g->d_row, static_cast<const float *>(g->d_cdf), g->d_val, g->d_col, g->d_word,
-                                                       d_ebase, g->d_rows2, g->d_edge4, d_bad);
-    V_CUDA(cudaGetLastError());
-    V_CUDA(cudaEventRecord(e1));
-    V_CUDA(cudaEventSynchronize(e1));
-    float ms = 0.f;
-    V_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-    int bad = 0;
-    V_CUDA(cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost));
-#undef V_CUDA
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    dev_free(d_ebase);
-    dev_free(d_bad);
-    if (bad) {                                           // a CDF value the 12-bit codes cannot hold: keep the old layout only
-        dev_free(g->d_rows2); dev_free(g->d_edge4); dev_free(g->d_word);
-        g->d_rows2 = nullptr; g->d_edge4 = nullptr; g->d_word = nullptr;
-        return CYP_OK;
     }
-    g->build_ms += ms;
-    g->v2_sectors = sectors;
-    g->v2_edge_units = units;
-    g->v2_max_sectors = max_sectors;
-    g->device_bytes += static_cast<int64_t>(rows_bytes + sizeof(uint32_t) * 4 * (units + 1) + sizeof(uint32_t) * n);
-    g->v2_ok = 1;
-    return CYP_OK;
+}
+
+// Device arrays (default stream).
+cudaError_t v2_alloc(cyp_graph *g, V2Build *b) {
+    cudaError_t e = dev_alloc(&g->d_rows2, b->rows_bytes);
+    if (e == cudaSuccess) e = dev_alloc(&g->d_edge4, sizeof(uint32_t) * 4 * static_cast<size_t>(b->units + 1));
+    if (e == cudaSuccess) e = dev_alloc(&g->d_word, sizeof(uint32_t) * g->n);
+    if (e == cudaSuccess) e = dev_alloc(&b->d_ebase, sizeof(uint32_t) * g->n);
+    if (e == cudaSuccess) e = dev_alloc(&b->d_bad, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemsetAsync(b->d_bad, 0, sizeof(int), nullptr);
+    if (e == cudaSuccess) e = cudaMemsetAsync(g->d_rows2, 0, b->rows_bytes, nullptr);
+    return e;
+}
+
+cudaError_t v2_upload(cyp_graph *g, V2Build *b, cudaStream_t stream) {
+    cudaError_t e = cudaMemcpyAsync(g->d_word, b->word.data(), sizeof(uint32_t) * g->n, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(b->d_ebase, b->ebase.data(), sizeof(uint32_t) * g->n, cudaMemcpyHostToDevice, stream);
+    return e;
+}
+
+// K1b for rows [row_begin, row_end) on `stream` (K1 has finished these rows on the same stream).
+cudaError_t v2_launch(cyp_graph *g, V2Build *b, int64_t row_begin, int64_t row_end, cudaStream_t stream) {
+    const int64_t rows = row_end - row_begin;
+    if (rows <= 0) return cudaSuccess;
+    const int threads = 256;
+    const unsigned grid = static_cast<unsigned>((rows * 32 + threads - 1) / threads);
+    if (g->cdf_mode == CYP_CDF_EXACT)
+        build_rows_v2_kernel<double><<<grid, threads, 0, stream>>>(row_begin, row_end, g->d_row, static_cast<const double *>(g->d_cdf), g->d_val,
+                                                                   g->d_col, g->d_word, b->d_ebase, g->d_rows2, g->d_edge4, b->d_bad);
+    else
+        build_rows_v2_kernel<float><<<grid, threads, 0, stream>>>(row_begin, row_end, g->d_row, static_cast<const float *>(g->d_cdf), g->d_val,
+                                                                  g->d_col, g->d_word, b->d_ebase, g->d_rows2, g->d_edge4, b->d_bad);
+    return cudaGetLastError();
+}
+
+// After the build stream has been synchronised: commits the layout (g->v2_ok = 1) unless a code did not fit.
+cudaError_t v2_finish(cyp_graph *g, V2Build *b, bool codes_ok) {
+    int bad = 0;
+    cudaError_t e = cudaMemcpy(&bad, b->d_bad, sizeof(int), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return e;
+    if (!bad && codes_ok) {
+        g->v2_sectors = b->sectors;
+        g->v2_edge_units = b->units;
+        g->v2_max_sectors = b->max_sectors;
+        g->device_bytes += static_cast<int64_t>(b->rows_bytes + sizeof(uint32_t) * 4 * (b->units + 1) + sizeof(uint32_t) * g->n);
+        g->v2_ok = 1;
+    }
+    v2_release(g, b);
+    return cudaSuccess;
 }
 
 }  // namespace cyp
