@@ -67,47 +67,75 @@ def make_graph(w, world):
 
 
 class ClockSampler:
-    """nvidia-smi clocks line of B200_PROFILING.md, sampled every 50 ms during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks line of B200_PROFILING.md, sampled every 50 ms.  nvidia-smi needs ~1 s to attach (it touches
+    every GPU of the box, which visibly stalls kernels running on them), so it is started BEFORE the warm-up and the
+    samples are cut to the timed region afterwards by their timestamps."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu):
-        self.gpu, self.proc = gpu, None
+        self.gpu, self.proc, self.lines, self.thread = gpu, None, [], None
 
-    def start(self):
+    def start(self, wait_s=5.0):
+        import threading
+        if os.environ.get("CYP_NO_CLOCKS"):
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "50"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
         except Exception:
             self.proc = None
+            return
 
-    def stop(self):
+        def pump():
+            for line in self.proc.stdout:
+                self.lines.append(line)
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+        t0 = time.time()
+        while not self.lines and time.time() - t0 < wait_s:      # attached and sampling before anything is timed
+            time.sleep(0.02)
+
+    def stop(self, t_begin=None, t_end=None):
+        import datetime
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+        time.sleep(0.12)
         self.proc.terminate()
         try:
-            out, _ = self.proc.communicate(timeout=5)
+            self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-            out = ""
-        sm, mx, reasons, power = [], [], set(), []
-        for line in out.strip().splitlines():
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        rows = []
+        for line in list(self.lines):
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
+            if len(f) < 10:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[2]), float(f[3]), float(f[4]), f[6:10]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+        inside = [r for r in rows if t_begin is not None and t_begin - 0.03 <= r[0] <= t_end + 0.03]
+        where = "timed region"
+        if not inside and rows and t_begin is not None:          # region shorter than the sampling period: nearest samples
+            inside = sorted(rows, key=lambda r: abs(r[0] - 0.5 * (t_begin + t_end)))[:2]
+            where = "nearest to the timed region"
+        if not inside:
+            inside, where = rows, "whole run"
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        reasons = set()
+        for r in inside:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": float(max(power))}
+        return {"sm_mhz": float(np.median([r[1] for r in inside])), "sm_max_mhz": float(max(r[2] for r in inside)),
+                "reasons": sorted(reasons), "samples": len(inside), "samples_from": where,
+                "power_w_max": float(max(r[3] for r in inside))}
 
 
 def mean_visited_row_len(C, seq_sample):
@@ -212,7 +240,7 @@ def run_reference(args, w):
         "e2e": {"value": value, "unit": "walker-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_b200(args, w):
@@ -221,9 +249,16 @@ def run_b200(args, w):
     from cytopath_b200 import _lib
 
     rank, local_rank, world = env_world()
-    if world > 1:
+    no_dist = bool(os.environ.get("BENCH_NO_DIST"))          # diagnostic: ranks run unsynchronised, no NCCL
+    if world > 1 and not no_dist:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep NCCL's version banner off stdout (one JSON line only)
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # Connect the NCCL transports NOW, before the graph and the trajectory buffers exist: when the first collective
+        # runs after those allocations, NCCL's peer-to-peer set-up re-maps them and K2 runs 25-28 % slower
+        # (13.5 vs 10.5 ms per step on both ranks, profiles/r01_multi_gpu_probe.md).
+        dist.barrier()
+        torch.cuda.synchronize()
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     _lib.require_device(local_rank)
@@ -239,7 +274,7 @@ def run_b200(args, w):
     w0 = rank * W
 
     def barrier():
-        if world > 1:
+        if world > 1 and not no_dist:
             dist.barrier()
 
     # ---- resident state: graph (K1), roots, trajectory buffer
@@ -254,26 +289,31 @@ def run_b200(args, w):
 
     def step(i):
         _lib.check(L.cyp_walk_device(graph.handle, d_roots.data_ptr(), n_roots, sims_per_root, w0, W, nt, args.seed, i,
-                                     None, d_seq.data_ptr(), d_miss.data_ptr(), args.variant, sptr))
+                                     None, d_seq.data_ptr(), None if os.environ.get("BENCH_NO_MISS") else d_miss.data_ptr(), args.variant, sptr))
 
+    clocks = ClockSampler(local_rank)
+    clocks.start()                                               # attached before the warm-up, see ClockSampler
+    barrier()
     for i in range(args.warmup):
         step(i)
     torch.cuda.synchronize()
-    clocks = ClockSampler(local_rank)
     barrier()
-    clocks.start()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.time()
     e0.record(stream)
     for i in range(args.steps):
         step(args.warmup + i)
     e1.record(stream)
     torch.cuda.synchronize()
+    t_end = time.time()
     barrier()
     ms = e0.elapsed_time(e1)
-    clk = clocks.stop()
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    clk = clocks.stop(t_begin, t_end)
     if world > 1:
+        print("rank %d: %.3f ms per step (device time of its own K2 launches)" % (rank, ms / args.steps), file=sys.stderr)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1 and not no_dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     value = total * nt * args.steps / (ms_max * 1e-3)
@@ -306,8 +346,10 @@ def run_b200(args, w):
 
     if args.kernel_only:
         if rank == 0:
-            print(json.dumps({"metric": "walker_steps_per_sec", "value": value, "ms_per_step": ms_max / args.steps,
-                              "kernel": kernel_name, "roofline_frac": achieved / peak, "kernel_only": True}), flush=True)
+            emit({"metric": "walker_steps_per_sec", "value": value, "ms_per_step": ms_max / args.steps,
+                  "kernel": kernel_name, "roofline_frac": achieved / peak, "kernel_only": True})
+        if world > 1 and not no_dist:
+            dist.destroy_process_group()
         return
     # ---- e2e through the C ABI with host buffers (pinned), every step: upload CSR + K1 + round (K2+K3) + read-back
     row_ptr = torch.from_numpy(np.ascontiguousarray(C.indptr, dtype=np.int64)).pin_memory()
@@ -413,9 +455,30 @@ def run_b200(args, w):
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:
-        print(json.dumps(line), flush=True)
-    if world > 1:
+        emit(line)
+    if world > 1 and not no_dist:
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def own_stdout():
+    """stdout must carry ONE JSON line: everything else that writes to fd 1 (NCCL prints its version banner there,
+    whatever NCCL_DEBUG says) is sent to stderr; emit() writes the line to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -436,6 +499,7 @@ def main():
     if args.warmup < 3 and args.impl == "b200":
         print("note: fewer than 3 warm-up steps requested", file=sys.stderr)
     w = WORKLOADS[args.workload]
+    own_stdout()
     if args.impl == "reference":
         run_reference(args, w)
         return

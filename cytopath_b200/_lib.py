@@ -21,7 +21,7 @@ CDF_EXACT = 1
 E_NOCROSSING = -4
 
 EXPORTS = [
-    "cyp_version", "cyp_last_error", "cyp_device_count",
+    "cyp_version", "cyp_last_error", "cyp_device_count", "cyp_release_cached_memory",
     "cyp_graph_create", "cyp_graph_create_f32", "cyp_graph_row_sum_range", "cyp_graph_destroy", "cyp_graph_info", "cyp_graph_layout", "cyp_graph_fetch_cdf", "cyp_graph_build_ms",
     "cyp_power_iteration", "cyp_walk", "cyp_walk_device", "cyp_walk_variant_name", "cyp_transition_scores",
     "cyp_session_create", "cyp_session_destroy", "cyp_session_round", "cyp_session_rows",
@@ -75,6 +75,7 @@ def load():
     L.cyp_version.restype = ci
     L.cyp_last_error.restype = ctypes.c_char_p
     L.cyp_device_count.argtypes = [P(ci)]
+    L.cyp_release_cached_memory.argtypes = [ci]
     L.cyp_graph_create.argtypes = [ci, i64, i64, vp, vp, vp, ci, P(vp)]
     L.cyp_graph_create_f32.argtypes = [ci, i64, i64, vp, vp, vp, ci, P(vp)]
     L.cyp_graph_row_sum_range.argtypes = [vp, P(ctypes.c_double), P(ctypes.c_double)]
@@ -117,6 +118,11 @@ def device_count() -> int:
     n = ctypes.c_int(0)
     check(load().cyp_device_count(ctypes.byref(n)))
     return n.value
+
+
+def release_cached_memory(device: int = -1) -> None:
+    """Give the device memory the library keeps for reuse back to the driver (device < 0: all devices)."""
+    check(load().cyp_release_cached_memory(device))
 
 
 def require_device(device: int = 0):

@@ -31,6 +31,8 @@ int fail(int code, const std::string &msg);
 // memory instead of paying cudaMalloc/cudaFree each time.  All calls use the legacy default stream.
 cudaError_t dev_alloc(void **p, size_t bytes);
 void dev_free(void *p);
+size_t dev_cached_bytes(int dev);     // bytes of freed >= 64 MB blocks kept for exact-size reuse (graph.cu)
+void dev_release_cached(int dev);     // dev < 0: all devices
 template <typename T>
 inline cudaError_t dev_alloc(T **p, size_t bytes) { return dev_alloc(reinterpret_cast<void **>(p), bytes); }
 

@@ -10,6 +10,8 @@
 #include <cfloat>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include "common.cuh"
@@ -21,6 +23,45 @@ static thread_local std::string g_last_error;
 int fail(int code, const std::string &msg) {
     g_last_error = msg;
     return code;
+}
+
+// Blocks of 64 MB and more are additionally kept in an exact-size cache when they are freed: the CUDA pool hands
+// memory back quickly, but for multi-GB requests it often has to re-map physical pages into a new contiguous
+// virtual range (3-5 ms per 2.5 GB block at C4, and far worse when several processes of one box do it at
+// once), while sampling() and every step of a benchmark ask for the same few sizes again and again.
+// cyp_release_cached_memory() empties the cache and trims the pool.
+namespace {
+struct BigBlock { void *p; size_t bytes; int dev; };
+std::mutex g_big_mutex;
+std::vector<BigBlock> g_big_free;
+std::unordered_map<void *, BigBlock> g_big_live;
+constexpr size_t kBigBlock = 64ull << 20;
+constexpr size_t kBigCacheEntries = 32;
+
+void big_cache_flush(int dev) {            // dev < 0: all devices.  Caller holds the mutex.
+    std::vector<BigBlock> keep;
+    for (const BigBlock &b : g_big_free) {
+        if (dev >= 0 && b.dev != dev) { keep.push_back(b); continue; }
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (cur != b.dev) cudaSetDevice(b.dev);
+        cudaFreeAsync(b.p, nullptr);
+        if (cur != b.dev && cur >= 0) cudaSetDevice(cur);
+    }
+    g_big_free.swap(keep);
+}
+}  // namespace
+
+size_t dev_cached_bytes(int dev) {
+    std::lock_guard<std::mutex> lock(g_big_mutex);
+    size_t total = 0;
+    for (const BigBlock &b : g_big_free) if (b.dev == dev) total += b.bytes;
+    return total;
+}
+
+void dev_release_cached(int dev) {
+    std::lock_guard<std::mutex> lock(g_big_mutex);
+    big_cache_flush(dev);
 }
 
 cudaError_t dev_alloc(void **p, size_t bytes) {
@@ -37,10 +78,48 @@ cudaError_t dev_alloc(void **p, size_t bytes) {
         pool_ready[dev] = true;
     }
     *p = nullptr;
-    return cudaMallocAsync(p, bytes ? bytes : 1, nullptr);
+    if (bytes >= kBigBlock) {
+        std::lock_guard<std::mutex> lock(g_big_mutex);
+        for (size_t i = 0; i < g_big_free.size(); ++i) {
+            if (g_big_free[i].dev == dev && g_big_free[i].bytes == bytes) {
+                *p = g_big_free[i].p;
+                g_big_live[*p] = g_big_free[i];
+                g_big_free.erase(g_big_free.begin() + i);
+                return cudaSuccess;
+            }
+        }
+    }
+    e = cudaMallocAsync(p, bytes ? bytes : 1, nullptr);
+    if (e == cudaErrorMemoryAllocation) {          // give the cached blocks back and try once more
+        cudaGetLastError();
+        {
+            std::lock_guard<std::mutex> lock(g_big_mutex);
+            big_cache_flush(dev);
+        }
+        cudaStreamSynchronize(nullptr);
+        e = cudaMallocAsync(p, bytes ? bytes : 1, nullptr);
+    }
+    if (e == cudaSuccess && bytes >= kBigBlock) {
+        std::lock_guard<std::mutex> lock(g_big_mutex);
+        g_big_live[*p] = BigBlock{*p, bytes, dev};
+    }
+    return e;
 }
 void dev_free(void *p) {
-    if (p) cudaFreeAsync(p, nullptr);
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lock(g_big_mutex);
+        auto it = g_big_live.find(p);
+        if (it != g_big_live.end()) {
+            const BigBlock b = it->second;
+            g_big_live.erase(it);
+            if (g_big_free.size() < kBigCacheEntries) {
+                g_big_free.push_back(b);          // reusable in default-stream order, like cudaFreeAsync(p, 0)
+                return;
+            }
+        }
+    }
+    cudaFreeAsync(p, nullptr);
 }
 
 // One CTA handles kK1Threads consecutive rows.  The CTA's slice of the CSR value array is
@@ -269,6 +348,22 @@ using namespace cyp;
 
 extern "C" int cyp_version(void) { return CYP_VERSION; }
 extern "C" const char *cyp_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int cyp_release_cached_memory(int device) {
+    dev_release_cached(device);
+    int ndev = 0;
+    CYP_CUDA(cudaGetDeviceCount(&ndev));
+    for (int d = 0; d < ndev; ++d) {
+        if (device >= 0 && d != device) continue;
+        DeviceGuard guard(d);
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, d) == cudaSuccess) {
+            cudaDeviceSynchronize();
+            cudaMemPoolTrimTo(pool, 0);
+        }
+    }
+    return CYP_OK;
+}
 
 extern "C" int cyp_device_count(int *n) {
     CYP_REQUIRE(n != nullptr, "cyp_device_count: n is NULL");

@@ -15,6 +15,9 @@
 //                  the result is exact for any hash quality;
 //   gather_rows    survivors are appended, in walker order, to the device-resident store.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "walk.cuh"
@@ -673,8 +676,21 @@ size_t free_device_bytes(int device) {
         cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
         cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
         free_b += static_cast<size_t>(reserved - used);
-    return free_b;
+    return free_b + dev_cached_bytes(device);        // dev_alloc gives cached blocks back when the pool runs dry
 }
+
+// CYP_TRACE=1: host wall-clock between marks, to stderr (developer aid)
+struct Tracer {
+    bool on;
+    std::chrono::steady_clock::time_point t;
+    Tracer() : on(getenv("CYP_TRACE") != nullptr), t(std::chrono::steady_clock::now()) {}
+    void mark(const char *what) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[cyp trace] %-22s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+        t = now;
+    }
+};
 
 // One chunk of a round: walkers [wb, we).  K2 in filter mode, K3 within the chunk, survivors appended to
 // the store and to the round's record list.  Statistics are accumulated into *stats.
@@ -683,6 +699,7 @@ int run_chunk(cyp_session *s, uint32_t round, int64_t sims_per_root, int64_t wb,
     cudaStream_t st = nullptr;
     const int64_t W = we - wb;
     const int32_t ncol = s->max_steps, nt = s->max_steps - 1;
+    Tracer tr;
     Scratch sc;
     int32_t *d_seq = nullptr, *d_slot = nullptr;
     uint64_t *d_hash = nullptr;
@@ -697,6 +714,7 @@ int run_chunk(cyp_session *s, uint32_t round, int64_t sims_per_root, int64_t wb,
         S_CUDA(sc.alloc(&d_u, static_cast<size_t>(W) * nt));
         S_CUDA(cudaMemcpyAsync(d_u, h_uniforms, sizeof(double) * static_cast<size_t>(W) * nt, cudaMemcpyHostToDevice, st));
     }
+    tr.mark("chunk allocs");
     cudaEvent_t ev[3];
     for (auto &e : ev) S_CUDA(cudaEventCreate(&e));
     struct EvGuard { cudaEvent_t *e; ~EvGuard() { for (int i = 0; i < 3; ++i) cudaEventDestroy(e[i]); } } evg{ev};
@@ -728,6 +746,7 @@ int run_chunk(cyp_session *s, uint32_t round, int64_t sims_per_root, int64_t wb,
     int rc = launch_walk(s->g, p, mode, 0, st);
     if (rc != CYP_OK) return rc;
     S_CUDA(cudaEventRecord(ev[1], st));
+    tr.mark("K2 launched");
 
     // ---- K3
     if (s->min_clusters > 1 && s->d_code32) {
@@ -743,6 +762,7 @@ int run_chunk(cyp_session *s, uint32_t round, int64_t sims_per_root, int64_t wb,
     rc = compact_indices(W, PredSlotGE{d_slot, 0}, sc, &d_cand, &n_cand, st);
     if (rc != CYP_OK) return rc;
 
+    tr.mark("compact candidates");
     int64_t *d_kept = nullptr, n_kept = n_cand;      // candidate ranks that survive; nullptr = all
     int passes = 0;
     if (s->unique && n_cand > 1) {
@@ -753,9 +773,11 @@ int run_chunk(cyp_session *s, uint32_t round, int64_t sims_per_root, int64_t wb,
         if (rc != CYP_OK) return rc;
     }
 
+    tr.mark("dedup");
     // ---- append survivors to the store
     rc = grow_store(s, s->store_rows + n_kept);
     if (rc != CYP_OK) return rc;
+    tr.mark("grow_store");
     rc = ensure_records(s, s->n_records + n_kept);
     if (rc != CYP_OK) return rc;
     if (n_kept) {
@@ -768,6 +790,7 @@ int run_chunk(cyp_session *s, uint32_t round, int64_t sims_per_root, int64_t wb,
     unsigned long long counters[4] = {0, 0, 0, 0};
     S_CUDA(cudaMemcpyAsync(counters, d_counters, sizeof(counters), cudaMemcpyDeviceToHost, st));
     S_CUDA(cudaStreamSynchronize(st));
+    tr.mark("gather + sync");
     float ms_walk = 0.f, ms_filter = 0.f;
     S_CUDA(cudaEventElapsedTime(&ms_walk, ev[0], ev[1]));
     S_CUDA(cudaEventElapsedTime(&ms_filter, ev[1], ev[2]));
@@ -811,8 +834,10 @@ extern "C" int cyp_session_round(cyp_session *s, uint32_t round, int64_t sims_pe
     // take the chunk's survivors (grow_store copies, hence the factor).
     const double per_walker = 4.0 * ncol + 20.0 + (h_uniforms ? 8.0 * nt : 0.0) + 120.0 + 2.5 * 4.0 * ncol;
     int64_t chunk = s->chunk_walkers;
+    Tracer tr;
     if (chunk <= 0) {
         const double free_b = static_cast<double>(free_device_bytes(s->device));
+        tr.mark("free_device_bytes");
         chunk = static_cast<int64_t>(0.8 * free_b / per_walker);
         if (chunk < 1024)
             return fail(CYP_E_NOMEM, "cyp_session_round: " + std::to_string(static_cast<long long>(free_b / (1 << 20))) +

@@ -16,6 +16,7 @@
 // The uniform stream, the comparisons and therefore the trajectories are bit-identical to walk.cu /
 // walk_tma.cu / walk_pp.cu and to the oracle.
 #include <cstdio>
+#include <cstdlib>
 
 #include "walk.cuh"
 
@@ -234,6 +235,14 @@ static int launch_v2_one(const WalkParams &p, const V2Config &c, int sm_count, c
     const int64_t resident = static_cast<int64_t>(sm_count) * c.ctas_per_sm;
     const unsigned grid = static_cast<unsigned>(need < resident ? need : resident);       // persistent CTAs
     if (grid == 0) return CYP_OK;
+    static const bool trace = getenv("CYP_TRACE") != nullptr;
+    if (trace) {
+        int dev = -1;
+        cudaGetDevice(&dev);
+        fprintf(stderr, "[cyp trace] walk_v2: device %d grid %u threads %d smem %zu walkers %lld begin %lld sims/root %lld nt %d\n", dev, grid,
+                c.threads, c.smem, static_cast<long long>(p.n_walkers), static_cast<long long>(p.walker_begin),
+                static_cast<long long>(p.sims_per_root), p.nt);
+    }
     kernel<<<grid, c.threads, c.smem, stream>>>(p, c.log_n);
     CYP_CUDA(cudaGetLastError());
     return CYP_OK;

@@ -125,6 +125,9 @@ def _listify(x):
     return x
 
 
+_NCCL_CONNECTED = False
+
+
 class _World:
     """torch.distributed plumbing for walker sharding (one process per GPU).  World size 1
     when torch.distributed is not initialised."""
@@ -144,6 +147,14 @@ class _World:
             return
         if dist.is_available() and dist.is_initialized():
             self.rank, self.size, self.dist, self.torch = dist.get_rank(), dist.get_world_size(), dist, torch
+            global _NCCL_CONNECTED
+            if self.size > 1 and not _NCCL_CONNECTED and dist.get_backend() == "nccl":
+                # NCCL connects its peer-to-peer transports at the first collective; if that happens after the graph
+                # and the trajectory buffers are allocated, the step kernel runs ~25 % slower (measured on 2 x B200,
+                # profiles/r01_multi_gpu_probe.md).  So: one tiny collective before anything is allocated.
+                dist.all_reduce(torch.zeros(1, device=torch.device("cuda", torch.cuda.current_device())))
+                torch.cuda.synchronize()
+                _NCCL_CONNECTED = True
         elif use_dist is True:
             raise RuntimeError("dist=True but torch.distributed is not initialised")
 

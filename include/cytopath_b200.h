@@ -52,6 +52,9 @@ typedef struct cyp_session cyp_session;
 int cyp_version(void);
 const char *cyp_last_error(void);
 int cyp_device_count(int *n);
+/* Device memory is recycled across calls (CUDA stream-ordered pool + an exact-size cache of large blocks): this
+ * returns all of it that is not in use to the driver.  device < 0: every device. */
+int cyp_release_cached_memory(int device);
 
 /* ---- a1: matrix_prep (markov_chain_sampler.py:11-31) -------------------------------
  * Uploads a canonical CSR (columns ascending, no duplicates, no explicit zeros: what

@@ -13,14 +13,27 @@ ap.add_argument("--cdf-mode", default="exact")
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--variants", default="404,802,804,1602,1604,3202,3204")
 ap.add_argument("--walkers", type=int, default=0)
+ap.add_argument("--sims-per-root", type=int, default=0)
+ap.add_argument("--walker-begin", type=int, default=0)
+ap.add_argument("--barrier", action="store_true", help="dist.barrier() before every timed block (with --init-nccl)")
+ap.add_argument("--init-nccl", action="store_true", help="initialise a 1-rank NCCL group first (does the communicator change K2's speed?)")
 args = ap.parse_args()
+if args.init_nccl:
+    import torch.distributed as dist
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29577")
+    rk, lrk, ws = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    torch.cuda.set_device(lrk)
+    dist.init_process_group("nccl", rank=rk, world_size=ws, device_id=torch.device("cuda", lrk))
+    x = torch.ones(4, device="cuda"); dist.all_reduce(x); torch.cuda.synchronize()
 w = bench.WORKLOADS[args.workload]
 g, C, roots = bench.make_graph(w, 1)
 mode = _lib.CDF_EXACT if args.cdf_mode == "exact" else _lib.CDF_REFERENCE
-graph = _lib.Graph(C, mode, 0)
+dev_index = torch.cuda.current_device()
+graph = _lib.Graph(C, mode, dev_index)
 L = _lib.load()
 W = args.walkers or w["walkers"]; nt = w["max_steps"] - 1
-sims = -(-W // len(roots))
+sims = args.sims_per_root or -(-W // len(roots))
+w0 = args.walker_begin
 d_roots = torch.tensor(roots, dtype=torch.int32, device="cuda")
 d_seq = torch.empty((W, nt + 1), dtype=torch.int32, device="cuda")
 sptr = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -29,9 +42,14 @@ bps = elem * (C.nnz / C.shape[0]) + 16
 print("workload %s mode %s W=%d nt=%d build_ms=%.2f" % (args.workload, args.cdf_mode, W, nt, graph.build_ms()))
 for v in [int(x) for x in args.variants.split(",")]:
     def step(i):
-        _lib.check(L.cyp_walk_device(graph.handle, d_roots.data_ptr(), len(roots), sims, 0, W, nt, 1234, i, None,
+        _lib.check(L.cyp_walk_device(graph.handle, d_roots.data_ptr(), len(roots), sims, w0, W, nt, 1234, i, None,
                                      d_seq.data_ptr(), None, v, sptr))
     step(0); torch.cuda.synchronize()
+    if args.barrier and args.init_nccl:
+        dist.barrier(); torch.cuda.synchronize()
+        import ctypes as _c
+        rt = _c.CDLL("libcudart.so.12"); lim = _c.c_size_t(0)
+        rt.cudaDeviceGetLimit(_c.byref(lim), 0x06); print("persisting L2 limit", lim.value)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps): step(1 + i)
