@@ -22,7 +22,7 @@ E_NOCROSSING = -4
 
 EXPORTS = [
     "cyp_version", "cyp_last_error", "cyp_device_count", "cyp_release_cached_memory",
-    "cyp_graph_create", "cyp_graph_create_f32", "cyp_graph_row_sum_range", "cyp_graph_destroy", "cyp_graph_info", "cyp_graph_layout", "cyp_graph_fetch_cdf", "cyp_graph_build_ms",
+    "cyp_graph_create", "cyp_graph_create_f32", "cyp_graph_row_sum_range", "cyp_graph_destroy", "cyp_graph_info", "cyp_graph_layout", "cyp_graph_fetch_fused", "cyp_graph_fetch_cdf", "cyp_graph_build_ms",
     "cyp_power_iteration", "cyp_walk", "cyp_walk_device", "cyp_walk_variant_name", "cyp_transition_scores",
     "cyp_session_create", "cyp_session_destroy", "cyp_session_round", "cyp_session_rows",
     "cyp_session_fetch_index", "cyp_session_fetch_rows", "cyp_session_round_records",
@@ -82,6 +82,7 @@ def load():
     L.cyp_graph_destroy.argtypes = [vp]
     L.cyp_graph_info.argtypes = [vp, P(i64), P(i64), P(i32), P(ci), P(ci), P(i64)]
     L.cyp_graph_layout.argtypes = [vp, P(ci), P(i64), P(i64), P(i32)]
+    L.cyp_graph_fetch_fused.argtypes = [vp, vp, vp, vp]
     L.cyp_graph_fetch_cdf.argtypes = [vp, vp]
     L.cyp_graph_build_ms.argtypes = [vp, P(ctypes.c_float)]
     L.cyp_power_iteration.argtypes = [ci, i64, i64, vp, vp, vp, vp, vp, i32, vp, vp]
@@ -216,6 +217,15 @@ class Graph:
         f, rb, tb, mb = ctypes.c_int(), ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int32()
         check(load().cyp_graph_layout(self._h, ctypes.byref(f), ctypes.byref(rb), ctypes.byref(tb), ctypes.byref(mb)))
         return dict(fused=bool(f.value), row_block_bytes=rb.value, target_word_bytes=tb.value, max_block_bytes=mb.value)
+
+    def fused(self):
+        """(row blocks uint8, row words uint32 [n], target words uint32) of the fused-row layout (test hook)."""
+        lay = self.layout()
+        rows = np.empty(lay["row_block_bytes"], dtype=np.uint8)
+        words = np.empty(self.n, dtype=np.uint32)
+        targets = np.empty(lay["target_word_bytes"] // 4, dtype=np.uint32)
+        check(load().cyp_graph_fetch_fused(self._h, ptr(rows), ptr(words), ptr(targets)))
+        return rows, words, targets
 
     def row_sum_range(self):
         lo, hi = ctypes.c_double(), ctypes.c_double()

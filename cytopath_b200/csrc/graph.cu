@@ -641,6 +641,16 @@ extern "C" int cyp_graph_layout(const cyp_graph *g, int *fused, int64_t *row_blo
     return CYP_OK;
 }
 
+extern "C" int cyp_graph_fetch_fused(const cyp_graph *g, uint8_t *h_rows, uint32_t *h_words, uint32_t *h_targets) {
+    CYP_REQUIRE(g != nullptr && h_rows && h_words && h_targets, "cyp_graph_fetch_fused: NULL argument");
+    CYP_REQUIRE(g->v2_ok, "cyp_graph_fetch_fused: this graph has no fused rows");
+    DeviceGuard guard(g->device);
+    CYP_CUDA(cudaMemcpy(h_rows, g->d_rows2, static_cast<size_t>(g->v2_sectors) * 32, cudaMemcpyDeviceToHost));
+    CYP_CUDA(cudaMemcpy(h_words, g->d_word, sizeof(uint32_t) * g->n, cudaMemcpyDeviceToHost));
+    CYP_CUDA(cudaMemcpy(h_targets, g->d_edge4, sizeof(uint32_t) * 4 * static_cast<size_t>(g->v2_edge_units), cudaMemcpyDeviceToHost));
+    return CYP_OK;
+}
+
 extern "C" int cyp_graph_build_ms(const cyp_graph *g, float *ms) {
     CYP_REQUIRE(g != nullptr && ms != nullptr, "cyp_graph_build_ms: NULL argument");
     *ms = g->build_ms;

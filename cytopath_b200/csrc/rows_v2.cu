@@ -161,6 +161,7 @@ cudaError_t v2_alloc(cyp_graph *g, V2Build *b) {
     if (e == cudaSuccess) e = dev_alloc(&b->d_bad, sizeof(int));
     if (e == cudaSuccess) e = cudaMemsetAsync(b->d_bad, 0, sizeof(int), nullptr);
     if (e == cudaSuccess) e = cudaMemsetAsync(g->d_rows2, 0, b->rows_bytes, nullptr);
+    if (e == cudaSuccess) e = cudaMemsetAsync(g->d_edge4, 0, sizeof(uint32_t) * 4 * static_cast<size_t>(b->units + 1), nullptr);   // row padding
     return e;
 }
 

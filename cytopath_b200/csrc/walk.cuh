@@ -31,6 +31,7 @@ struct WalkParams {
     const unsigned char *rows2 = nullptr;
     const uint32_t *edge4 = nullptr;
     const uint32_t *word = nullptr;
+    int l1_rows = 0;                // row copies allocate in L1 (small graphs: many walkers per cell)
 };
 
 // Kernel modes: what is fused into the step loop besides the walk itself.

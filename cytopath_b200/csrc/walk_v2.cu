@@ -30,6 +30,10 @@ __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void *gmem_s
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
 }
 
+__device__ __forceinline__ void cp_async16_l1(uint32_t smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+}
+
 __device__ __forceinline__ uint32_t ldg_word(const uint32_t *p) {
     uint32_t v;
     asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
@@ -40,8 +44,12 @@ constexpr int kModeExact = 0, kModeRef = 1;
 
 }  // namespace
 
-// CPR = 16-byte chunks per slot; CDFM = kModeExact / kModeRef.
-template <int CPR, int CDFM, int MODE>
+// CPR = 16-byte chunks per slot; CDFM = kModeExact / kModeRef; L1ROWS: the row copies allocate in L1 (cp.async.ca
+// instead of .cg).  On small graphs many walkers sit on the same few cells, every SM asks the same L2 lines at once
+// and the L2 slices serialise them: 13.7 G walker-steps/s at 3,696 cells against 85 G at 20k+ cells.  With L1
+// allocation the hot rows are served by the SM's own L1: 63 G at any size -- better below ~16k cells, worse above
+// (profiles/r01_small_graphs.log).
+template <int CPR, int CDFM, int MODE, bool L1ROWS>
 __global__ void __launch_bounds__(1024, 1) walk_v2_kernel(const WalkParams p, const int log_n /* search depth: 2^log_n >= longest row */) {
     constexpr int SLOT_STRIDE = 16 * CPR + 32;           // +32 spreads same-position probes over 4 bank groups and keeps slots sector aligned
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -57,13 +65,15 @@ __global__ void __launch_bounds__(1024, 1) walk_v2_kernel(const WalkParams p, co
     const int nt = p.nt;
     const bool vec_store = (p.ld & 3) == 0;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * nthreads;
-
     auto issue_copy = [&](uint32_t word) {
 #pragma unroll
         for (int i = 0; i < CPR; ++i) {
             const uint32_t wd = __shfl_sync(0xffffffffu, word, i, CPR);
             const uint32_t off = (wd << 5) + src_c;                  // the shift drops the sector count
-            if (wd >= need_thr) cp_async16(dst0 + static_cast<uint32_t>(i) * SLOT_STRIDE, p.rows2 + off);
+            if (wd >= need_thr) {
+                if constexpr (L1ROWS) cp_async16_l1(dst0 + static_cast<uint32_t>(i) * SLOT_STRIDE, p.rows2 + off);
+                else cp_async16(dst0 + static_cast<uint32_t>(i) * SLOT_STRIDE, p.rows2 + off);
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -176,6 +186,8 @@ __global__ void __launch_bounds__(1024, 1) walk_v2_kernel(const WalkParams p, co
 // is now the default).  ncu (profiles/r01_ncu_walk_v2_fused_c4_exact.csv): L2 hit rate 73 %, the misses are ~20 G
 // random 32..128-byte DRAM gathers per second against a measured ceiling of 22-29 G/s for 128-byte gathers
 // (profiles/r01_gather_ceilings.log): the kernel is at the DRAM random-access rate of this graph.
+constexpr int64_t kV2L1Cells = 16384;      // below: L1-allocating row copies (see walk_v2_kernel)
+
 struct V2Config {
     int cpr;
     int ctas_per_sm;
@@ -223,9 +235,9 @@ static int v2_sm_count() {
     return cached;
 }
 
-template <int CPR, int CDFM, int MODE>
-static int launch_v2_one(const WalkParams &p, const V2Config &c, int sm_count, cudaStream_t stream) {
-    auto kernel = walk_v2_kernel<CPR, CDFM, MODE>;
+template <int CPR, int CDFM, int MODE, bool L1ROWS>
+static int launch_v2_l1(const WalkParams &p, const V2Config &c, int sm_count, cudaStream_t stream) {
+    auto kernel = walk_v2_kernel<CPR, CDFM, MODE, L1ROWS>;
     static size_t smem_set = 0;
     if (c.smem > smem_set) {
         CYP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c.smem)));
@@ -246,6 +258,11 @@ static int launch_v2_one(const WalkParams &p, const V2Config &c, int sm_count, c
     kernel<<<grid, c.threads, c.smem, stream>>>(p, c.log_n);
     CYP_CUDA(cudaGetLastError());
     return CYP_OK;
+}
+
+template <int CPR, int CDFM, int MODE>
+static int launch_v2_one(const WalkParams &p, const V2Config &c, int sm_count, cudaStream_t stream) {
+    return p.l1_rows ? launch_v2_l1<CPR, CDFM, MODE, true>(p, c, sm_count, stream) : launch_v2_l1<CPR, CDFM, MODE, false>(p, c, sm_count, stream);
 }
 
 template <int CPR, int CDFM>
@@ -273,6 +290,8 @@ int launch_walk_v2(const cyp_graph *g, const WalkParams &p_in, WalkMode mode, in
     p.rows2 = g->d_rows2;
     p.edge4 = g->d_edge4;
     p.word = g->d_word;
+    p.l1_rows = g->n < kV2L1Cells ? 1 : 0;
+    if (const char *e = getenv("CYP_V2_L1")) p.l1_rows = atoi(e);
     switch (c.cpr) {
         case 2: return launch_v2_cdf<2>(g, p, mode, c, sm_count, stream);
         case 4: return launch_v2_cdf<4>(g, p, mode, c, sm_count, stream);
@@ -287,8 +306,8 @@ const char *walk_v2_name(const cyp_graph *g, int variant) {
     static thread_local char buf[128];
     V2Config c;
     if (!v2_config(g, variant, 0, 0, &c)) return nullptr;
-    snprintf(buf, sizeof(buf), "walk_v2_kernel<%s,fused rows,threads<=%d,slot=%dB>", g->cdf_mode == CYP_CDF_EXACT ? "q12/f64" : "q12/f32",
-             c.threads, 16 * c.cpr);
+    snprintf(buf, sizeof(buf), "walk_v2_kernel<%s,fused rows,threads<=%d,slot=%dB%s>", g->cdf_mode == CYP_CDF_EXACT ? "q12/f64" : "q12/f32",
+             c.threads, 16 * c.cpr, g->n < kV2L1Cells ? ",L1 rows" : "");
     return buf;
 }
 

@@ -80,6 +80,10 @@ int cyp_graph_fetch_cdf(const cyp_graph *g, void *h_cdf);
  * other outputs are 0), bytes of the row blocks, bytes of the 4-byte target words, largest block in bytes. */
 int cyp_graph_layout(const cyp_graph *g, int *fused, int64_t *row_block_bytes, int64_t *target_word_bytes,
                      int32_t *max_block_bytes);
+/* Test / inspection hook: copies the fused rows to the host.  h_rows [row_block_bytes], h_words [n_cells] (row word
+ * of every cell: sectors << 27 | first sector), h_targets [target_word_bytes / 4] (row words of all targets, rows
+ * padded to 4 words).  Fails with CYP_E_INVALID when the graph has no fused rows. */
+int cyp_graph_fetch_fused(const cyp_graph *g, uint8_t *h_rows, uint32_t *h_words, uint32_t *h_targets);
 /* Milliseconds the K1 prefix-sum kernel took when the graph was created (CUDA events). */
 int cyp_graph_build_ms(const cyp_graph *g, float *ms);
 

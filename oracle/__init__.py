@@ -14,6 +14,10 @@ What it restates (reference = /root/reference/cytopath/markov_chain_sampler.py):
   walk.c           the same CDF recipe + first-crossing step loop + Philox in plain C
                    (gcc), used to check large cases in seconds and as a compiled CPU
                    baseline next to the faithful Python/joblib port
+  fused_rows_port.py  the device layout K1b derives from that CDF (12-bit codes, inlined
+                   targets, row words; cytopath_b200/csrc/rows_v2.cu) rebuilt in numpy, so that the
+                   layout is checked byte for byte and not only through the walks it produces
+  hausdorff_port.py  the directed-Hausdorff distance matrix of sample_clustering.py:57-71
 
 Parity pinning: the reference ships no tests or golden vectors,
 so the oracle is pinned against the reference ITSELF: `oracle/make_golden.py` imports

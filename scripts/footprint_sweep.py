@@ -12,11 +12,14 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--cells", default="125000,250000,500000,1000000")
 ap.add_argument("--variants", default="0,9332")
 ap.add_argument("--k", type=int, default=50)
+ap.add_argument("--base", default="c4")
+ap.add_argument("--walkers", type=int, default=0)
 ap.add_argument("--steps", type=int, default=3)
 args = ap.parse_args()
 L = _lib.load()
 for n in [int(x) for x in args.cells.split(",")]:
-    w = dict(bench.WORKLOADS["c4"], n=n, k=args.k)
+    w = dict(bench.WORKLOADS[args.base], n=n, k=args.k)
+    if args.walkers: w["walkers"] = args.walkers
     g, C, roots = bench.make_graph(w, 1)
     graph = _lib.Graph(C, _lib.CDF_EXACT, 0)
     W, nt = w["walkers"], w["max_steps"] - 1

@@ -113,6 +113,53 @@ def test_sampling_accepts_float32_matrix_in_place_and_checks_normalisation_on_de
     run_quiet(cytopath_b200.sampling, ad, **kw2, seed=5)
 
 
+@pytest.mark.parametrize("gname", ["k4", "k12", "k30", "k50", "k200", "ragged"])
+@pytest.mark.parametrize("mode,omode", MODES)
+def test_k1b_fused_rows_byte_exact_vs_oracle(gname, mode, omode, monkeypatch):
+    """K1b (csrc/rows_v2.cu): header, 12-bit code planes, inlined targets of the most probable entries, row words
+    and target words, byte for byte against the numpy restatement built from the oracle's CDF -- with the automatic
+    choice of extra inline sectors and with 0 / 2 forced."""
+    from oracle import fused_rows_port as frp
+    C = sp.canonical_csr(GRAPHS[gname]())
+    cdf = cwalk.build_cdf(C, omode)
+    for extra in (None, 0, 2):
+        if extra is None:
+            monkeypatch.delenv("CYP_V2_EXTRA", raising=False)
+        else:
+            monkeypatch.setenv("CYP_V2_EXTRA", str(extra))
+        g = _lib.Graph(C, mode)
+        lay = g.layout()
+        assert lay["fused"]
+        rows, words, targets = g.fused()
+        want_rows, want_words, want_targets = frp.build(C, cdf, exact=(mode == _lib.CDF_EXACT), extra=extra)
+        np.testing.assert_array_equal(words, want_words)
+        np.testing.assert_array_equal(targets, want_targets)
+        assert rows.shape == want_rows.shape and lay["max_block_bytes"] == int((want_words >> 27).max()) * 32
+        np.testing.assert_array_equal(rows, want_rows)
+        g.close()
+
+
+def test_k1b_not_applicable_falls_back_to_edge_records():
+    """Negative probabilities (CDF not monotone) and rows too long for a block: no fused rows, the 16-bit / plain
+    kernels take over and still match the oracle."""
+    from scipy import sparse
+    rng = np.random.default_rng(11)
+    n = 900
+    dense_row = np.full(n, 1.0 / n)                                   # 900 entries: block would need 43 sectors
+    M = sparse.lil_matrix((n, n))
+    M[0, :] = dense_row
+    for i in range(1, n):
+        c = rng.choice(n, size=5, replace=False)
+        M[i, c] = 0.2
+    C = sp.canonical_csr(M.tocsr())
+    g = _lib.Graph(C, _lib.CDF_EXACT)
+    assert not g.layout()["fused"] and "walk_v2" not in g.variant_name(0)
+    roots = np.array([0, 1, 2, 3])
+    want = cwalk.walk(C, cwalk.build_cdf(C, 1), np.repeat(roots, 30), 40, seed=2)
+    np.testing.assert_array_equal(g.walk(roots, 30, 40, seed=2), want)
+    g.close()
+
+
 # ---- K4 ---------------------------------------------------------------------------------
 def test_k4_power_iteration_matches_scipy():
     """eps history of iterate_state_probability (:62-87): the state vector is bit-equal to scipy's
@@ -162,7 +209,7 @@ GRAPHS = {
 
 @pytest.mark.parametrize("gname", list(GRAPHS))
 @pytest.mark.parametrize("mode,omode", MODES)
-def test_k2_bit_exact_vs_oracle_all_variants(gname, mode, omode):
+def test_k2_bit_exact_vs_oracle_all_variants(gname, mode, omode, monkeypatch):
     C = sp.canonical_csr(GRAPHS[gname]())
     g = _lib.Graph(C, mode)
     cdf = cwalk.build_cdf(C, omode)
@@ -210,7 +257,8 @@ def test_k2_bit_exact_vs_oracle_all_variants(gname, mode, omode):
             torch.cuda.synchronize()
             np.testing.assert_array_equal(out.cpu().numpy(), wnt, err_msg="%s nt=%d" % (g.variant_name(variant), n_t))
     # fused-row flavour (12-bit codes, inlined targets): 32 / 128 / 512 / 1024 threads per CTA; 62, 63 and 64 columns
-    for variant in (9501, 9504, 9516, 9532):
+    for variant, l1 in ((9501, "1"), (9504, "0"), (9516, "1"), (9532, "0")):        # L1-allocating and L1-bypassing row copies
+        monkeypatch.setenv("CYP_V2_L1", l1)
         assert "walk_v2_kernel" in g.variant_name(variant), g.variant_name(variant)
         for n_t in (nt, 62, 63):
             wnt = want if n_t == nt else cwalk.walk(C, cdf, np.repeat(roots, sims), n_t, seed=seed, round_idx=rnd, strict=False)
@@ -221,6 +269,7 @@ def test_k2_bit_exact_vs_oracle_all_variants(gname, mode, omode):
                                          ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
             torch.cuda.synchronize()
             np.testing.assert_array_equal(out.cpu().numpy(), wnt, err_msg="%s nt=%d" % (g.variant_name(variant), n_t))
+    monkeypatch.delenv("CYP_V2_L1")
     assert ("walk_v2_kernel" in g.variant_name(0)) == (gname != "k200")     # the auto variant picks it, except for long rows
     # auto variant through the host entry point, a shard in the middle of the round
     got = g.walk(roots, sims, nt, seed=seed, round_idx=rnd, walker_begin=100, n_walkers=211, strict=False)
