@@ -40,6 +40,33 @@ __device__ __forceinline__ uint32_t ldg_word(const uint32_t *p) {
     return v;
 }
 
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "V2_WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra V2_WAIT_DONE;\n"
+        "bra V2_WAIT_LOOP;\n"
+        "V2_WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (TMA, no tensor map); completion is reported to `bar` in bytes
+__device__ __forceinline__ void bulk_copy_g2s(const void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 constexpr int kModeExact = 0, kModeRef = 1;
 
 }  // namespace
@@ -49,15 +76,28 @@ constexpr int kModeExact = 0, kModeRef = 1;
 // and the L2 slices serialise them: 13.7 G walker-steps/s at 3,696 cells against 85 G at 20k+ cells.  With L1
 // allocation the hot rows are served by the SM's own L1: 63 G at any size -- better below ~16k cells, worse above
 // (profiles/r01_small_graphs.log).
+// CPR = 0: long rows.  Every thread issues ONE cp.async.bulk (UBLKCP) for its whole block and the warp's 32 copies
+// complete on one mbarrier; the slot is exactly the largest block (`bulk_stride` bytes, any multiple of 32).
 template <int CPR, int CDFM, int MODE, bool L1ROWS>
-__global__ void __launch_bounds__(1024, 1) walk_v2_kernel(const WalkParams p, const int log_n /* search depth: 2^log_n >= longest row */) {
-    constexpr int SLOT_STRIDE = 16 * CPR + 32;           // +32 spreads same-position probes over 4 bank groups and keeps slots sector aligned
+__global__ void __launch_bounds__(1024, 1) walk_v2_kernel(const WalkParams p, const int log_n /* search depth: 2^log_n >= longest row */,
+                                                          const int bulk_stride) {
+    constexpr bool BULK = CPR == 0;
+    const int SLOT_STRIDE = BULK ? bulk_stride : 16 * CPR + 32;   // +32 spreads same-position probes over 4 bank groups and keeps slots sector aligned
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int nthreads = blockDim.x;
-    const unsigned char *const slot = smem_raw + static_cast<size_t>(threadIdx.x) * SLOT_STRIDE;
+    const int bar_bytes = BULK ? (((nthreads >> 5) * 8 + 127) & ~127) : 0;
+    const unsigned char *const slot = smem_raw + bar_bytes + static_cast<size_t>(threadIdx.x) * SLOT_STRIDE;
+    uint64_t *const bar = reinterpret_cast<uint64_t *>(smem_raw) + (threadIdx.x >> 5);
+    uint32_t parity = 0;
+    if constexpr (BULK) {
+        if (lane == 0) mbar_init(bar, 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+    }
     // cooperative copy geometry: lane = (group, chunk); instruction i moves chunk `chunk` of the block of lane (lane & ~(CPR-1)) + i
-    const int chunk = lane & (CPR - 1);
+    const int chunk = BULK ? 0 : lane & ((BULK ? 1 : CPR) - 1);
     const uint32_t dst0 = smem_u32(slot) - static_cast<uint32_t>(chunk) * SLOT_STRIDE + static_cast<uint32_t>(chunk) * 16u;
     const uint32_t src_c = static_cast<uint32_t>(chunk) * 16u;     // byte offsets into rows2 fit 32 bits (< 2^27 sectors)
     const uint32_t need_thr = (static_cast<uint32_t>(chunk >> 1) + 1u) << kWordOffBits;     // word >= need_thr <=> sectors > chunk / 2
@@ -66,9 +106,19 @@ __global__ void __launch_bounds__(1024, 1) walk_v2_kernel(const WalkParams p, co
     const bool vec_store = (p.ld & 3) == 0;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * nthreads;
     auto issue_copy = [&](uint32_t word) {
+        if constexpr (BULK) {
+            const uint32_t bytes = (word >> kWordOffBits) * 32u;
+            if (bytes) {
+                mbar_arrive_expect_tx(bar, bytes);
+                bulk_copy_g2s(slot, p.rows2 + (static_cast<size_t>(word & kWordOffMask) << 5), bytes, bar);
+            } else {
+                mbar_arrive(bar);
+            }
+            return;
+        }
 #pragma unroll
-        for (int i = 0; i < CPR; ++i) {
-            const uint32_t wd = __shfl_sync(0xffffffffu, word, i, CPR);
+        for (int i = 0; i < (BULK ? 1 : CPR); ++i) {
+            const uint32_t wd = __shfl_sync(0xffffffffu, word, i, BULK ? 32 : CPR);
             const uint32_t off = (wd << 5) + src_c;                  // the shift drops the sector count
             if (wd >= need_thr) {
                 if constexpr (L1ROWS) cp_async16_l1(dst0 + static_cast<uint32_t>(i) * SLOT_STRIDE, p.rows2 + off);
@@ -94,8 +144,13 @@ __global__ void __launch_bounds__(1024, 1) walk_v2_kernel(const WalkParams p, co
         if (!p.uniforms && nt > 0) walker_uniform_pair(p.seed, p.round, gw, 0u, u_even, u_odd);
 
         for (int t = 0; t <= nt; ++t) {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            __syncwarp();
+            if constexpr (BULK) {
+                mbar_wait(bar, parity);
+                parity ^= 1u;
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncwarp();
+            }
             uint32_t next = word;
             if (active) {
                 const uint4 h = *reinterpret_cast<const uint4 *>(slot);          // cell | len, label, m | inline mask
@@ -189,23 +244,31 @@ __global__ void __launch_bounds__(1024, 1) walk_v2_kernel(const WalkParams p, co
 constexpr int64_t kV2L1Cells = 16384;      // below: L1-allocating row copies (see walk_v2_kernel)
 
 struct V2Config {
-    int cpr;
+    int cpr;            // 16-byte chunks per slot (cooperative cp.async copies); 0 = one bulk copy per row
     int ctas_per_sm;
     int threads;
     int log_n;
+    int stride;         // bytes between slots
     size_t smem;
 };
 
-// variant: 0 = auto; 9500 + T/32 = T threads per CTA.
+// variant: 0 = auto; 9500 + T/32 = T threads per CTA; 9600 + T/32 = two CTAs of T threads per SM (experiment).
 static bool v2_config(const cyp_graph *g, int variant, int64_t n_walkers, int sm_count, V2Config *out) {
     if (!g->v2_ok) return false;
-    int cpr = 2;
-    while (cpr * 16 < g->v2_max_sectors * 32) cpr <<= 1;
-    if (cpr > 32) return false;
-    const size_t stride = 16 * cpr + 32;
+    const int block = g->v2_max_sectors * 32;
+    int cpr = 0, stride = 0;
+    if (block <= 256) {                                  // small rows: cooperative 16-byte copies, power-of-two slots
+        cpr = 2;
+        while (cpr * 16 < block) cpr <<= 1;
+        stride = 16 * cpr + 32;
+    } else {                                             // long rows: one bulk copy per row, slot = the largest block
+        stride = block + ((block % 128 == 0) ? 32 : 0);  // never a multiple of 128: same-position probes spread over the banks
+    }
     int ctas = 1;
-    if (variant > 9600) { ctas = 2; variant -= 100; }     // 96xx: two CTAs per SM (experiment)
-    int threads = static_cast<int>((226 * 1024 / ctas - 1024) / stride) / 32 * 32;
+    if (variant > 9600) { ctas = 2; variant -= 100; }
+    const size_t budget = 226 * 1024 / ctas - 1024;
+    int threads = static_cast<int>(budget / stride) / 32 * 32;
+    if (cpr == 0) threads = static_cast<int>((budget - (((threads >> 5) * 8 + 127) & ~127)) / stride) / 32 * 32;
     if (threads > 1024) threads = 1024;
     if (variant > 9500) {
         threads = (variant - 9500) * 32 < threads ? (variant - 9500) * 32 : threads;
@@ -220,7 +283,8 @@ static bool v2_config(const cyp_graph *g, int variant, int64_t n_walkers, int sm
     if (threads < 32) threads = 32;
     int log_n = 1;
     while ((1 << log_n) < g->max_len) ++log_n;
-    *out = V2Config{cpr, ctas, threads, log_n, static_cast<size_t>(threads) * stride};
+    const size_t bars = cpr == 0 ? static_cast<size_t>(((threads >> 5) * 8 + 127) & ~127) : 0;
+    *out = V2Config{cpr, ctas, threads, log_n, stride, bars + static_cast<size_t>(threads) * stride};
     return true;
 }
 
@@ -255,7 +319,7 @@ static int launch_v2_l1(const WalkParams &p, const V2Config &c, int sm_count, cu
                 c.threads, c.smem, static_cast<long long>(p.n_walkers), static_cast<long long>(p.walker_begin),
                 static_cast<long long>(p.sims_per_root), p.nt);
     }
-    kernel<<<grid, c.threads, c.smem, stream>>>(p, c.log_n);
+    kernel<<<grid, c.threads, c.smem, stream>>>(p, c.log_n, c.stride);
     CYP_CUDA(cudaGetLastError());
     return CYP_OK;
 }
@@ -293,11 +357,11 @@ int launch_walk_v2(const cyp_graph *g, const WalkParams &p_in, WalkMode mode, in
     p.l1_rows = g->n < kV2L1Cells ? 1 : 0;
     if (const char *e = getenv("CYP_V2_L1")) p.l1_rows = atoi(e);
     switch (c.cpr) {
+        case 0: return launch_v2_cdf<0>(g, p, mode, c, sm_count, stream);
         case 2: return launch_v2_cdf<2>(g, p, mode, c, sm_count, stream);
         case 4: return launch_v2_cdf<4>(g, p, mode, c, sm_count, stream);
         case 8: return launch_v2_cdf<8>(g, p, mode, c, sm_count, stream);
         case 16: return launch_v2_cdf<16>(g, p, mode, c, sm_count, stream);
-        case 32: return launch_v2_cdf<32>(g, p, mode, c, sm_count, stream);
     }
     return kNotApplicable;
 }
@@ -307,7 +371,7 @@ const char *walk_v2_name(const cyp_graph *g, int variant) {
     V2Config c;
     if (!v2_config(g, variant, 0, 0, &c)) return nullptr;
     snprintf(buf, sizeof(buf), "walk_v2_kernel<%s,fused rows,threads<=%d,slot=%dB%s>", g->cdf_mode == CYP_CDF_EXACT ? "q12/f64" : "q12/f32",
-             c.threads, 16 * c.cpr, g->n < kV2L1Cells ? ",L1 rows" : "");
+             c.threads, c.cpr ? 16 * c.cpr : c.stride, c.cpr == 0 ? ",bulk" : (g->n < kV2L1Cells ? ",L1 rows" : ""));
     return buf;
 }
 
