@@ -27,7 +27,7 @@ EXPORTS = [
     "cyp_session_create", "cyp_session_destroy", "cyp_session_round", "cyp_session_rows",
     "cyp_session_fetch_index", "cyp_session_fetch_rows", "cyp_session_round_records",
     "cyp_session_round_prune", "cyp_session_set_hash_bits", "cyp_session_set_chunk_walkers",
-    "cyp_hausdorff_matrix",
+    "cyp_hausdorff_matrix", "cyp_directionality_scores",
 ]
 
 
@@ -101,6 +101,7 @@ def load():
     L.cyp_session_round_prune.argtypes = [vp, vp, i64, P(i64)]
     L.cyp_session_set_hash_bits.argtypes = [vp, ci]
     L.cyp_session_set_chunk_walkers.argtypes = [vp, i64]
+    L.cyp_directionality_scores.argtypes = [ci, i64, i32, vp, vp, vp, vp, i64, vp, i64, vp, vp, vp, vp, P(ctypes.c_float)]
     L.cyp_hausdorff_matrix.argtypes = [ci, vp, i64, i32, i32, ci, vp, P(ctypes.c_float)]
     for name in EXPORTS:
         fn = getattr(L, name)
@@ -166,6 +167,23 @@ def power_iteration(T, init, stationary, max_iter: int, device: int = 0, return_
 
 
 HAUSDORFF_METRICS = {"euclidean": 0, "manhattan": 1, "chebyshev": 2, "cosine": 3}
+
+
+def directionality_scores(pos, indptr, indices, w, dirs, cell, fwd, bwd, device: int = 0, return_ms: bool = False):
+    """f4 kernel (cyp_directionality_scores): one score per (cell, forward direction, backward direction) instance."""
+    require_device(device)
+    pos = np.ascontiguousarray(pos, dtype=np.float64)
+    indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+    indices = np.ascontiguousarray(indices, dtype=np.int32)
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    dirs = np.ascontiguousarray(dirs, dtype=np.float64).reshape(-1, pos.shape[1])
+    cell, fwd, bwd = (np.ascontiguousarray(a, dtype=np.int32) for a in (cell, fwd, bwd))
+    out = np.empty(cell.shape[0], dtype=np.float64)
+    ms = ctypes.c_float(0.0)
+    check(load().cyp_directionality_scores(device, pos.shape[0], pos.shape[1], ptr(pos), ptr(indptr), ptr(indices), ptr(w),
+                                           dirs.shape[0], ptr(dirs), cell.shape[0], ptr(cell), ptr(fwd), ptr(bwd), ptr(out),
+                                           ctypes.byref(ms)))
+    return (out, ms.value) if return_ms else out
 
 
 def hausdorff_matrix(coords, metric: str = "euclidean", device: int = 0, return_ms: bool = False):

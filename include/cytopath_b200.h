@@ -192,6 +192,17 @@ int cyp_hausdorff_matrix(int device, const double *h_coords, int64_t n_chains, i
 /* test hook: keep only the low `bits` bits of the 128-bit sequence hash (forces collisions) */
 int cyp_session_set_hash_bits(cyp_session *s, int bits);
 
+/* f4 -- directionality_score (reference cytopath/trajectory_estimation/cyto_path.py:155-243).
+ * Masked velocity graph as CSR over n_cells (h_row_ptr int64 [n_cells+1], h_col, h_w = expm1(weight) as float64);
+ * h_pos [n_cells, dims] cell coordinates; h_dirs [n_dirs, dims] trajectory directions; one instance per (trajectory,
+ * step, cell): h_cell, h_fwd / h_bwd = index of the forward / backward direction or -1 (first step: forward only,
+ * last step: backward only, else max of both).  h_score [n_inst]: mean over the cell's entries of
+ * cos(direction, x_target - x_cell) * w; nan for a cell without entries.  kernel_ms may be NULL. */
+int cyp_directionality_scores(int device, int64_t n_cells, int32_t dims, const double *h_pos, const int64_t *h_row_ptr,
+                              const int32_t *h_col, const double *h_w, int64_t n_dirs, const double *h_dirs,
+                              int64_t n_inst, const int32_t *h_cell, const int32_t *h_fwd, const int32_t *h_bwd,
+                              double *h_score, float *kernel_ms);
+
 #ifdef __cplusplus
 }
 #endif

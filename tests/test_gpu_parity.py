@@ -660,3 +660,43 @@ def test_f2_runs_on_sampler_output():
     np.testing.assert_array_equal(coords, hp.coordinate_assigner(ad.obsm["X_pca"], seqs))
     D = run_quiet(cytopath_b200.distance_matrix, coords)
     np.testing.assert_allclose(D, hp.distance_matrix(coords), rtol=1e-12, atol=1e-14)
+
+
+# ---- f4: directionality score ------------------------------------------------------------
+@pytest.mark.parametrize("name", ["directionality_d2_f32", "directionality_d10_f64"])
+def test_f4_directionality_score_matches_reference_golden(name):
+    """cytopath_b200.directionality_score (csrc/directionality.cu) against outputs of the reference's own
+    directionality_score (cyto_path.py:155-243): same nested list shape, nan in the same places, values to 1e-12
+    (float64 sums in a different order; the reference's numba cosine is fastmath)."""
+    from tests.test_oracle_golden import _directionality_case
+    ad, nbhd, pos, want = _directionality_case(name)
+    got = cytopath_b200.directionality_score(ad, nbhd, "end", pos, num_cores=1)
+    assert [len(t) for t in got] == [len(t) for t in nbhd]
+    assert all(len(a) == len(b) for t, u in zip(got, nbhd) for a, b in zip(t, u))
+    flat = np.concatenate([np.concatenate(t) for t in got])
+    assert np.array_equal(np.isnan(flat), np.isnan(want))
+    np.testing.assert_allclose(flat, want, rtol=1e-12, atol=1e-15, equal_nan=True)
+
+
+def test_f4_directionality_score_vs_oracle_large():
+    from scipy import sparse
+    from oracle import directionality_port as dp
+    g = synth.branching_graph(n=6000, k=30, n_branches=3, seed=5, workers=1)
+    rng = np.random.default_rng(0)
+    T = g.T.tocsr()
+    vg = sparse.csr_matrix((rng.random(T.nnz).astype(np.float32), T.indices, T.indptr), shape=T.shape)
+    vgn = sparse.csr_matrix((-(rng.random(T.nnz) * (rng.random(T.nnz) < 0.3)).astype(np.float32), T.indices, T.indptr), shape=T.shape)
+    vgn.eliminate_zeros()
+    pos = rng.normal(size=(6000, 30))
+    coords = {"trajectory_%d_coordinates" % i: np.cumsum(rng.normal(size=(40, 30)), axis=0) for i in range(4)}
+    nbhd = [[rng.choice(6000, size=int(rng.integers(50, 400)), replace=False) for _ in range(40)] for _ in range(4)]
+
+    class Shim:
+        pass
+    ad = Shim()
+    ad.uns = {"T_forward": T, "velocity_graph": vg, "velocity_graph_neg": vgn, "trajectories": {"trajectories_coordinates": {"end": coords}}}
+    got = cytopath_b200.directionality_score(ad, nbhd, "end", pos)
+    want = dp.directionality_score(ad, nbhd, "end", pos)
+    for t, u in zip(got, want):
+        for a, b in zip(t, u):
+            np.testing.assert_allclose(a, b, rtol=1e-11, atol=1e-14, equal_nan=True)

@@ -102,3 +102,36 @@ def test_sampling_port_matches_reference(name, stepper):
     assert s["cluster_sequences"].dtype == z["cluster_sequences"].dtype
     assert s["transition_score"].dtype == np.float32
     np.testing.assert_allclose(s["transition_score"], z["transition_score"], rtol=2e-6)
+
+
+def _directionality_case(name):
+    from scipy import sparse
+    z = load(name)
+    n = int(z["T_shape"][0])
+    mk = lambda p: sparse.csr_matrix((z[p + "_data"], z[p + "_indices"], z[p + "_indptr"]), shape=(n, n))
+    coords, sizes, cells = z["coords"], z["sizes"], z["cells"]
+
+    class Shim:
+        pass
+    ad = Shim()
+    ad.uns = {"T_forward": mk("T"), "velocity_graph": mk("vg"), "velocity_graph_neg": mk("vgn"),
+              "trajectories": {"trajectories_coordinates": {"end": {"trajectory_%d_coordinates" % i: coords[i] for i in range(len(coords))}}}}
+    nbhd, o = [], 0
+    for i in range(sizes.shape[0]):
+        t = []
+        for j in range(sizes.shape[1]):
+            t.append(cells[o:o + sizes[i, j]])
+            o += sizes[i, j]
+        nbhd.append(t)
+    return ad, nbhd, z["pos"], z["scores"]
+
+
+@pytest.mark.parametrize("name", ["directionality_d2_f32", "directionality_d10_f64"])
+def test_directionality_port_matches_reference_golden(name):
+    """f4: the numpy restatement of cyto_path.py:155-243 against outputs of the reference's own function (numba
+    fastmath cosine: agreement to 1e-12, nan for cells without graph entries in the same places)."""
+    from oracle import directionality_port as dp
+    ad, nbhd, pos, want = _directionality_case(name)
+    got = np.concatenate([np.concatenate(t) for t in dp.directionality_score(ad, nbhd, "end", pos)])
+    assert np.array_equal(np.isnan(got), np.isnan(want)) and np.isnan(want).any() and (~np.isnan(want)).sum() > 100
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-15, equal_nan=True)
