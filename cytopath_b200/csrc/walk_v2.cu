@@ -74,8 +74,8 @@ constexpr int kModeExact = 0, kModeRef = 1;
 // CPR = 16-byte chunks per slot; CDFM = kModeExact / kModeRef; L1ROWS: the row copies allocate in L1 (cp.async.ca
 // instead of .cg).  On small graphs many walkers sit on the same few cells, every SM asks the same L2 lines at once
 // and the L2 slices serialise them: 13.7 G walker-steps/s at 3,696 cells against 85 G at 20k+ cells.  With L1
-// allocation the hot rows are served by the SM's own L1: 63 G at any size -- better below ~16k cells, worse above
-// (profiles/r01_small_graphs.log).
+// allocation the hot rows are served by the SM's own L1: 80 G at 3,696 .. 10,000 cells (profiles/r01_small_graphs.log);
+// above ~16k cells the L1-bypassing copies are the faster ones.
 // CPR = 0: long rows.  Every thread issues ONE cp.async.bulk (UBLKCP) for its whole block and the warp's 32 copies
 // complete on one mbarrier; the slot is exactly the largest block (`bulk_stride` bytes, any multiple of 32).
 template <int CPR, int CDFM, int MODE, bool L1ROWS>
