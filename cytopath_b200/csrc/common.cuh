@@ -150,7 +150,9 @@ struct cyp_graph {
     // fused rows (see above); v2_ok = 0 when a row needs more than kV2MaxSectors sectors, the codes are unusable
     // (q16_ok / monotone) or the blocks exceed 2^27 sectors
     int v2_ok = 0;
-    int v2_max_sectors = 0;              // largest block, in sectors (shared-memory slot size of the step kernel)
+    int v2_max_sectors = 0;              // largest block, in sectors
+    int v2_slot_sectors = 0;             // shared-memory slot of the step kernel: covers >= 97 % of the rows (power of two, <= 8
+                                         // sectors) or, if no such size does, the largest block; longer rows are searched in HBM
     int64_t v2_sectors = 0;              // total sectors of d_rows2
     unsigned char *d_rows2 = nullptr;    // [v2_sectors * 32]
     uint32_t *d_edge4 = nullptr;         // [v2_edge_units * 4] row words of all targets, rows padded to 4 words
@@ -165,7 +167,7 @@ struct V2Build {
     bool planned = false;
     std::vector<uint32_t> word, ebase;       // per cell: row word; start of its targets in edge4 (units of 4 words)
     int64_t sectors = 0, units = 0;
-    int max_sectors = 0;
+    int max_sectors = 0, slot_sectors = 0;
     size_t rows_bytes = 0;
     uint32_t *d_ebase = nullptr;
     int *d_bad = nullptr;

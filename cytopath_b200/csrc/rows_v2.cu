@@ -121,6 +121,7 @@ bool v2_plan(const cyp_graph *g, const int64_t *h_row_ptr, V2Build *b) {
     b->ebase.resize(static_cast<size_t>(n));
     int64_t sectors = 0, units = 0;
     int max_sectors = 0;
+    int64_t hist[kV2MaxSectors + 1] = {0};
     for (int64_t r = 0; r < n; ++r) {
         const int len = static_cast<int>(h_row_ptr[r + 1] - h_row_ptr[r]);
         int nsect = (v2_used_bytes(len) + 31) / 32;
@@ -132,7 +133,17 @@ bool v2_plan(const cyp_graph *g, const int64_t *h_row_ptr, V2Build *b) {
         sectors += nsect;
         units += (len + 3) / 4;
         if (nsect > max_sectors) max_sectors = nsect;
+        ++hist[nsect];
     }
+    // slot of the step kernel: the smallest power of two (1..8 sectors) that holds 97 % of the rows; the few longer
+    // rows of a ragged graph are then searched in global memory instead of making every slot as large as the longest
+    int slot = max_sectors;
+    for (int cand = 1; cand <= 8; cand <<= 1) {
+        int64_t covered = 0;
+        for (int k = 0; k <= cand && k <= kV2MaxSectors; ++k) covered += hist[k];
+        if (cand >= max_sectors || covered * 100 >= n * 97) { slot = cand < max_sectors ? cand : max_sectors; break; }
+    }
+    b->slot_sectors = slot;
     b->sectors = sectors;
     b->units = units;
     b->max_sectors = max_sectors;
@@ -195,6 +206,7 @@ cudaError_t v2_finish(cyp_graph *g, V2Build *b, bool codes_ok) {
         g->v2_sectors = b->sectors;
         g->v2_edge_units = b->units;
         g->v2_max_sectors = b->max_sectors;
+        g->v2_slot_sectors = b->slot_sectors;
         g->device_bytes += static_cast<int64_t>(b->rows_bytes + sizeof(uint32_t) * 4 * (b->units + 1) + sizeof(uint32_t) * g->n);
         g->v2_ok = 1;
     }

@@ -191,7 +191,7 @@ static int launch_variant(const WalkParams &p, WalkVariant v, WalkMode mode, cud
 // long rows (C5, k = 200, 352-byte blocks): 16-bit rows + edge records through walk_tma.cu's bulk copies do 24.4 G
 // walker-steps/s, the fused rows 21.2 G with cooperative copies and 23.1 G with their own bulk flavour (few entries
 // of a 200-entry row fit the slack, so most steps still need the second gather)
-bool walk_auto_is_v2(const cyp_graph *g) { return g->v2_ok && g->v2_max_sectors * 32 <= 256; }
+bool walk_auto_is_v2(const cyp_graph *g) { return g->v2_ok && g->v2_slot_sectors * 32 <= 256; }
 
 WalkVariant pick_walk_variant(const cyp_graph *g, int variant) {
     if (variant > 0) return WalkVariant{variant / 100, variant % 100};

@@ -78,7 +78,9 @@ constexpr int kModeExact = 0, kModeRef = 1;
 // above ~16k cells the L1-bypassing copies are the faster ones.
 // CPR = 0: long rows.  Every thread issues ONE cp.async.bulk (UBLKCP) for its whole block and the warp's 32 copies
 // complete on one mbarrier; the slot is exactly the largest block (`bulk_stride` bytes, any multiple of 32).
-template <int CPR, int CDFM, int MODE, bool L1ROWS>
+// OVERSIZE: the graph has rows whose block is longer than the slot; they are searched in global memory (a template
+// parameter because the test costs 2-3 % on graphs that have none).
+template <int CPR, int CDFM, int MODE, bool L1ROWS, bool OVERSIZE>
 __global__ void __launch_bounds__(1024, 1) walk_v2_kernel(const WalkParams p, const int log_n /* search depth: 2^log_n >= longest row */,
                                                           const int bulk_stride) {
     constexpr bool BULK = CPR == 0;
@@ -185,41 +187,47 @@ __global__ void __launch_bounds__(1024, 1) walk_v2_kernel(const WalkParams p, co
                         while (key > 0 && u <= static_cast<double>(__fdiv_rn(static_cast<float>(key - 1), 1000.0f))) --key;
                         while (u > static_cast<double>(__fdiv_rn(static_cast<float>(key), 1000.0f))) ++key;
                     }
-                    const unsigned char *hi = slot + kV2Header;
-                    const unsigned char *lo = hi + len;
-                    const int key_hi = key >> 4;
-                    int j = 0;
-                    for (int step = 1 << (log_n - 1); step >= 1; step >>= 1) {
-                        const int probe = j + step - 1;
-                        if (probe < len && static_cast<int>(hi[probe]) < key_hi) j += step;
-                    }
-                    auto code_at = [&](int jj) { return (static_cast<int>(hi[jj]) << 4) | ((static_cast<int>(lo[jj >> 1]) >> ((jj & 1) * 4)) & 15); };
-                    if constexpr (CDFM == kModeExact) {
-                        while (j < len) {
-                            const int q = code_at(j);
-                            if (q >= t_def) break;                               // certain crossing
-                            if (q == key) {                                      // undecided by the code: float64 compare (:49)
-                                const RowInfo ri = p.rows[cell];
-                                if (u <= __ldg(static_cast<const double *>(p.cdf) + static_cast<int64_t>(ri.off_units) * kRowAlign + j)) break;
+                    // a block longer than the slot (a few long rows of a ragged graph: the slot is sized for the typical
+                    // row) is searched where it lies, in global memory; its header did fit
+                    const bool oversize = OVERSIZE && !BULK && (word >> kWordOffBits) * 32u > static_cast<uint32_t>(16 * CPR);
+                    auto follow = [&](const unsigned char *blk) -> int {        // returns the entry, sets `next`
+                        const unsigned char *hi = blk + kV2Header;
+                        const unsigned char *lo = hi + len;
+                        const int key_hi = key >> 4;
+                        int j = 0;
+                        for (int step = 1 << (log_n - 1); step >= 1; step >>= 1) {
+                            const int probe = j + step - 1;
+                            if (probe < len && static_cast<int>(hi[probe]) < key_hi) j += step;
+                        }
+                        auto code_at = [&](int jj) { return (static_cast<int>(hi[jj]) << 4) | ((static_cast<int>(lo[jj >> 1]) >> ((jj & 1) * 4)) & 15); };
+                        if constexpr (CDFM == kModeExact) {
+                            while (j < len) {
+                                const int q = code_at(j);
+                                if (q >= t_def) break;                           // certain crossing
+                                if (q == key) {                                  // undecided by the code: float64 compare (:49)
+                                    const RowInfo ri = p.rows[cell];
+                                    if (u <= __ldg(static_cast<const double *>(p.cdf) + static_cast<int64_t>(ri.off_units) * kRowAlign + j)) break;
+                                }
+                                ++j;
                             }
-                            ++j;
-                        }
-                    } else {
-                        while (j < len && code_at(j) < key) ++j;
-                    }
-                    // ---- next row word
-                    if (j < len) {
-                        const unsigned long long mask = (static_cast<unsigned long long>(h.w) << 32) | h.z;
-                        if (j < 64 && ((mask >> j) & 1ull)) {
-                            const int rank = __popcll(mask & ((1ull << j) - 1ull));
-                            next = *reinterpret_cast<const uint32_t *>(slot + v2_used_bytes(len) + 4 * rank);
                         } else {
-                            const uint32_t ebase = *reinterpret_cast<const uint32_t *>(slot + 16);
-                            next = ldg_word(p.edge4 + static_cast<size_t>(ebase) * 4 + j);
+                            while (j < len && code_at(j) < key) ++j;
                         }
-                    } else if (p.nocross) {
-                        atomicAdd(p.nocross, 1ull);                              // stays where it is (reference: IndexError at :49)
-                    }
+                        // ---- next row word
+                        if (j < len) {
+                            const unsigned long long mask = (static_cast<unsigned long long>(h.w) << 32) | h.z;
+                            if (j < 64 && ((mask >> j) & 1ull)) {
+                                const int rank = __popcll(mask & ((1ull << j) - 1ull));
+                                next = *reinterpret_cast<const uint32_t *>(blk + v2_used_bytes(len) + 4 * rank);
+                            } else {
+                                const uint32_t ebase = *reinterpret_cast<const uint32_t *>(blk + 16);
+                                next = ldg_word(p.edge4 + static_cast<size_t>(ebase) * 4 + j);
+                            }
+                        }
+                        return j;
+                    };
+                    const int j = oversize ? follow(p.rows2 + (static_cast<size_t>(word & kWordOffMask) << 5)) : follow(slot);
+                    if (j >= len && p.nocross) atomicAdd(p.nocross, 1ull);       // stays where it is (reference: IndexError at :49)
                 }
             }
             if (t == nt) break;
@@ -249,13 +257,19 @@ struct V2Config {
     int threads;
     int log_n;
     int stride;         // bytes between slots
+    bool oversize;      // some blocks are longer than the slot
     size_t smem;
 };
 
-// variant: 0 = auto; 9500 + T/32 = T threads per CTA; 9600 + T/32 = two CTAs of T threads per SM (experiment).
+// variant: 0 = auto; 9500 + T/32 = T threads per CTA; 9600 + T/32 = two CTAs of T threads per SM (experiment);
+// 9700 + T/32 = slot sized for the longest row (bulk copies above 256 bytes).
 static bool v2_config(const cyp_graph *g, int variant, int64_t n_walkers, int sm_count, V2Config *out) {
     if (!g->v2_ok) return false;
-    const int block = g->v2_max_sectors * 32;
+    // slot = the block size that covers (almost) every row (cyp_graph::v2_slot_sectors, rows_v2.cu); variants 97xx
+    // force the largest block instead (then rows above 256 bytes take the bulk flavour)
+    bool force_max = false;
+    if (variant > 9700) { force_max = true; variant -= 200; }
+    const int block = (force_max ? g->v2_max_sectors : g->v2_slot_sectors) * 32;
     int cpr = 0, stride = 0;
     if (block <= 256) {                                  // small rows: cooperative 16-byte copies, power-of-two slots
         cpr = 2;
@@ -284,7 +298,7 @@ static bool v2_config(const cyp_graph *g, int variant, int64_t n_walkers, int sm
     int log_n = 1;
     while ((1 << log_n) < g->max_len) ++log_n;
     const size_t bars = cpr == 0 ? static_cast<size_t>(((threads >> 5) * 8 + 127) & ~127) : 0;
-    *out = V2Config{cpr, ctas, threads, log_n, stride, bars + static_cast<size_t>(threads) * stride};
+    *out = V2Config{cpr, ctas, threads, log_n, stride, cpr != 0 && g->v2_max_sectors * 32 > 16 * cpr, bars + static_cast<size_t>(threads) * stride};
     return true;
 }
 
@@ -299,9 +313,9 @@ static int v2_sm_count() {
     return cached;
 }
 
-template <int CPR, int CDFM, int MODE, bool L1ROWS>
+template <int CPR, int CDFM, int MODE, bool L1ROWS, bool OVERSIZE>
 static int launch_v2_l1(const WalkParams &p, const V2Config &c, int sm_count, cudaStream_t stream) {
-    auto kernel = walk_v2_kernel<CPR, CDFM, MODE, L1ROWS>;
+    auto kernel = walk_v2_kernel<CPR, CDFM, MODE, L1ROWS, OVERSIZE>;
     static size_t smem_set = 0;
     if (c.smem > smem_set) {
         CYP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c.smem)));
@@ -326,7 +340,10 @@ static int launch_v2_l1(const WalkParams &p, const V2Config &c, int sm_count, cu
 
 template <int CPR, int CDFM, int MODE>
 static int launch_v2_one(const WalkParams &p, const V2Config &c, int sm_count, cudaStream_t stream) {
-    return p.l1_rows ? launch_v2_l1<CPR, CDFM, MODE, true>(p, c, sm_count, stream) : launch_v2_l1<CPR, CDFM, MODE, false>(p, c, sm_count, stream);
+    if constexpr (CPR == 0) return launch_v2_l1<CPR, CDFM, MODE, false, false>(p, c, sm_count, stream);     // bulk copies: whole rows, L2 only
+    if (c.oversize)
+        return p.l1_rows ? launch_v2_l1<CPR, CDFM, MODE, true, true>(p, c, sm_count, stream) : launch_v2_l1<CPR, CDFM, MODE, false, true>(p, c, sm_count, stream);
+    return p.l1_rows ? launch_v2_l1<CPR, CDFM, MODE, true, false>(p, c, sm_count, stream) : launch_v2_l1<CPR, CDFM, MODE, false, false>(p, c, sm_count, stream);
 }
 
 template <int CPR, int CDFM>

@@ -207,3 +207,19 @@ def random_sparse_rows(n=200, max_nnz=12, seed=0, messy=True, dtype=np.float64) 
     indptr = np.concatenate([[0], np.cumsum(np.bincount(rows, minlength=n))])
     M = sparse.csr_matrix((vals[order], cols[order].astype(np.int32), indptr), shape=(n, n))
     return M
+
+
+def hub_graph(n=3000, k_typ=(8, 40), hub_share=0.02, k_hub=(150, 300), seed=0) -> sparse.csr_matrix:
+    """Row-stochastic matrix whose rows have `k_typ` entries except a few hubs with `k_hub` entries, with skewed
+    probabilities: the shape of a real velocity graph (most rows ~30 entries, a few long ones)."""
+    rng = np.random.default_rng(seed)
+    lens = rng.integers(k_typ[0], k_typ[1] + 1, size=n)
+    hubs = rng.random(n) < hub_share
+    lens[hubs] = rng.integers(k_hub[0], k_hub[1] + 1, size=int(hubs.sum()))
+    lens = np.minimum(lens, n)
+    rows = np.repeat(np.arange(n), lens)
+    cols = np.concatenate([np.sort(rng.choice(n, size=int(l), replace=False)) for l in lens])
+    vals = np.exp(4.0 * rng.normal(size=len(cols)))
+    M = sparse.csr_matrix((vals, (rows, cols)), shape=(n, n))
+    M = sparse.diags(1.0 / np.asarray(M.sum(axis=1)).ravel()) @ M
+    return M.tocsr()

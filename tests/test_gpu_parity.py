@@ -113,7 +113,7 @@ def test_sampling_accepts_float32_matrix_in_place_and_checks_normalisation_on_de
     run_quiet(cytopath_b200.sampling, ad, **kw2, seed=5)
 
 
-@pytest.mark.parametrize("gname", ["k4", "k12", "k30", "k50", "k200", "ragged"])
+@pytest.mark.parametrize("gname", ["k4", "k12", "k30", "k50", "k200", "ragged", "hubs"])
 @pytest.mark.parametrize("mode,omode", MODES)
 def test_k1b_fused_rows_byte_exact_vs_oracle(gname, mode, omode, monkeypatch):
     """K1b (csrc/rows_v2.cu): header, 12-bit code planes, inlined targets of the most probable entries, row words
@@ -204,6 +204,7 @@ GRAPHS = {
     "k50": lambda: synth.branching_graph(n=4000, k=50, n_branches=4, seed=3, workers=1).T,
     "k200": lambda: synth.cycling_graph(n=3000, k=200, seed=4, workers=1).T,
     "ragged": lambda: synth.random_sparse_rows(n=400, max_nnz=70, seed=9, messy=True),
+    "hubs": lambda: synth.hub_graph(n=3000, seed=6),        # 2 % of the rows are longer than the fused-row kernel's slot
 }
 
 
@@ -244,7 +245,7 @@ def test_k2_bit_exact_vs_oracle_all_variants(gname, mode, omode, monkeypatch):
     # paired flavour (two walkers per thread): 32 / 128 / 512 / 1024 threads per CTA; 62, 63 and 64 columns
     for variant in (9401, 9404, 9416, 9432):
         if g.variant_name(variant) == "not applicable":
-            assert gname == "ragged"                          # negative probabilities: no 16-bit codes
+            assert gname in ("ragged", "hubs")                # rows that do not fit one slot of the paired kernel
             continue
         assert "walk_pp_kernel" in g.variant_name(variant)
         for n_t in (nt, 62, 63):
@@ -271,6 +272,15 @@ def test_k2_bit_exact_vs_oracle_all_variants(gname, mode, omode, monkeypatch):
             np.testing.assert_array_equal(out.cpu().numpy(), wnt, err_msg="%s nt=%d" % (g.variant_name(variant), n_t))
     monkeypatch.delenv("CYP_V2_L1")
     assert ("walk_v2_kernel" in g.variant_name(0)) == (gname != "k200")     # the auto variant picks it, except for long rows
+    if gname == "hubs":                                       # slot for the typical row; the hubs are searched in HBM
+        assert "slot=128B" in g.variant_name(0) and g.layout()["max_block_bytes"] > 256
+        for variant in (9704, 9716):                          # slot for the longest row: bulk-copy flavour
+            assert "bulk" in g.variant_name(variant)
+            out = torch.full((len(roots) * sims, nt + 1), -7, dtype=torch.int32, device="cuda")
+            _lib.check(L.cyp_walk_device(g.handle, d_roots.data_ptr(), len(roots), sims, 0, len(roots) * sims, nt, seed, rnd,
+                                         None, out.data_ptr(), None, variant, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            torch.cuda.synchronize()
+            np.testing.assert_array_equal(out.cpu().numpy(), want, err_msg=g.variant_name(variant))
     # auto variant through the host entry point, a shard in the middle of the round
     got = g.walk(roots, sims, nt, seed=seed, round_idx=rnd, walker_begin=100, n_walkers=211, strict=False)
     np.testing.assert_array_equal(got, want[100:311])
