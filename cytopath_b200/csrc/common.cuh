@@ -120,8 +120,14 @@ struct EdgeRec {
 constexpr int kWordOffBits = 27;
 constexpr uint32_t kWordOffMask = (1u << kWordOffBits) - 1u;
 constexpr int kV2Header = 20;
-constexpr int kV2MaxSectors = 31;          // 5 bits of a row word
+constexpr int kV2MaxSectors = 31;          // 5 bits of a row word (saturating)
 __host__ __device__ inline int v2_used_bytes(int len) { return (kV2Header + len + (len + 1) / 2 + 3) & ~3; }
+// sectors of a row's block: what it uses, plus `extra` sectors of inlined targets while the block stays below
+// kV2MaxSectors (longer blocks exist -- the row word's sector field saturates there -- but get no extra)
+__host__ __device__ inline int v2_block_sectors(int len, int extra) {
+    const int n = (v2_used_bytes(len) + 31) / 32;
+    return (len > 0 && n + extra <= kV2MaxSectors) ? n + extra : n;
+}
 
 }  // namespace cyp
 
@@ -167,7 +173,7 @@ struct V2Build {
     bool planned = false;
     std::vector<uint32_t> word, ebase;       // per cell: row word; start of its targets in edge4 (units of 4 words)
     int64_t sectors = 0, units = 0;
-    int max_sectors = 0, slot_sectors = 0;
+    int max_sectors = 0, slot_sectors = 0, extra = 0;
     size_t rows_bytes = 0;
     uint32_t *d_ebase = nullptr;
     int *d_bad = nullptr;

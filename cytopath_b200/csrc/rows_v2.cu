@@ -37,7 +37,7 @@ template <typename CdfT>
 __global__ void __launch_bounds__(256)
 build_rows_v2_kernel(int64_t row_begin, int64_t row_end, const RowInfo *__restrict__ rows, const CdfT *__restrict__ cdf, const double *__restrict__ val,
                      const int32_t *__restrict__ col, const uint32_t *__restrict__ word, const uint32_t *__restrict__ ebase,
-                     unsigned char *__restrict__ rows2, uint32_t *__restrict__ edge4, int *__restrict__ bad_flag) {
+                     int extra, unsigned char *__restrict__ rows2, uint32_t *__restrict__ edge4, int *__restrict__ bad_flag) {
     const int64_t r = row_begin + ((static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     if (r >= row_end) return;
@@ -46,8 +46,8 @@ build_rows_v2_kernel(int64_t row_begin, int64_t row_end, const RowInfo *__restri
     const int64_t off = static_cast<int64_t>(ri.off_units) * kRowAlign;
     const uint32_t w = word[r];
     unsigned char *blk = rows2 + static_cast<size_t>(w & kWordOffMask) * 32;
-    const int nsect = static_cast<int>(w >> kWordOffBits);
     const int used = v2_used_bytes(len);
+    const int nsect = v2_block_sectors(len, extra);          // the word's field saturates at kV2MaxSectors
     int m = (nsect * 32 - used) / 4;
     if (m > len) m = len;
     if (m > 64) m = 64;
@@ -124,16 +124,16 @@ bool v2_plan(const cyp_graph *g, const int64_t *h_row_ptr, V2Build *b) {
     int64_t hist[kV2MaxSectors + 1] = {0};
     for (int64_t r = 0; r < n; ++r) {
         const int len = static_cast<int>(h_row_ptr[r + 1] - h_row_ptr[r]);
-        int nsect = (v2_used_bytes(len) + 31) / 32;
-        if (len > 0 && nsect + extra <= kV2MaxSectors) nsect += extra;
-        if (nsect > kV2MaxSectors) return false;
+        const int nsect = v2_block_sectors(len, extra);
         if (sectors > static_cast<int64_t>(kWordOffMask) - nsect - kV2MaxSectors || units >= (1ll << 32) - 1) return false;
-        b->word[r] = (static_cast<uint32_t>(nsect) << kWordOffBits) | static_cast<uint32_t>(sectors);
+        // the word's sector field saturates: a longer block is never copied whole (slots hold <= 8 sectors), the step
+        // kernel searches it in HBM and takes its length from the header
+        b->word[r] = (static_cast<uint32_t>(nsect < kV2MaxSectors ? nsect : kV2MaxSectors) << kWordOffBits) | static_cast<uint32_t>(sectors);
         b->ebase[r] = static_cast<uint32_t>(units);
         sectors += nsect;
         units += (len + 3) / 4;
         if (nsect > max_sectors) max_sectors = nsect;
-        ++hist[nsect];
+        ++hist[nsect < kV2MaxSectors ? nsect : kV2MaxSectors];
     }
     // slot of the step kernel: the smallest power of two (1..8 sectors) that holds 97 % of the rows; the few longer
     // rows of a ragged graph are then searched in global memory instead of making every slot as large as the longest
@@ -144,6 +144,7 @@ bool v2_plan(const cyp_graph *g, const int64_t *h_row_ptr, V2Build *b) {
         if (cand >= max_sectors || covered * 100 >= n * 97) { slot = cand < max_sectors ? cand : max_sectors; break; }
     }
     b->slot_sectors = slot;
+    b->extra = extra;
     b->sectors = sectors;
     b->units = units;
     b->max_sectors = max_sectors;
@@ -190,10 +191,10 @@ cudaError_t v2_launch(cyp_graph *g, V2Build *b, int64_t row_begin, int64_t row_e
     const unsigned grid = static_cast<unsigned>((rows * 32 + threads - 1) / threads);
     if (g->cdf_mode == CYP_CDF_EXACT)
         build_rows_v2_kernel<double><<<grid, threads, 0, stream>>>(row_begin, row_end, g->d_row, static_cast<const double *>(g->d_cdf), g->d_val,
-                                                                   g->d_col, g->d_word, b->d_ebase, g->d_rows2, g->d_edge4, b->d_bad);
+                                                                   g->d_col, g->d_word, b->d_ebase, b->extra, g->d_rows2, g->d_edge4, b->d_bad);
     else
         build_rows_v2_kernel<float><<<grid, threads, 0, stream>>>(row_begin, row_end, g->d_row, static_cast<const float *>(g->d_cdf), g->d_val,
-                                                                  g->d_col, g->d_word, b->d_ebase, g->d_rows2, g->d_edge4, b->d_bad);
+                                                                  g->d_col, g->d_word, b->d_ebase, b->extra, g->d_rows2, g->d_edge4, b->d_bad);
     return cudaGetLastError();
 }
 

@@ -269,6 +269,7 @@ static bool v2_config(const cyp_graph *g, int variant, int64_t n_walkers, int sm
     // force the largest block instead (then rows above 256 bytes take the bulk flavour)
     bool force_max = false;
     if (variant > 9700) { force_max = true; variant -= 200; }
+    if (force_max && g->v2_max_sectors > kV2MaxSectors) return false;      // a bulk copy needs the block's exact size in the row word
     const int block = (force_max ? g->v2_max_sectors : g->v2_slot_sectors) * 32;
     int cpr = 0, stride = 0;
     if (block <= 256) {                                  // small rows: cooperative 16-byte copies, power-of-two slots

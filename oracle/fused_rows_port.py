@@ -20,7 +20,7 @@ def plan(indptr, extra=None):
         extra = 1 if (int(nsect.sum()) + len(lens)) * 32 <= (32 << 20) else 0
     nsect = nsect + np.where((lens > 0) & (nsect + extra <= 31), extra, 0)
     first = np.concatenate([[0], np.cumsum(nsect)[:-1]])
-    words = ((nsect.astype(np.uint64) << OFF_BITS) | first.astype(np.uint64)).astype(np.uint32)
+    words = ((np.minimum(nsect, 31).astype(np.uint64) << OFF_BITS) | first.astype(np.uint64)).astype(np.uint32)   # the sector field saturates
     ebase = np.concatenate([[0], np.cumsum((lens + 3) // 4)[:-1]]).astype(np.int64)
     return words, ebase, int(nsect.sum()), int(((lens + 3) // 4).sum()), extra
 
@@ -37,13 +37,15 @@ def build(C, cdf, exact, extra=None):
     indptr, indices, data = C.indptr, C.indices, np.asarray(C.data, dtype=np.float64)
     n = C.shape[0]
     words, ebase, sectors, units, extra = plan(indptr, extra)
+    first_sector = (words & np.uint32((1 << OFF_BITS) - 1)).astype(np.int64)
+    true_nsect = np.diff(np.concatenate([first_sector, [sectors]]))
     rows = np.zeros(sectors * 32, dtype=np.uint8)
     targets = np.zeros(units * 4, dtype=np.uint32)
     for r in range(n):
         a, b = int(indptr[r]), int(indptr[r + 1])
         length = b - a
-        first = int(words[r]) & ((1 << OFF_BITS) - 1)
-        nsect = int(words[r]) >> OFF_BITS
+        first = int(first_sector[r])
+        nsect = int(true_nsect[r])
         blk = rows[first * 32:(first + nsect) * 32]
         used = used_bytes(length)
         m = min(length, 64, (nsect * 32 - used) // 4)

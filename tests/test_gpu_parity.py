@@ -140,24 +140,51 @@ def test_k1b_fused_rows_byte_exact_vs_oracle(gname, mode, omode, monkeypatch):
 
 
 def test_k1b_not_applicable_falls_back_to_edge_records():
-    """Negative probabilities (CDF not monotone) and rows too long for a block: no fused rows, the 16-bit / plain
-    kernels take over and still match the oracle."""
+    """A negative probability (CDF not monotone): no fused rows, no 16-bit codes; the literal-scan kernels take over
+    and still match the oracle."""
     from scipy import sparse
-    rng = np.random.default_rng(11)
-    n = 900
-    dense_row = np.full(n, 1.0 / n)                                   # 900 entries: block would need 43 sectors
-    M = sparse.lil_matrix((n, n))
-    M[0, :] = dense_row
-    for i in range(1, n):
-        c = rng.choice(n, size=5, replace=False)
-        M[i, c] = 0.2
-    C = sp.canonical_csr(M.tocsr())
+    P = np.array([[0.5, -0.25, 0.75, 0.0], [0.0, 1.0, 0.0, 0.0], [0.25, 0.25, 0.25, 0.25], [1.0, 0, 0, 0]])
+    C = sp.canonical_csr(sparse.csr_matrix(P))
     g = _lib.Graph(C, _lib.CDF_EXACT)
     assert not g.layout()["fused"] and "walk_v2" not in g.variant_name(0)
     roots = np.array([0, 1, 2, 3])
-    want = cwalk.walk(C, cwalk.build_cdf(C, 1), np.repeat(roots, 30), 40, seed=2)
-    np.testing.assert_array_equal(g.walk(roots, 30, 40, seed=2), want)
+    want = cwalk.walk(C, cwalk.build_cdf(C, 1), np.repeat(roots, 30), 40, seed=2, strict=False)
+    np.testing.assert_array_equal(g.walk(roots, 30, 40, seed=2, strict=False), want)
     g.close()
+
+
+def test_k1b_very_long_row_is_searched_in_hbm(monkeypatch):
+    """One row of 900 entries (its block needs 43 sectors, more than a row word can say): the word's sector field
+    saturates, the step kernel takes the length from the header and searches the block in global memory."""
+    from scipy import sparse
+    from oracle import fused_rows_port as frp
+    rng = np.random.default_rng(11)
+    n = 900
+    M = sparse.lil_matrix((n, n))
+    M[0, :] = np.exp(3.0 * rng.normal(size=n))
+    for i in range(1, n):
+        c = rng.choice(n, size=5, replace=False)
+        M[i, c] = rng.random(5) + 0.05
+        M[i, 0] = 2.0                                                  # everybody keeps returning to the long row
+    M = M.tocsr()
+    M = sparse.diags(1.0 / np.asarray(M.sum(axis=1)).ravel()) @ M
+    C = sp.canonical_csr(M)
+    for mode, omode in MODES:
+        g = _lib.Graph(C, mode)
+        lay = g.layout()
+        assert lay["fused"] and lay["max_block_bytes"] > 31 * 32 and "walk_v2" in g.variant_name(0)
+        cdf = cwalk.build_cdf(C, omode)
+        rows, words, targets = g.fused()
+        want_rows, want_words, want_targets = frp.build(C, cdf, exact=(mode == _lib.CDF_EXACT))
+        np.testing.assert_array_equal(words, want_words)
+        np.testing.assert_array_equal(rows, want_rows)
+        np.testing.assert_array_equal(targets, want_targets)
+        roots = np.array([0, 1, 2, 3])
+        want = cwalk.walk(C, cdf, np.repeat(roots, 200), 60, seed=2)
+        assert (want == 0).mean() > 0.2                               # the long row is visited all the time
+        np.testing.assert_array_equal(g.walk(roots, 200, 60, seed=2), want)
+        assert g.variant_name(9704) == "not applicable"               # no bulk flavour: a row word cannot hold this block's size
+        g.close()
 
 
 # ---- K4 ---------------------------------------------------------------------------------
