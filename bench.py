@@ -289,7 +289,7 @@ def run_b200(args, w):
 
     def step(i):
         _lib.check(L.cyp_walk_device(graph.handle, d_roots.data_ptr(), n_roots, sims_per_root, w0, W, nt, args.seed, i,
-                                     None, d_seq.data_ptr(), None if os.environ.get("BENCH_NO_MISS") else d_miss.data_ptr(), args.variant, sptr))
+                                     None, d_seq.data_ptr(), d_miss.data_ptr(), args.variant, sptr))
 
     clocks = ClockSampler(local_rank)
     clocks.start()                                               # attached before the warm-up, see ClockSampler

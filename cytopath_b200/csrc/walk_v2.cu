@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(1024, 1) walk_v2_kernel(const WalkParams p, co
     }
 }
 
-// Tried on C4 and dropped (gpurun_out/flags.log, profiles/r01_v2_experiments.md): L2 cache hints (streaming
+// Tried on C4 and dropped (profiles/r01_v2_experiments.md, r01_v2_flags.log): L2 cache hints (streaming
 // trajectory stores, evict-first target gathers, evict-last row copies: 52.2-52.3 G walker-steps/s with any
 // combination, i.e. no effect), a persisting-L2 access-policy window on the fused rows (hitRatio 0.3..1.0: 24-34 G,
 // much worse), two CTAs of 512..640 threads per SM (57.7-58.6 vs 57.0 G: no gain from more walkers in flight), a

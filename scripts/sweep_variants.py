@@ -47,9 +47,6 @@ for v in [int(x) for x in args.variants.split(",")]:
     step(0); torch.cuda.synchronize()
     if args.barrier and args.init_nccl:
         dist.barrier(); torch.cuda.synchronize()
-        import ctypes as _c
-        rt = _c.CDLL("libcudart.so.12"); lim = _c.c_size_t(0)
-        rt.cudaDeviceGetLimit(_c.byref(lim), 0x06); print("persisting L2 limit", lim.value)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps): step(1 + i)
