@@ -116,7 +116,7 @@ struct EdgeRec {
 // exactly what a warp needs to start copying the next row, so for the inlined entries (the most
 // probable ones: the slack of the block's last sector is filled with them) a step is ONE gather.
 // 12-bit codes: exact mode q = min(4095, floor(cdf * 4096)) (undecided compares are settled against the
-// float64 CDF, as for the 16-bit codes); reference mode q = m with cdf = fl32(m / 1000), lossless.
+// float64 CDF, as for the 16-bit codes); reference mode q = 4 m with cdf = fl32(m / 1000), lossless.
 constexpr int kWordOffBits = 27;
 constexpr uint32_t kWordOffMask = (1u << kWordOffBits) - 1u;
 constexpr int kV2Header = 20;

@@ -27,9 +27,11 @@ __device__ __forceinline__ int code12(CdfT c, int *bad) {
         const double x = floor(c * 4096.0);
         return static_cast<int>(x > 4095.0 ? 4095.0 : x);
     } else {
-        const float m = rintf(__fmul_rn(c, 1000.0f));       // the stored value is fl32(m / 1000) exactly (:31)
-        if (!(m >= 0.0f && m <= 4095.0f)) { *bad = 1; return 0; }
-        return static_cast<int>(m);
+        // the stored value is fl32(m / 1000) exactly (:31).  The code is 4 m: m <= 1001 needs 10 bits, and shifted
+        // by two the upper-8-bit plane (what the binary search runs on) tells 251 levels apart instead of 63
+        const float m = rintf(__fmul_rn(c, 1000.0f));
+        if (!(m >= 0.0f && m <= 1023.0f)) { *bad = 1; return 0; }
+        return static_cast<int>(m) << 2;
     }
 }
 

@@ -186,6 +186,7 @@ __global__ void __launch_bounds__(1024, 1) walk_v2_kernel(const WalkParams p, co
                         key = static_cast<int>(ceil(u * 1000.0));               // smallest integer m with u <= (double)fl32(m / 1000)
                         while (key > 0 && u <= static_cast<double>(__fdiv_rn(static_cast<float>(key - 1), 1000.0f))) --key;
                         while (u > static_cast<double>(__fdiv_rn(static_cast<float>(key), 1000.0f))) ++key;
+                        key <<= 2;                                               // the codes are 4 m (rows_v2.cu): 8 significant bits in the upper plane
                     }
                     // a block longer than the slot (a few long rows of a ragged graph: the slot is sized for the typical
                     // row) is searched where it lies, in global memory; its header did fit

@@ -28,7 +28,7 @@ def plan(indptr, extra=None):
 def codes12(cdf_row, exact):
     if exact:
         return np.minimum(4095, np.floor(np.asarray(cdf_row, dtype=np.float64) * 4096.0)).astype(np.int64)
-    return np.rint(np.asarray(cdf_row, dtype=np.float32) * np.float32(1000.0)).astype(np.int64)
+    return np.rint(np.asarray(cdf_row, dtype=np.float32) * np.float32(1000.0)).astype(np.int64) << 2     # 4 m, see rows_v2.cu
 
 
 def build(C, cdf, exact, extra=None):
