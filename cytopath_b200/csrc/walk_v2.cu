@@ -331,9 +331,9 @@ static int launch_v2_l1(const WalkParams &p, const V2Config &c, int sm_count, cu
     if (trace) {
         int dev = -1;
         cudaGetDevice(&dev);
-        fprintf(stderr, "[cyp trace] walk_v2: device %d grid %u threads %d smem %zu walkers %lld begin %lld sims/root %lld nt %d\n", dev, grid,
+        fprintf(stderr, "[cyp trace] walk_v2: device %d grid %u threads %d smem %zu walkers %lld begin %lld sims/root %lld nt %d rows2 %p edge4 %p out %p\n", dev, grid,
                 c.threads, c.smem, static_cast<long long>(p.n_walkers), static_cast<long long>(p.walker_begin),
-                static_cast<long long>(p.sims_per_root), p.nt);
+                static_cast<long long>(p.sims_per_root), p.nt, static_cast<const void *>(p.rows2), static_cast<const void *>(p.edge4), static_cast<const void *>(p.out_seq));
     }
     kernel<<<grid, c.threads, c.smem, stream>>>(p, c.log_n, c.stride);
     CYP_CUDA(cudaGetLastError());

@@ -15,6 +15,7 @@ ap.add_argument("--variants", default="404,802,804,1602,1604,3202,3204")
 ap.add_argument("--walkers", type=int, default=0)
 ap.add_argument("--sims-per-root", type=int, default=0)
 ap.add_argument("--walker-begin", type=int, default=0)
+ap.add_argument("--pad-mb", type=int, default=0, help="allocate this much device memory first (shifts every later allocation)")
 ap.add_argument("--barrier", action="store_true", help="dist.barrier() before every timed block (with --init-nccl)")
 ap.add_argument("--init-nccl", action="store_true", help="initialise a 1-rank NCCL group first (does the communicator change K2's speed?)")
 args = ap.parse_args()
@@ -25,6 +26,10 @@ if args.init_nccl:
     torch.cuda.set_device(lrk)
     dist.init_process_group("nccl", rank=rk, world_size=ws, device_id=torch.device("cuda", lrk))
     x = torch.ones(4, device="cuda"); dist.all_reduce(x); torch.cuda.synchronize()
+if args.pad_mb:
+    _pad = torch.empty(args.pad_mb << 20, dtype=torch.uint8, device="cuda")
+    import ctypes as _ct                                     # ... including the library's (stream-ordered pool)
+    _pp = _ct.c_void_p(); _lib.load(); _rt = _ct.CDLL("libcudart.so.12"); _rt.cudaMallocAsync(_ct.byref(_pp), _ct.c_size_t(args.pad_mb << 20), None)
 w = bench.WORKLOADS[args.workload]
 g, C, roots = bench.make_graph(w, 1)
 mode = _lib.CDF_EXACT if args.cdf_mode == "exact" else _lib.CDF_REFERENCE
@@ -40,6 +45,7 @@ sptr = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 elem = 8 if mode == _lib.CDF_EXACT else 4
 bps = elem * (C.nnz / C.shape[0]) + 16
 print("workload %s mode %s W=%d nt=%d build_ms=%.2f" % (args.workload, args.cdf_mode, W, nt, graph.build_ms()))
+print("d_seq at 0x%x roots at 0x%x" % (d_seq.data_ptr(), d_roots.data_ptr()))
 for v in [int(x) for x in args.variants.split(",")]:
     def step(i):
         _lib.check(L.cyp_walk_device(graph.handle, d_roots.data_ptr(), len(roots), sims, w0, W, nt, 1234, i, None,
