@@ -161,6 +161,7 @@ struct cyp_graph {
                                          // sectors) or, if no such size does, the largest block; longer rows are searched in HBM
     int64_t v2_sectors = 0;              // total sectors of d_rows2
     unsigned char *d_rows2 = nullptr;    // [v2_sectors * 32]
+    unsigned char *d_rows2_base = nullptr;   // the allocation d_rows2 lies in (d_rows2 = base + placement offset)
     uint32_t *d_edge4 = nullptr;         // [v2_edge_units * 4] row words of all targets, rows padded to 4 words
     int64_t v2_edge_units = 0;
     uint32_t *d_word = nullptr;          // [n] row word of every cell (the roots start from it)

@@ -381,7 +381,7 @@ static void graph_free(cyp_graph *g) {
     dev_free(g->d_edge);
     dev_free(g->d_val);
     dev_free(g->d_row_ptr);
-    dev_free(g->d_rows2);
+    dev_free(g->d_rows2_base);
     dev_free(g->d_edge4);
     dev_free(g->d_word);
     delete g;

@@ -161,14 +161,19 @@ void v2_release(cyp_graph *g, V2Build *b) {
     b->d_ebase = nullptr;
     b->d_bad = nullptr;
     if (!g->v2_ok) {
-        dev_free(g->d_rows2); dev_free(g->d_edge4); dev_free(g->d_word);
-        g->d_rows2 = nullptr; g->d_edge4 = nullptr; g->d_word = nullptr;
+        dev_free(g->d_rows2_base); dev_free(g->d_edge4); dev_free(g->d_word);
+        g->d_rows2 = nullptr; g->d_rows2_base = nullptr; g->d_edge4 = nullptr; g->d_word = nullptr;
     }
 }
 
 // Device arrays (default stream).
 cudaError_t v2_alloc(cyp_graph *g, V2Build *b) {
-    cudaError_t e = dev_alloc(&g->d_rows2, b->rows_bytes);
+    // CYP_ROWS2_OFFSET_KB (developer switch, multiples of 4): shifts the fused rows inside their allocation; which L2
+    // slices serve the hot rows depends on it (scripts/placement_scan.py)
+    size_t offset = 0;
+    if (const char *o = getenv("CYP_ROWS2_OFFSET_KB")) offset = static_cast<size_t>(atol(o)) << 10;
+    cudaError_t e = dev_alloc(&g->d_rows2_base, b->rows_bytes + offset);
+    g->d_rows2 = g->d_rows2_base ? g->d_rows2_base + offset : nullptr;
     if (e == cudaSuccess) e = dev_alloc(&g->d_edge4, sizeof(uint32_t) * 4 * static_cast<size_t>(b->units + 1));
     if (e == cudaSuccess) e = dev_alloc(&g->d_word, sizeof(uint32_t) * g->n);
     if (e == cudaSuccess) e = dev_alloc(&b->d_ebase, sizeof(uint32_t) * g->n);
