@@ -737,3 +737,18 @@ def test_f4_directionality_score_vs_oracle_large():
     for t, u in zip(got, want):
         for a, b in zip(t, u):
             np.testing.assert_allclose(a, b, rtol=1e-11, atol=1e-14, equal_nan=True)
+
+
+def test_release_cached_memory_then_reuse():
+    """Large blocks are kept for exact-size reuse across calls (graph.cu); cyp_release_cached_memory returns them and
+    the library keeps working afterwards."""
+    C = sp.canonical_csr(synth.branching_graph(n=200_000, k=50, n_branches=4, seed=1, workers=1).T)     # ~80 MB per CDF array
+    want = None
+    for _ in range(3):
+        g = _lib.Graph(C, _lib.CDF_EXACT)
+        got = g.walk(np.arange(16), 8, 30, seed=4)
+        want = got if want is None else want
+        np.testing.assert_array_equal(got, want)
+        g.close()
+        _lib.release_cached_memory()
+    _lib.release_cached_memory(0)
