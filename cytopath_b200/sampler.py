@@ -197,7 +197,10 @@ def sampling(data, auto_adjust=True, matrix_key="T_forward", cluster_key="louvai
         Key of the Philox4x32-10 uniform stream (walker, step and round are the counter).
     cdf_mode : 'reference' | 'exact'
         'reference' reproduces the reference's float32, 3-decimal CDF bit for bit (:23,:31);
-        'exact' keeps the float64 cumulative sums.
+        'exact' keeps the float64 cumulative sums.  In 'exact' mode a row whose float64 sum is below 1 leaves a gap
+        above its last CDF value, and a uniform that falls into it raises like the reference's IndexError at :49
+        -- at 1e9+ steps even a float32 rounding error of 1e-7 is hit, so pass normalize=True with float32
+        matrices (the 3-decimal rounding of 'reference' mode closes such gaps by itself).
     device : int, optional
         CUDA device; defaults to LOCAL_RANK under torchrun, else 0.
     dist : 'auto' | bool
