@@ -26,6 +26,60 @@ __device__ __forceinline__ uint4 ldg_na(const uint4 *p) {
     return v;
 }
 
+__device__ __forceinline__ uint32_t xorshift32(uint32_t &s) {
+    s ^= s << 13; s ^= s >> 17; s ^= s << 5;
+    return s;
+}
+
+// "fast" flavour: the index costs ~6 integer instructions (xorshift32 + multiply-shift), so that the memory system
+// and not the index arithmetic is what the kernel measures.  Every lane of a gather's group computes the same index.
+template <int LPG, int ILP>
+__global__ void __launch_bounds__(1024) gather_fast_kernel(const uint4 *__restrict__ data, uint32_t n_slots, int iters, uint32_t *__restrict__ sink) {
+    const uint32_t gthread = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t group = gthread / LPG;
+    const int sub = static_cast<int>(gthread % LPG);
+    uint32_t state = group * 2654435761u + 12345u;
+    if (state == 0) state = 1;
+    uint32_t acc = 0;
+    for (int it = 0; it < iters; ++it) {
+        uint4 v[ILP];
+#pragma unroll
+        for (int k = 0; k < ILP; ++k) {
+            const uint32_t slot = static_cast<uint32_t>((static_cast<uint64_t>(xorshift32(state)) * n_slots) >> 32);
+            v[k] = ldg_na(data + static_cast<uint64_t>(slot) * LPG + sub);
+        }
+#pragma unroll
+        for (int k = 0; k < ILP; ++k) acc ^= v[k].x ^ v[k].y ^ v[k].z ^ v[k].w;
+    }
+    if (acc == 0x12345678u) sink[0] = acc;
+}
+
+// "cpasync" flavour: the same gathers, but through cp.async (LDGSTS, L1 bypass) into shared memory, ILP 16-byte copies
+// per lane in flight, then cp.async.wait_group 0 -- the data path K2 uses for its rows.
+template <int LPG, int ILP>
+__global__ void __launch_bounds__(1024) gather_cpasync_kernel(const uint4 *__restrict__ data, uint32_t n_slots, int iters, uint32_t *__restrict__ sink) {
+    extern __shared__ uint4 sbuf[];                                  // [blockDim.x * ILP]
+    const uint32_t gthread = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t group = gthread / LPG;
+    const int sub = static_cast<int>(gthread % LPG);
+    uint32_t state = group * 2654435761u + 12345u;
+    if (state == 0) state = 1;
+    uint32_t acc = 0;
+    uint4 *mine = sbuf + static_cast<size_t>(threadIdx.x) * ILP;
+    const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(mine));
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < ILP; ++k) {
+            const uint32_t slot = static_cast<uint32_t>((static_cast<uint64_t>(xorshift32(state)) * n_slots) >> 32);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + k * 16), "l"(data + static_cast<uint64_t>(slot) * LPG + sub) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        acc ^= mine[it % ILP].x;
+    }
+    if (acc == 0x12345678u) sink[0] = acc;
+}
+
 // LPG lanes (16 bytes each) read one gather of S = 16 * LPG bytes; ILP gathers in flight per lane group.
 template <int LPG, int ILP>
 __global__ void __launch_bounds__(1024) gather_kernel(const uint4 *__restrict__ data, uint64_t n_slots /* working set / S */, int iters,
@@ -102,7 +156,7 @@ int main() {
     CK(cudaMemset(data, 0x5a, max_bytes));
     printf("SMs %d\n", sms);
     printf("%-10s %6s %8s %5s %5s %10s %9s\n", "kind", "S", "set", "thr", "ilp", "G gath/s", "TB/s");
-    const size_t sets[] = {32ull << 20, 320ull << 20, 1200ull << 20, 4ull << 30};
+    const size_t sets[] = {32ull << 20, 128ull << 20, 320ull << 20, 1200ull << 20, 3800ull << 20};
 #define RUN_G(LPG, ILP, THREADS)                                                                                   \
     for (size_t ws : sets) {                                                                                        \
         const int iters = 2000 / ILP;                                                                               \
@@ -111,6 +165,27 @@ int main() {
         const double gathers = static_cast<double>(sms) * THREADS / LPG * iters * ILP;                              \
         printf("%-10s %6d %6zuMB %5d %5d %10.2f %9.3f\n", "indep", 16 * LPG, ws >> 20, THREADS, ILP, gathers / ms / 1e6, gathers * 16 * LPG / ms / 1e9); \
     }
+#define RUN_F(LPG, ILP, THREADS)                                                                                   \
+    for (size_t ws : sets) {                                                                                        \
+        const int iters = 4000 / ILP;                                                                               \
+        const uint32_t n_slots = static_cast<uint32_t>(ws / (16 * LPG));                                            \
+        const double ms = time_kernel([&] { gather_fast_kernel<LPG, ILP><<<sms, THREADS>>>(data, n_slots, iters, sink); }); \
+        const double gathers = static_cast<double>(sms) * THREADS / LPG * iters * ILP;                              \
+        printf("%-10s %6d %6zuMB %5d %5d %10.2f %9.3f\n", "fast", 16 * LPG, ws >> 20, THREADS, ILP, gathers / ms / 1e6, gathers * 16 * LPG / ms / 1e9); \
+    }
+#define RUN_A(LPG, ILP, THREADS)                                                                                   \
+    for (size_t ws : sets) {                                                                                        \
+        const int iters = 4000 / ILP;                                                                               \
+        const uint32_t n_slots = static_cast<uint32_t>(ws / (16 * LPG));                                            \
+        const size_t smem = static_cast<size_t>(THREADS) * ILP * 16;                                                \
+        CK(cudaFuncSetAttribute(gather_cpasync_kernel<LPG, ILP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
+        const double ms = time_kernel([&] { gather_cpasync_kernel<LPG, ILP><<<sms, THREADS, smem>>>(data, n_slots, iters, sink); }); \
+        const double gathers = static_cast<double>(sms) * THREADS / LPG * iters * ILP;                              \
+        printf("%-10s %6d %6zuMB %5d %5d %10.2f %9.3f\n", "cpasync", 16 * LPG, ws >> 20, THREADS, ILP, gathers / ms / 1e6, gathers * 16 * LPG / ms / 1e9); \
+    }
+    RUN_A(8, 1, 1024) RUN_A(8, 2, 1024) RUN_A(8, 4, 1024) RUN_A(8, 8, 1024) RUN_A(2, 8, 1024)
+    RUN_F(8, 1, 1024) RUN_F(8, 2, 1024)
+    RUN_F(2, 8, 1024) RUN_F(4, 8, 1024) RUN_F(8, 8, 1024) RUN_F(8, 4, 1024) RUN_F(8, 16, 512) RUN_F(16, 8, 1024)
     RUN_G(1, 8, 1024) RUN_G(2, 8, 1024) RUN_G(4, 8, 1024) RUN_G(8, 8, 1024) RUN_G(16, 8, 1024) RUN_G(32, 8, 1024)
     RUN_G(2, 4, 1024) RUN_G(8, 4, 1024) RUN_G(2, 16, 1024) RUN_G(8, 16, 1024)
 #define RUN_C(LPG, CH, THREADS)                                                                                    \
