@@ -247,9 +247,12 @@ __global__ void __launch_bounds__(1024, 1) walk_v2_kernel(const WalkParams p, co
 // much worse), two CTAs of 512..640 threads per SM (57.7-58.6 vs 57.0 G: no gain from more walkers in flight), a
 // fully unrolled 7-level search with a separate refine loop (3-6 % slower: two more dependent shared-memory round
 // trips per step), one or two extra sectors of inlined targets per row (51 / 48 vs 57 G at C4; +10 % at C3, where it
-// is now the default).  ncu (profiles/r01_ncu_walk_v2_fused_c4_exact.csv): L2 hit rate 73 %, the misses are ~20 G
-// random 32..128-byte DRAM gathers per second against a measured ceiling of 22-29 G/s for 128-byte gathers
-// (profiles/r01_gather_ceilings.log): the kernel is at the DRAM random-access rate of this graph.
+// is now the default), a lower bound on the full 12-bit code unrolled per row length (no gain), row copies through
+// registers (LDG.128 + STS.128: 35 vs 58 G).  ncu (profiles/r01_ncu_walk_v2_fused_c4_exact.csv): L2 hit rate 70 %, issue
+// slots 61 % busy, DRAM 2 TB/s.  A dependency-free kernel gathers 96 G rows/s of 128 bytes out of a 128 MB array on the
+// same GPU (profiles/r01_gather_ceilings_tuned.log); this kernel, where every gather waits for the search on the row
+// before, moves 58 G/s plus the target words and the trajectory stores.  What moves it: bytes per step, the L2 hit rate
+// (locality of the graph), the share of inlined targets (skew of the probabilities).
 constexpr int64_t kV2L1Cells = 16384;      // below: L1-allocating row copies (see walk_v2_kernel)
 
 struct V2Config {
