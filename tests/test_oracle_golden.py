@@ -135,3 +135,43 @@ def test_directionality_port_matches_reference_golden(name):
     got = np.concatenate([np.concatenate(t) for t in dp.directionality_score(ad, nbhd, "end", pos)])
     assert np.array_equal(np.isnan(got), np.isnan(want)) and np.isnan(want).any() and (~np.isnan(want)).sum() > 100
     np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-15, equal_nan=True)
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_fused_rows_port_is_self_consistent(exact):
+    """The numpy restatement of the device layout (oracle/fused_rows_port.py), decoded again: the 12-bit codes bracket
+    the oracle's CDF (exact mode) or equal 4 m (reference mode), the header fields are right, the inlined targets are the
+    row words of the most probable entries, every target word points at the block of its column."""
+    from cytopath_b200 import synth
+    from oracle import fused_rows_port as frp
+    C = sp.canonical_csr(synth.hub_graph(n=600, hub_share=0.03, seed=3))
+    cdf = cwalk.build_cdf(C, 1 if exact else 0)
+    rows, words, targets = frp.build(C, cdf, exact)
+    first = (words & np.uint32((1 << 27) - 1)).astype(np.int64)
+    units = np.concatenate([[0], np.cumsum((np.diff(C.indptr) + 3) // 4)[:-1]])
+    for r in range(C.shape[0]):
+        a, b = C.indptr[r], C.indptr[r + 1]
+        n = b - a
+        blk = rows[first[r] * 32:]
+        assert int(np.frombuffer(blk[0:4].tobytes(), dtype=np.int32)[0]) == r
+        assert int(np.frombuffer(blk[4:6].tobytes(), dtype=np.uint16)[0]) == n
+        m = int(blk[7])
+        mask = int(np.frombuffer(blk[8:16].tobytes(), dtype=np.uint64)[0])
+        assert bin(mask).count("1") == m and int(np.frombuffer(blk[16:20].tobytes(), dtype=np.uint32)[0]) == units[r]
+        hi = blk[20:20 + n].astype(np.int64)
+        lo_bytes = blk[20 + n:20 + n + (n + 1) // 2].astype(np.int64)
+        lo = np.stack([lo_bytes & 15, lo_bytes >> 4], axis=1).ravel()[:n]
+        code = (hi << 4) | lo
+        c = np.asarray(cdf[a:b], dtype=np.float64)
+        if exact:
+            assert np.all(code / 4096.0 <= c) and np.all((c < (code + 1) / 4096.0) | (code == 4095))
+        else:
+            np.testing.assert_array_equal(code, 4 * np.rint(c * 1000.0).astype(np.int64))
+        tw = words[C.indices[a:b]]
+        np.testing.assert_array_equal(targets[units[r] * 4:units[r] * 4 + n], tw)
+        inl_j = [j for j in range(min(n, 64)) if (mask >> j) & 1]
+        used = frp.used_bytes(n)
+        np.testing.assert_array_equal(np.frombuffer(blk[used:used + 4 * m].tobytes(), dtype=np.uint32), tw[inl_j])
+        if 0 < m < min(n, 64):                                       # the inlined entries are the most probable ones
+            p = C.data[a:b][:64]
+            assert p[inl_j].min() >= np.delete(p, inl_j).max()
