@@ -111,11 +111,14 @@ int cyp_walk(const cyp_graph *g, const int32_t *h_root_cells, int64_t n_roots, i
              int64_t walker_begin, int64_t n_walkers, int32_t n_transitions, uint64_t seed, uint32_t round,
              const double *h_uniforms, int32_t *h_out_seq, int64_t *n_nocrossing);
 /* Same, everything resident in HBM, enqueued on `stream`.  d_nocrossing (may be NULL) is
- * incremented atomically.  `variant` selects the step kernel: 0 = auto (TMA flavour on 16-bit
- * CDF codes when the graph allows it, CTA size from the row length), 9200 + T/32 = TMA flavour
- * on 16-bit codes with T threads per CTA, 9000 + T/32 = TMA flavour on the CDF rows as stored,
- * L*100 + U = register flavour with L lanes per walker and U 16-byte loads per lane per chunk.
- * All flavours return identical sequences. */
+ * incremented atomically.  `variant` selects the step kernel: 0 = auto (fused rows -- 12-bit CDF
+ * codes with the targets of the most probable entries inlined -- when the graph has them and 97 %
+ * of its rows fit 256 bytes, else staged 16-bit CDF codes + edge records); 9500 + T/32 = fused rows
+ * with T threads per CTA (9600 + T/32: two CTAs per SM; 9700 + T/32: slot sized for the longest
+ * row, bulk copies above 256 bytes); 9400 + T/32 = two walkers per thread on 16-bit codes;
+ * 9300 + T/32 / 9200 + T/32 = staged 16-bit codes, cooperative cp.async / per-thread bulk copies;
+ * 9000 + T/32 = the CDF rows as stored, bulk copies; L*100 + U = register flavour with L lanes per
+ * walker and U 16-byte loads per lane per chunk.  All flavours return identical sequences. */
 int cyp_walk_device(const cyp_graph *g, const int32_t *d_root_cells, int64_t n_roots, int64_t sims_per_root,
                     int64_t walker_begin, int64_t n_walkers, int32_t n_transitions, uint64_t seed,
                     uint32_t round, const double *d_uniforms, int32_t *d_out_seq,
