@@ -52,8 +52,17 @@ def host_cores():
 
 
 def make_graph(w, world):
+    """Synthetic graph of a workload (seeded: identical on every rank).  BENCH_GRAPH_CACHE=<dir> keeps the generated
+    graph on disk so that the processes of an A/B run or of a torchrun launch do not each spend a minute on the kNN search."""
+    import pickle
     from cytopath_b200 import synth
     from cytopath_b200.sampler import _canonical_csr
+    cache = os.environ.get("BENCH_GRAPH_CACHE")
+    path = os.path.join(cache, "graph_%s.pkl" % "_".join("%s%s" % (k, w[k]) for k in ("n", "k", "branches", "stems")) +
+                        ("_l%d" % w["layers"] if "layers" in w else "")) if cache else None
+    if path and os.path.exists(path):
+        with open(path, "rb") as f:
+            return pickle.load(f)
     workers = max(1, host_cores() // world)
     if w["branches"] == 0:
         g = synth.cycling_graph(n=w["n"], k=w["k"], seed=0, workers=workers)
@@ -63,6 +72,12 @@ def make_graph(w, world):
                                   n_layers=w.get("layers", 1))
         roots = np.where(np.isin(g.clusters, g.root_clusters))[0].astype(np.int32)
     C = _canonical_csr(g.T)
+    if path:
+        os.makedirs(cache, exist_ok=True)
+        tmp = "%s.%d.tmp" % (path, os.getpid())
+        with open(tmp, "wb") as f:
+            pickle.dump((g, C, roots), f, protocol=4)
+        os.replace(tmp, path)
     return g, C, roots
 
 

@@ -157,6 +157,7 @@ struct cyp_graph {
     // (q16_ok / monotone) or the blocks exceed 2^27 sectors
     int v2_ok = 0;
     int v2_max_sectors = 0;              // largest block, in sectors
+    int v2_uniform = 0;                  // at least 90 % of the blocks fill the slot: the step kernel copies whole slots without per-chunk predicates
     int v2_slot_sectors = 0;             // shared-memory slot of the step kernel: covers >= 97 % of the rows (power of two, <= 8
                                          // sectors) or, if no such size does, the largest block; longer rows are searched in HBM
     int64_t v2_sectors = 0;              // total sectors of d_rows2
@@ -174,7 +175,7 @@ struct V2Build {
     bool planned = false;
     std::vector<uint32_t> word, ebase;       // per cell: row word; start of its targets in edge4 (units of 4 words)
     int64_t sectors = 0, units = 0;
-    int max_sectors = 0, slot_sectors = 0, extra = 0;
+    int max_sectors = 0, slot_sectors = 0, extra = 0, uniform = 0;
     size_t rows_bytes = 0;
     uint32_t *d_ebase = nullptr;
     int *d_bad = nullptr;

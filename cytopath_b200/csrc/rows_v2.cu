@@ -146,6 +146,11 @@ bool v2_plan(const cyp_graph *g, const int64_t *h_row_ptr, V2Build *b) {
         if (cand >= max_sectors || covered * 100 >= n * 97) { slot = cand < max_sectors ? cand : max_sectors; break; }
     }
     b->slot_sectors = slot;
+    {   // blocks shorter than the slot: when they are rare the step kernel copies whole slots unconditionally
+        int64_t shorter = 0;
+        for (int k = 0; k < slot && k <= kV2MaxSectors; ++k) shorter += hist[k];
+        b->uniform = shorter * 10 <= n ? 1 : 0;
+    }
     b->extra = extra;
     b->sectors = sectors;
     b->units = units;
@@ -215,6 +220,7 @@ cudaError_t v2_finish(cyp_graph *g, V2Build *b, bool codes_ok) {
         g->v2_edge_units = b->units;
         g->v2_max_sectors = b->max_sectors;
         g->v2_slot_sectors = b->slot_sectors;
+        g->v2_uniform = b->uniform;
         g->device_bytes += static_cast<int64_t>(b->rows_bytes + sizeof(uint32_t) * 4 * (b->units + 1) + sizeof(uint32_t) * g->n);
         g->v2_ok = 1;
     }

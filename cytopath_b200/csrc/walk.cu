@@ -189,8 +189,8 @@ static int launch_variant(const WalkParams &p, WalkVariant v, WalkMode mode, cud
 }
 
 // long rows (C5, k = 200, 352-byte blocks): 16-bit rows + edge records through walk_tma.cu's bulk copies do 24.4 G
-// walker-steps/s, the fused rows 21.2 G with cooperative copies and 23.1 G with their own bulk flavour (few entries
-// of a 200-entry row fit the slack, so most steps still need the second gather)
+// walker-steps/s, the fused rows 21.2 G with cooperative copies and 23.1 G with a bulk flavour of their own (round 1,
+// since removed: few entries of a 200-entry row fit the slack, so most steps still need the second gather)
 bool walk_auto_is_v2(const cyp_graph *g) { return g->v2_ok && g->v2_slot_sectors * 32 <= 256; }
 
 WalkVariant pick_walk_variant(const cyp_graph *g, int variant) {
@@ -216,11 +216,6 @@ int launch_walk(const cyp_graph *g, const WalkParams &p_in, WalkMode mode, int v
     }
     WalkParams p = p_in;
     p.edge = g->d_edge;
-    if (variant >= 9400) {        // paired flavour: on request only (same throughput as the default: K2 is bound by the memory system)
-        const int rc = launch_walk_pp(g, p, mode, variant, stream);
-        if (rc != kPpNotApplicable) return rc;
-        return fail(CYP_E_INVALID, "launch_walk: the paired kernel (variant 94xx) does not apply to this graph");
-    }
     if (variant == 0 || variant >= 9000) return launch_walk_tma(g, p, mode, variant, stream);
     const WalkVariant v = pick_walk_variant(g, variant);
     if (g->cdf_mode == CYP_CDF_EXACT) return launch_variant<double>(p, v, mode, stream);
@@ -236,10 +231,6 @@ extern "C" const char *cyp_walk_variant_name(const cyp_graph *g, int variant) {
     if (!g) return "";
     if (variant >= 9500 || (variant == 0 && walk_auto_is_v2(g))) {
         const char *name = walk_v2_name(g, variant);
-        return name ? name : "not applicable";
-    }
-    if (variant >= 9400) {
-        const char *name = walk_pp_name(g, variant);
         return name ? name : "not applicable";
     }
     if (variant >= 9000 || variant == 0) return walk_tma_name(g, variant);

@@ -119,14 +119,7 @@ int launch_walk(const cyp_graph *g, const WalkParams &p, WalkMode mode, int vari
 int launch_walk_tma(const cyp_graph *g, const WalkParams &p, WalkMode mode, int variant, cudaStream_t stream);
 const char *walk_tma_name(const cyp_graph *g, int variant);
 
-// K2, paired flavour (walk_pp.cu): two walkers per thread sharing one shared-memory slot of 16-bit CDF
-// codes.  `variant` = 9400 + threads per CTA / 32; 0 = auto.  Returns kPpNotApplicable (nothing launched)
-// when the graph does not qualify; walk_pp_name returns nullptr then.
 constexpr int kNotApplicable = 1;
-constexpr int kPpNotApplicable = kNotApplicable;
-int launch_walk_pp(const cyp_graph *g, const WalkParams &p, WalkMode mode, int variant, cudaStream_t stream);
-const char *walk_pp_name(const cyp_graph *g, int variant);
-
 
 // K2, fused-row flavour (walk_v2.cu, the default where cyp_graph::v2_ok): `variant` = 9500 + threads per
 // CTA / 32; 0 = auto.  Returns kNotApplicable (nothing launched) when the graph has no fused rows.

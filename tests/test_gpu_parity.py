@@ -183,7 +183,6 @@ def test_k1b_very_long_row_is_searched_in_hbm(monkeypatch):
         want = cwalk.walk(C, cdf, np.repeat(roots, 200), 60, seed=2)
         assert (want == 0).mean() > 0.2                               # the long row is visited all the time
         np.testing.assert_array_equal(g.walk(roots, 200, 60, seed=2), want)
-        assert g.variant_name(9704) == "not applicable"               # no bulk flavour: a row word cannot hold this block's size
         g.close()
 
 
@@ -269,21 +268,6 @@ def test_k2_bit_exact_vs_oracle_all_variants(gname, mode, omode, monkeypatch):
                                          ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
             torch.cuda.synchronize()
             np.testing.assert_array_equal(out.cpu().numpy(), wnt, err_msg="%s nt=%d" % (g.variant_name(variant), n_t))
-    # paired flavour (two walkers per thread): 32 / 128 / 512 / 1024 threads per CTA; 62, 63 and 64 columns
-    for variant in (9401, 9404, 9416, 9432):
-        if g.variant_name(variant) == "not applicable":
-            assert gname in ("ragged", "hubs")                # rows that do not fit one slot of the paired kernel
-            continue
-        assert "walk_pp_kernel" in g.variant_name(variant)
-        for n_t in (nt, 62, 63):
-            wnt = want if n_t == nt else cwalk.walk(C, cdf, np.repeat(roots, sims), n_t, seed=seed, round_idx=rnd, strict=False)
-            out = torch.full((len(roots) * sims, n_t + 1), -7, dtype=torch.int32, device="cuda")
-            miss = torch.zeros(1, dtype=torch.int64, device="cuda")
-            _lib.check(L.cyp_walk_device(g.handle, d_roots.data_ptr(), len(roots), sims, 0, len(roots) * sims, n_t, seed, rnd,
-                                         None, out.data_ptr(), miss.data_ptr(), variant,
-                                         ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
-            torch.cuda.synchronize()
-            np.testing.assert_array_equal(out.cpu().numpy(), wnt, err_msg="%s nt=%d" % (g.variant_name(variant), n_t))
     # fused-row flavour (12-bit codes, inlined targets): 32 / 128 / 512 / 1024 threads per CTA; 62, 63 and 64 columns
     for variant, l1 in ((9501, "1"), (9504, "0"), (9516, "1"), (9532, "0")):        # L1-allocating and L1-bypassing row copies
         monkeypatch.setenv("CYP_V2_L1", l1)
@@ -301,13 +285,6 @@ def test_k2_bit_exact_vs_oracle_all_variants(gname, mode, omode, monkeypatch):
     assert ("walk_v2_kernel" in g.variant_name(0)) == (gname != "k200")     # the auto variant picks it, except for long rows
     if gname == "hubs":                                       # slot for the typical row; the hubs are searched in HBM
         assert "slot=128B" in g.variant_name(0) and g.layout()["max_block_bytes"] > 256
-        for variant in (9704, 9716):                          # slot for the longest row: bulk-copy flavour
-            assert "bulk" in g.variant_name(variant)
-            out = torch.full((len(roots) * sims, nt + 1), -7, dtype=torch.int32, device="cuda")
-            _lib.check(L.cyp_walk_device(g.handle, d_roots.data_ptr(), len(roots), sims, 0, len(roots) * sims, nt, seed, rnd,
-                                         None, out.data_ptr(), None, variant, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
-            torch.cuda.synchronize()
-            np.testing.assert_array_equal(out.cpu().numpy(), want, err_msg=g.variant_name(variant))
     # auto variant through the host entry point, a shard in the middle of the round
     got = g.walk(roots, sims, nt, seed=seed, round_idx=rnd, walker_begin=100, n_walkers=211, strict=False)
     np.testing.assert_array_equal(got, want[100:311])
@@ -388,7 +365,7 @@ def test_k2_q16_ambiguous_codes_are_resolved_in_float64():
     L = _lib.load()
     for mode, omode in MODES:
         g = _lib.Graph(C, mode)
-        assert "q12" in g.variant_name(0) and "q16" in g.variant_name(9204) and "q16" in g.variant_name(9404)
+        assert "q12" in g.variant_name(0) and "q16" in g.variant_name(9204)
         cdf = cwalk.build_cdf(C, omode)
         cdf64 = cdf.astype(np.float64)
         roots = np.arange(n)
@@ -402,7 +379,7 @@ def test_k2_q16_ambiguous_codes_are_resolved_in_float64():
         want = cwalk.walk(C, cdf, np.repeat(roots, 8), nt, uniforms=u, strict=False)
         d_roots = torch.tensor(roots, dtype=torch.int32, device="cuda")
         d_u = torch.tensor(u, dtype=torch.float64, device="cuda")
-        for variant in (0, 9504, 9404, 9204, 9304, 9008, 404):
+        for variant in (0, 9504, 9204, 9304, 9008, 404):
             out = torch.zeros((n * 8, nt + 1), dtype=torch.int32, device="cuda")
             miss = torch.zeros(1, dtype=torch.int64, device="cuda")
             _lib.check(L.cyp_walk_device(g.handle, d_roots.data_ptr(), n, 8, 0, n * 8, nt, 0, 0, d_u.data_ptr(), out.data_ptr(),
