@@ -25,7 +25,7 @@ EXPORTS = [
     "cyp_graph_create", "cyp_graph_create_f32", "cyp_graph_row_sum_range", "cyp_graph_destroy", "cyp_graph_info", "cyp_graph_layout", "cyp_graph_fetch_fused", "cyp_graph_fetch_cdf", "cyp_graph_build_ms",
     "cyp_power_iteration", "cyp_walk", "cyp_walk_device", "cyp_walk_variant_name", "cyp_transition_scores",
     "cyp_session_create", "cyp_session_destroy", "cyp_session_round", "cyp_session_rows",
-    "cyp_session_fetch_index", "cyp_session_fetch_rows", "cyp_session_round_records",
+    "cyp_session_fetch_index", "cyp_session_fetch_rows", "cyp_session_slot_counts", "cyp_session_round_records",
     "cyp_session_round_prune", "cyp_session_set_hash_bits", "cyp_session_set_chunk_walkers",
     "cyp_hausdorff_matrix", "cyp_directionality_scores",
 ]
@@ -36,7 +36,7 @@ class RoundStats(ctypes.Structure):
         ("n_walkers", ctypes.c_int64), ("n_pass_clusters", ctypes.c_int64), ("n_terminal", ctypes.c_int64),
         ("n_kept", ctypes.c_int64), ("n_nocrossing", ctypes.c_int64), ("store_rows", ctypes.c_int64),
         ("dedup_passes", ctypes.c_int32), ("ms_walk", ctypes.c_float), ("ms_filter", ctypes.c_float),
-        ("n_chunks", ctypes.c_int32),
+        ("n_chunks", ctypes.c_int32), ("n_replayed", ctypes.c_int64),
     ]
 
     def as_dict(self):
@@ -93,10 +93,11 @@ def load():
     L.cyp_transition_scores.argtypes = [vp, vp, i64, i32, vp]
     L.cyp_session_create.argtypes = [vp, vp, i64, vp, i32, i32, vp, i32, i32, ci, u64, P(vp)]
     L.cyp_session_destroy.argtypes = [vp]
-    L.cyp_session_round.argtypes = [vp, u32, i64, i64, i64, vp, P(RoundStats)]
+    L.cyp_session_round.argtypes = [vp, u32, i64, i64, i64, P(RoundStats)]
     L.cyp_session_rows.argtypes = [vp, P(i64)]
     L.cyp_session_fetch_index.argtypes = [vp, i64, i64, vp, vp, vp]
     L.cyp_session_fetch_rows.argtypes = [vp, vp, i64, vp]
+    L.cyp_session_slot_counts.argtypes = [vp, i64, i64, vp]
     L.cyp_session_round_records.argtypes = [vp, P(vp), P(i64)]
     L.cyp_session_round_prune.argtypes = [vp, vp, i64, P(i64)]
     L.cyp_session_set_hash_bits.argtypes = [vp, ci]
@@ -310,6 +311,7 @@ class Session:
                  n_end_slots: int, max_steps: int, unique: bool, seed: int):
         self.graph = graph
         self.max_steps = int(max_steps)
+        self.n_end_slots = int(n_end_slots)
         self._h = ctypes.c_void_p()
         roots = np.ascontiguousarray(root_cells, dtype=np.int32)
         code = np.ascontiguousarray(cell_code, dtype=np.int32)
@@ -319,13 +321,9 @@ class Session:
                                         ptr(slot), n_end_slots, max_steps, int(bool(unique)), seed,
                                         ctypes.byref(self._h)))
 
-    def round(self, round_idx: int, sims_per_root: int, walker_begin: int, walker_end: int, uniforms=None) -> dict:
+    def round(self, round_idx: int, sims_per_root: int, walker_begin: int, walker_end: int) -> dict:
         st = RoundStats()
-        if uniforms is not None:
-            uniforms = np.ascontiguousarray(uniforms, dtype=np.float64)
-            assert uniforms.shape == (walker_end - walker_begin, self.max_steps - 1)
-        rc = load().cyp_session_round(self._h, round_idx, sims_per_root, walker_begin, walker_end, ptr(uniforms),
-                                      ctypes.byref(st))
+        rc = load().cyp_session_round(self._h, round_idx, sims_per_root, walker_begin, walker_end, ctypes.byref(st))
         if rc == E_NOCROSSING:
             raise IndexError("index 0 is out of bounds for axis 0 with size 0")
         check(rc)
@@ -345,6 +343,14 @@ class Session:
         if n_rows:
             check(load().cyp_session_fetch_index(self._h, row_begin, n_rows, ptr(rnd), ptr(walker), ptr(slot)))
         return rnd, walker, slot
+
+    def slot_counts(self, row_begin: int = 0, n_rows: int | None = None) -> np.ndarray:
+        """How many of the kept rows [row_begin, row_begin + n_rows) end on each end-point slot."""
+        if n_rows is None:
+            n_rows = self.rows() - row_begin
+        out = np.zeros(self.n_end_slots, dtype=np.int64)
+        check(load().cyp_session_slot_counts(self._h, row_begin, n_rows, ptr(out)))
+        return out
 
     def fetch_rows(self, rows) -> np.ndarray:
         rows = np.ascontiguousarray(rows, dtype=np.int64)

@@ -66,14 +66,23 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const WalkParams p) 
     const int nt = p.nt;
 
     for (int64_t w = (static_cast<int64_t>(blockIdx.x) * kWalkThreads + threadIdx.x) / G; w < p.n_walkers; w += n_groups) {
-        const uint64_t gw = static_cast<uint64_t>(p.walker_begin + w);
-        int32_t cur = p.roots[gw / static_cast<uint64_t>(p.sims_per_root)];
+        uint64_t gw = static_cast<uint64_t>(p.walker_begin + w);
+        uint32_t round = p.round;
+        int32_t cur;
+        if (p.replay) {
+            const ReplayItem it = p.replay[w];
+            gw = static_cast<uint64_t>(it.walker);
+            round = it.round;
+            cur = it.root;
+        } else {
+            cur = p.roots[gw / static_cast<uint64_t>(p.sims_per_root)];
+        }
         RowInfo ri = rows[cur];
-        int32_t *__restrict__ out_row = p.out_seq + w * p.ld;
+        int32_t *__restrict__ out_row = p.out_seq ? p.out_seq + w * p.ld : nullptr;
         const double *__restrict__ urow = p.uniforms ? p.uniforms + w * static_cast<int64_t>(nt) : nullptr;
 
         int32_t mine = cur;                               // lane (c % G) holds column c until the group flushes
-        if (G == 1) out_row[0] = cur;
+        if (G == 1 && out_row) out_row[0] = cur;
         WalkerDigest<MODE> dg;
         dg.visit(cur, WalkerDigest<MODE>::MASKW > 0 ? p.code8[cur] : 0u);
         unsigned misses = 0;
@@ -86,7 +95,7 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const WalkParams p) 
                 u = urow[t];
             } else {
                 const int r = t & (2 * G - 1);
-                if (r == 0) walker_uniform_pair(p.seed, p.round, gw, static_cast<uint32_t>((t >> 1) + gl), u_even, u_odd);
+                if (r == 0) walker_uniform_pair(p.seed, round, gw, static_cast<uint32_t>((t >> 1) + gl), u_even, u_odd);
                 const double mine_u = (r & 1) ? u_odd : u_even;
                 u = (G == 1) ? mine_u : __shfl_sync(gmask, mine_u, r >> 1, G);
             }
@@ -129,11 +138,11 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const WalkParams p) 
             if ((c & (G - 1)) == gl) mine = cur;
             if ((c & (G - 1)) == G - 1 || c == nt) {
                 const int cbase = c & ~(G - 1);
-                if (cbase + gl <= c) out_row[cbase + gl] = mine;
+                if (out_row && cbase + gl <= c) out_row[cbase + gl] = mine;
             }
             dg.visit(cur, code);
         }
-        if (nt == 0 && G > 1 && gl == 0) out_row[0] = mine;
+        if (nt == 0 && G > 1 && gl == 0 && out_row) out_row[0] = mine;
         if (gl == 0) {
             if (misses && p.nocross) atomicAdd(p.nocross, static_cast<unsigned long long>(misses));
             dg.finish(p, w, cur);

@@ -5,6 +5,15 @@
 
 namespace cyp {
 
+// A walker named explicitly (instead of by its position in a contiguous range of one round): what the replay
+// launches of session.cu pass.  Because the uniform stream is keyed by (walker, step, round), walking the same
+// item again reproduces the same trajectory: kept sequences are stored as these 16 bytes, not as rows.
+struct ReplayItem {
+    int64_t walker;     // global walker id of its round
+    uint32_t round;
+    int32_t root;       // root cell (= root_cells[walker / sims_per_root] of that round)
+};
+
 struct WalkParams {
     const RowInfo *rows;            // [n_cells] row descriptor (read for the root cell only)
     const void *cdf;                // float / double, sector-aligned rows
@@ -17,7 +26,8 @@ struct WalkParams {
     uint32_t round;
     uint64_t seed;
     const double *uniforms;         // [n_walkers, nt] or nullptr -> Philox stream
-    int32_t *out_seq;               // [n_walkers, ld]
+    const ReplayItem *replay = nullptr;   // [n_walkers] or nullptr: walker w is walker_begin + w of round `round`, starting at roots[.. / sims_per_root]
+    int32_t *out_seq;               // [n_walkers, ld]; nullptr: no trajectory is written (filter modes: hash + slot only)
     int64_t ld;                     // row stride of out_seq in elements (>= nt + 1)
     unsigned long long *nocross;    // may be nullptr
     // filter outputs, only read/written by the FILTER modes

@@ -175,14 +175,25 @@ __global__ void __launch_bounds__(1024, 1) walk_tma_kernel(const WalkParams p, c
     for (int64_t wbase = static_cast<int64_t>(blockIdx.x) * nthreads + warp * 32; wbase < p.n_walkers; wbase += stride) {
         const int64_t w = wbase + lane;
         const bool active = w < p.n_walkers;
-        const uint64_t gw = static_cast<uint64_t>(p.walker_begin + w);
-        int32_t cur = active ? p.roots[gw / static_cast<uint64_t>(p.sims_per_root)] : 0;
+        uint64_t gw = static_cast<uint64_t>(p.walker_begin + w);
+        uint32_t round = p.round;
+        int32_t cur = 0;
+        if (active) {
+            if (p.replay) {
+                const ReplayItem it = p.replay[w];
+                gw = static_cast<uint64_t>(it.walker);
+                round = it.round;
+                cur = it.root;
+            } else {
+                cur = p.roots[gw / static_cast<uint64_t>(p.sims_per_root)];
+            }
+        }
         RowInfo ri{0u, 0u};
         if (active) ri = rows[cur];
-        int32_t *__restrict__ out_row = p.out_seq + (active ? w : 0) * p.ld;
+        int32_t *__restrict__ out_row = (p.out_seq && active) ? p.out_seq + w * p.ld : nullptr;
         const double *__restrict__ urow = (p.uniforms && active) ? p.uniforms + w * static_cast<int64_t>(nt) : nullptr;
         int32_t b0 = cur, b1 = 0, b2 = 0, b3 = 0;         // columns 4q .. 4q+3 of the trajectory
-        if (active && (nt == 0 || !vec_store)) out_row[0] = cur;
+        if (out_row && (nt == 0 || !vec_store)) out_row[0] = cur;
         WalkerDigest<MODE> dg;
         if (active) dg.visit(cur, WalkerDigest<MODE>::MASKW > 0 ? p.code8[cur] : 0u);
         unsigned misses = 0;
@@ -193,7 +204,7 @@ __global__ void __launch_bounds__(1024, 1) walk_tma_kernel(const WalkParams p, c
             if (urow) {
                 u = urow[t];
             } else {
-                if ((t & 1) == 0) walker_uniform_pair(p.seed, p.round, gw, static_cast<uint32_t>(t >> 1), u_even, u_odd);
+                if ((t & 1) == 0) walker_uniform_pair(p.seed, round, gw, static_cast<uint32_t>(t >> 1), u_even, u_odd);
                 u = (t & 1) ? u_odd : u_even;
             }
             const int len = static_cast<int>(ri.len);
@@ -249,7 +260,9 @@ __global__ void __launch_bounds__(1024, 1) walk_tma_kernel(const WalkParams p, c
                     if constexpr (WalkerDigest<MODE>::MASKW > 0) code = p.code8[cur];
                 }
                 const int c = t + 1;
-                if (vec_store) {
+                if (!out_row) {
+                    // no trajectory buffer: digest only
+                } else if (vec_store) {
                     const int q = c & 3;
                     if (q == 0) b0 = cur; else if (q == 1) b1 = cur; else if (q == 2) b2 = cur; else b3 = cur;
                     if (q == 3) {

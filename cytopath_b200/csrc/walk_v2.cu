@@ -23,8 +23,7 @@ int launch_walk_v2(const cyp_graph *g, const WalkParams &p_in, WalkMode mode, in
     p.rows2 = g->d_rows2;
     p.edge4 = g->d_edge4;
     p.word = g->d_word;
-    p.l1_rows = g->n < kV2L1Cells ? 1 : 0;
-    if (const char *e = getenv("CYP_V2_L1")) p.l1_rows = atoi(e);
+    p.l1_rows = c.l1_rows;
     return g->cdf_mode == CYP_CDF_EXACT ? launch_walk_v2_exact(p, mode, c, sm_count, stream)
                                         : launch_walk_v2_ref(p, mode, c, sm_count, stream);
 }
@@ -34,8 +33,8 @@ const char *walk_v2_name(const cyp_graph *g, int variant) {
     V2Config c;
     if (!v2_config(g, variant, 0, 0, &c)) return nullptr;
     static const char *flavor[] = {"uniform rows", "ragged rows", "ragged rows + long rows in HBM"};
-    snprintf(buf, sizeof(buf), "walk_v2_kernel<%s,fused rows,threads<=%d,slot=%dB rotated,%s%s>", g->cdf_mode == CYP_CDF_EXACT ? "q12/f64" : "q12/f32",
-             c.threads, 16 * c.cpr, flavor[c.flavor], g->n < kV2L1Cells ? ",L1 rows" : "");
+    snprintf(buf, sizeof(buf), "walk_v2_kernel<%s,fused rows,threads<=%d x %d walker%s%s,slot=%dB rotated,%s%s>", g->cdf_mode == CYP_CDF_EXACT ? "q12/f64" : "q12/f32",
+             c.threads, c.nw, c.nw > 1 ? "s" : "", c.ctas > 1 ? ",2 CTAs/SM" : "", 16 * c.cpr, flavor[c.flavor], c.l1_rows ? ",L1 rows" : "");
     return buf;
 }
 

@@ -85,9 +85,27 @@ using IC = std::integral_constant<int, N>;
 // same L2 lines at once and the L2 slices serialise them: 13.7 G walker-steps/s at 3,696 cells against 85 G at
 // 20k+ cells.  With L1 allocation the hot rows are served by the SM's own L1: 80 G at 3,696 .. 10,000 cells
 // (profiles/r01_small_graphs.log); above ~16k cells the L1-bypassing copies are the faster ones.
-template <int CPR, int CDFM, int MODE, int FLAVOR, bool L1ROWS>
-__global__ void __launch_bounds__(1024, 1) walk_v2_kernel(const WalkParams p, const int log_n /* 2^log_n >= longest row */) {
+// NW = walkers per thread, each with its own slot (slot index = thread * NW + k).  With NW = 2 the warp alternates
+// between its two sets of 32 walkers: while it searches the rows of one set, the copies of the other set are in
+// flight (cp.async groups, wait_group NW - 1), so a warp-step no longer waits for the slowest of its 32 row copies
+// AND the slowest of its target gathers with nothing else to do.
+template <int MODE>
+struct V2Walker {
+    uint32_t word = 0u;          // row word of the row being copied / searched
+    bool active = false;
+    int32_t *out_row = nullptr;
+    const double *urow = nullptr;
+    int32_t b0 = 0, b1 = 0, b2 = 0, cell = 0;
+    uint32_t gw_lo = 0u, gw_hi = 0u, round = 0u;
+    int64_t w = 0;
+    uint4 x = make_uint4(0u, 0u, 0u, 0u);     // Philox output for transitions 2k (x, y) and 2k + 1 (z, w)
+    WalkerDigest<MODE> dg;
+};
+
+template <int CPR, int CDFM, int MODE, int FLAVOR, bool L1ROWS, int NW, int CTAS = 1>
+__global__ void __launch_bounds__(CTAS == 2 ? 640 : (NW == 1 ? 1024 : 896), CTAS) walk_v2_kernel(const WalkParams p, const int log_n /* 2^log_n >= longest row */) {
     using namespace v2;
+    static_assert(NW == 1 || NW == 2, "one or two walkers per thread");
     constexpr int SLOT = 16 * CPR;
     constexpr uint32_t SMASK = SLOT - 1;
     constexpr int LPB = CPR >= 8 ? 1 : 8 / CPR;            // lanes whose slots share one 128-byte bank row
@@ -95,199 +113,235 @@ __global__ void __launch_bounds__(1024, 1) walk_v2_kernel(const WalkParams p, co
     extern __shared__ __align__(256) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int nthreads = blockDim.x;
-    const uint32_t slot_sm = smem_u32(smem_raw) + static_cast<uint32_t>(threadIdx.x) * SLOT;     // SLOT-aligned: OR-able
+    const uint32_t slot_sm = smem_u32(smem_raw) + static_cast<uint32_t>(threadIdx.x) * (NW * SLOT);     // SLOT-aligned: OR-able
     const uint32_t rot16 = static_cast<uint32_t>((lane / LPB) & (CPR - 1)) * 16u;
-    auto at = [&](uint32_t x) { return slot_sm | ((x + rot16) & SMASK); };        // address of row byte x of this thread's slot
-    const uint32_t hdr_addr = at(0);
     const uint32_t r20 = kV2Header + rot16;
 
     // cooperative copy geometry: lane = (group, c); instruction i serves the row of lane gb + i: this lane fetches
-    // logical chunk c of that row (source = row + 16 c: one 64-bit multiply-add) and writes it to the chunk
-    // (c + rot_i) % CPR of that row's slot (CPR precomputed shared-memory addresses)
+    // logical chunk c of that row (source = row + 16 c) and writes it to the chunk (c + rot_i) % CPR of that row's
+    // slot (CPR precomputed shared-memory addresses; slot k of a thread is k * SLOT further)
     const int c = lane & (CPR - 1);
     const int gb = lane & ~(CPR - 1);
     const unsigned char *const src_c = p.rows2 + c * 16;
     uint32_t dst[CPR];
 #pragma unroll
     for (int i = 0; i < CPR; ++i)
-        dst[i] = slot_sm + static_cast<uint32_t>(i - c) * SLOT + (static_cast<uint32_t>(c + (((gb + i) / LPB) & (CPR - 1))) * 16u & SMASK);
+        dst[i] = slot_sm + static_cast<uint32_t>(i - c) * (NW * SLOT) + (static_cast<uint32_t>(c + (((gb + i) / LPB) & (CPR - 1))) * 16u & SMASK);
 
     const int nt = p.nt;
     const bool vec_store = (p.ld & 3) == 0;
     const bool native = p.uniforms == nullptr;
-    const int64_t stride = static_cast<int64_t>(gridDim.x) * nthreads;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * nthreads * NW;
     const int depth = log_n < DEPTH ? log_n : DEPTH;
+    const uint2 pkey = make_uint2(static_cast<uint32_t>(p.seed), static_cast<uint32_t>(p.seed >> 32));
 
-    auto issue_copy = [&](uint32_t word) {
+    auto issue_copy = [&](uint32_t word, auto K) {
+        constexpr uint32_t koff = decltype(K)::value * SLOT;
         if constexpr (FLAVOR == kUniform) {
             const uint32_t woff = word << 5;                           // byte offset of the block (the shift drops the sector count)
 #pragma unroll
-            for (int i = 0; i < CPR; ++i) cp_async16<L1ROWS>(dst[i], src_c + __shfl_sync(0xffffffffu, woff, i, CPR));
+            for (int i = 0; i < CPR; ++i) cp_async16<L1ROWS>(dst[i] + koff, src_c + __shfl_sync(0xffffffffu, woff, i, CPR));
         } else {
 #pragma unroll
             for (int i = 0; i < CPR; ++i) {
                 const uint32_t wd = __shfl_sync(0xffffffffu, word, i, CPR);
                 if ((wd >> kWordOffBits) > static_cast<uint32_t>(c >> 1))          // the block has this sector
-                    cp_async16<L1ROWS>(dst[i], src_c + (wd << 5));
+                    cp_async16<L1ROWS>(dst[i] + koff, src_c + (wd << 5));
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    for (int64_t wbase = static_cast<int64_t>(blockIdx.x) * nthreads + (threadIdx.x & ~31); wbase < p.n_walkers; wbase += stride) {
-        const int64_t w = wbase + lane;
-        const bool active = w < p.n_walkers;
-        const uint64_t gw = static_cast<uint64_t>(p.walker_begin + w);
-        uint32_t word = 0u;                               // inactive lanes copy the first block (uniform) / nothing (ragged)
-        if (active) word = p.word[p.roots[gw / static_cast<uint64_t>(p.sims_per_root)]];
-        int32_t *__restrict__ out_row = p.out_seq + (active ? w : 0) * p.ld;
-        const double *__restrict__ urow = (!native && active) ? p.uniforms + w * static_cast<int64_t>(nt) : nullptr;
-        int32_t b0 = 0, b1 = 0, b2 = 0;
-        int32_t cell = 0;
-        WalkerDigest<MODE> dg;
-        uint4 x = make_uint4(0u, 0u, 0u, 0u);             // Philox output for transitions 2k (x, y) and 2k + 1 (z, w)
-        const uint2 pkey = make_uint2(static_cast<uint32_t>(p.seed), static_cast<uint32_t>(p.seed >> 32));
-        const uint32_t gw_lo = static_cast<uint32_t>(gw), gw_hi = static_cast<uint32_t>(gw >> 32);
-        issue_copy(word);
-        if (native && nt > 0) x = philox4x32_10(make_uint4(gw_lo, gw_hi, 0u, p.round), pkey);
-        int t = 0;
-
-        // one step; Q = t % 4 is static.  Returns true after the last column has been written.
-        auto step = [&](auto Q) -> bool {
-            constexpr int q = decltype(Q)::value;
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            __syncwarp();
-            uint32_t next = word;
-            if (active) {
-                const uint4 h = lds128(hdr_addr);                            // cell | len, label, m | inline mask
-                cell = static_cast<int32_t>(h.x);
-                const int len = static_cast<int>(h.y & 0xffffu);
-                // ---- trajectory column t, hash, label bitmap
-                if (vec_store) {
-                    if constexpr (q == 3) {
-                        *reinterpret_cast<int4 *>(out_row + (t - 3)) = make_int4(b0, b1, b2, cell);
-                    } else {
-                        if constexpr (q == 0) b0 = cell; else if constexpr (q == 1) b1 = cell; else b2 = cell;
-                        if (t == nt) {
-                            out_row[t - q] = b0;
-                            if constexpr (q >= 1) out_row[t - q + 1] = b1;
-                            if constexpr (q >= 2) out_row[t - q + 2] = b2;
-                        }
-                    }
-                } else {
-                    out_row[t] = cell;
-                }
-                dg.visit(cell, (h.y >> 16) & 0xffu);
-                if (t < nt) {
-                    // ---- the key of this transition's uniform
-                    const uint32_t ua = (q & 1) ? x.z : x.x, ub = (q & 1) ? x.w : x.y;
-                    double u = 0.0;
-                    int key, t_def = 0;
-                    if constexpr (CDFM == kModeExact) {
-                        // t_def = ceil(u * 4096): q >= t_def <=> u <= q / 4096;  key = t_def - 1: q >= key <=> u <= (q + 1) / 4096
-                        if (native) {
-                            // u = mant * 2^-53, mant = (ua >> 5) * 2^26 + (ub >> 6): ceil(mant / 2^41) in integers
-                            t_def = static_cast<int>(ua >> 20) + ((((ua & 0xFFFE0u) | (ub >> 6)) != 0u) ? 1 : 0);
-                        } else {
-                            u = urow[t];
-                            t_def = static_cast<int>(ceil(u * 4096.0));
-                        }
-                        key = t_def - 1;
-                    } else {
-                        u = native ? bits_to_unit_double(ua, ub) : urow[t];
-                        key = static_cast<int>(ceil(u * 1000.0));               // smallest integer m with u <= (double)fl32(m / 1000)
-                        while (key > 0 && u <= static_cast<double>(__fdiv_rn(static_cast<float>(key - 1), 1000.0f))) --key;
-                        while (u > static_cast<double>(__fdiv_rn(static_cast<float>(key), 1000.0f))) ++key;
-                        key <<= 2;                                               // the codes are 4 m (rows_v2.cu): 8 significant bits in the upper plane
-                    }
-                    const int key_hi = key >> 4;
-                    int j = 0;
-                    bool in_slot = true;
-                    if constexpr (FLAVOR == kOversize) in_slot = (word >> kWordOffBits) * 32u <= static_cast<uint32_t>(SLOT);
-                    if (in_slot) {
-                        // ---- first crossing in the slot: lower bound on the upper plane, then the 12-bit codes
-#pragma unroll
-                        for (int lv = DEPTH - 1; lv >= 0; --lv) {
-                            if (lv >= DEPTH - 2 && lv >= depth) continue;                    // uniform: the top levels only exist for the longest rows a slot holds
-                            const int probe = j + (1 << lv) - 1;
-                            if (probe < len && lds8(slot_sm | ((static_cast<uint32_t>(probe) + r20) & SMASK)) < key_hi) j += 1 << lv;
-                        }
-                        const uint32_t lo0 = r20 + static_cast<uint32_t>(len);
-                        auto code_at = [&](int jj) {
-                            const int hi = lds8(slot_sm | ((static_cast<uint32_t>(jj) + r20) & SMASK));
-                            const int lo = lds8(slot_sm | ((static_cast<uint32_t>(jj >> 1) + lo0) & SMASK));
-                            return (hi << 4) | ((lo >> ((jj & 1) * 4)) & 15);
-                        };
-                        if constexpr (CDFM == kModeExact) {
-                            while (j < len) {
-                                const int code = code_at(j);
-                                if (code >= t_def) break;                        // certain crossing
-                                if (code == key) {                               // undecided by the code: float64 compare (:49)
-                                    if (native) u = bits_to_unit_double(ua, ub);
-                                    const RowInfo ri = p.rows[cell];
-                                    if (u <= __ldg(static_cast<const double *>(p.cdf) + static_cast<int64_t>(ri.off_units) * kRowAlign + j)) break;
-                                }
-                                ++j;
-                            }
-                        } else {
-                            while (j < len && code_at(j) < key) ++j;
-                        }
-                        // ---- next row word
-                        if (j < len) {
-                            const uint32_t mword = j < 32 ? h.z : h.w;          // inline mask, the half that holds bit j
-                            const uint32_t below = j < 32 ? 0u : static_cast<uint32_t>(__popc(h.z));
-                            if (j < 64 && ((mword >> (j & 31)) & 1u)) {
-                                const uint32_t rank = below + static_cast<uint32_t>(__popc(mword & ((1u << (j & 31)) - 1u)));
-                                next = lds32(at(static_cast<uint32_t>(v2_used_bytes(len)) + 4u * rank));
-                            } else {
-                                next = ldg_word(p.edge4 + static_cast<size_t>(lds32(at(16))) * 4 + j);
-                            }
-                        }
-                    } else {
-                        // a block longer than the slot (a few long rows of a ragged graph: the slot is sized for the typical
-                        // row) is searched where it lies, in global memory; its header did fit
-                        const unsigned char *blk = p.rows2 + (static_cast<size_t>(word & kWordOffMask) << 5);
-                        const unsigned char *hi = blk + kV2Header;
-                        const unsigned char *lo = hi + len;
-                        for (int s = 1 << (log_n - 1); s >= 1; s >>= 1) {
-                            const int probe = j + s - 1;
-                            if (probe < len && static_cast<int>(hi[probe]) < key_hi) j += s;
-                        }
-                        auto code_at = [&](int jj) { return (static_cast<int>(hi[jj]) << 4) | ((static_cast<int>(lo[jj >> 1]) >> ((jj & 1) * 4)) & 15); };
-                        if constexpr (CDFM == kModeExact) {
-                            while (j < len) {
-                                const int code = code_at(j);
-                                if (code >= t_def) break;
-                                if (code == key) {
-                                    if (native) u = bits_to_unit_double(ua, ub);
-                                    const RowInfo ri = p.rows[cell];
-                                    if (u <= __ldg(static_cast<const double *>(p.cdf) + static_cast<int64_t>(ri.off_units) * kRowAlign + j)) break;
-                                }
-                                ++j;
-                            }
-                        } else {
-                            while (j < len && code_at(j) < key) ++j;
-                        }
-                        if (j < len) {
-                            const unsigned long long mask = (static_cast<unsigned long long>(h.w) << 32) | h.z;
-                            if (j < 64 && ((mask >> j) & 1ull)) {
-                                const int rank = __popcll(mask & ((1ull << j) - 1ull));
-                                next = *reinterpret_cast<const uint32_t *>(blk + v2_used_bytes(len) + 4 * rank);
-                            } else {
-                                next = ldg_word(p.edge4 + static_cast<size_t>(*reinterpret_cast<const uint32_t *>(blk + 16)) * 4 + j);
-                            }
-                        }
-                    }
-                    if (j >= len && p.nocross) atomicAdd(p.nocross, 1ull);       // stays where it is (reference: IndexError at :49)
+    // One transition of one walker whose row is in slot K: writes trajectory column t, returns the next row word.
+    auto process = [&](V2Walker<MODE> &s, auto K, auto Q, const int t) -> uint32_t {
+        constexpr int q = decltype(Q)::value;
+        const uint32_t slot_k = slot_sm + decltype(K)::value * SLOT;
+        auto at = [&](uint32_t x) { return slot_k | ((x + rot16) & SMASK); };        // address of row byte x of this slot
+        uint32_t next = s.word;
+        if (!s.active) return next;
+        const uint4 h = lds128(at(0));                                // cell | len, label, m | inline mask
+        s.cell = static_cast<int32_t>(h.x);
+        const int len = static_cast<int>(h.y & 0xffffu);
+        // ---- trajectory column t, hash, label bitmap
+        if (s.out_row == nullptr) {
+            // filter modes without a trajectory buffer: the digest is all that is kept
+        } else if (vec_store) {
+            if constexpr (q == 3) {
+                *reinterpret_cast<int4 *>(s.out_row + (t - 3)) = make_int4(s.b0, s.b1, s.b2, s.cell);
+            } else {
+                if constexpr (q == 0) s.b0 = s.cell; else if constexpr (q == 1) s.b1 = s.cell; else s.b2 = s.cell;
+                if (t == nt) {
+                    s.out_row[t - q] = s.b0;
+                    if constexpr (q >= 1) s.out_row[t - q + 1] = s.b1;
+                    if constexpr (q >= 2) s.out_row[t - q + 2] = s.b2;
                 }
             }
-            if (t == nt) return true;
-            word = next;
+        } else {
+            s.out_row[t] = s.cell;
+        }
+        s.dg.visit(s.cell, (h.y >> 16) & 0xffu);
+        if (t >= nt) return next;
+        // ---- the key of this transition's uniform
+        const uint32_t ua = (q & 1) ? s.x.z : s.x.x, ub = (q & 1) ? s.x.w : s.x.y;
+        double u = 0.0;
+        int key, t_def = 0;
+        if constexpr (CDFM == kModeExact) {
+            // t_def = ceil(u * 4096): code >= t_def <=> u <= code / 4096;  key = t_def - 1: code >= key <=> u <= (code + 1) / 4096
+            if (native) {
+                // u = mant * 2^-53, mant = (ua >> 5) * 2^26 + (ub >> 6): ceil(mant / 2^41) in integers
+                t_def = static_cast<int>(ua >> 20) + ((((ua & 0xFFFE0u) | (ub >> 6)) != 0u) ? 1 : 0);
+            } else {
+                u = s.urow[t];
+                t_def = static_cast<int>(ceil(u * 4096.0));
+            }
+            key = t_def - 1;
+        } else {
+            u = native ? bits_to_unit_double(ua, ub) : s.urow[t];
+            key = static_cast<int>(ceil(u * 1000.0));               // smallest integer m with u <= (double)fl32(m / 1000)
+            while (key > 0 && u <= static_cast<double>(__fdiv_rn(static_cast<float>(key - 1), 1000.0f))) --key;
+            while (u > static_cast<double>(__fdiv_rn(static_cast<float>(key), 1000.0f))) ++key;
+            key <<= 2;                                               // the codes are 4 m (rows_v2.cu): 8 significant bits in the upper plane
+        }
+        const int key_hi = key >> 4;
+        auto settle = [&](int j) {                                   // undecided by the code: the float64 compare of :49
+            if (native) u = bits_to_unit_double(ua, ub);
+            const RowInfo ri = p.rows[s.cell];
+            return u <= __ldg(static_cast<const double *>(p.cdf) + static_cast<int64_t>(ri.off_units) * kRowAlign + j);
+        };
+        int j = 0;
+        bool in_slot = true;
+        if constexpr (FLAVOR == kOversize) in_slot = (s.word >> kWordOffBits) * 32u <= static_cast<uint32_t>(SLOT);
+        if (in_slot) {
+            // ---- first crossing in the slot: lower bound on the upper plane, then the 12-bit codes
+#pragma unroll
+            for (int lv = DEPTH - 1; lv >= 0; --lv) {
+                if (lv >= DEPTH - 2 && lv >= depth) continue;        // uniform: the top levels only exist for the longest rows a slot holds
+                const int probe = j + (1 << lv) - 1;
+                if (probe < len && lds8(slot_k | ((static_cast<uint32_t>(probe) + r20) & SMASK)) < key_hi) j += 1 << lv;
+            }
+            const uint32_t lo0 = r20 + static_cast<uint32_t>(len);
+            auto code_at = [&](int jj) {
+                const int hi = lds8(slot_k | ((static_cast<uint32_t>(jj) + r20) & SMASK));
+                const int lo = lds8(slot_k | ((static_cast<uint32_t>(jj >> 1) + lo0) & SMASK));
+                return (hi << 4) | ((lo >> ((jj & 1) * 4)) & 15);
+            };
+            if constexpr (CDFM == kModeExact) {
+                while (j < len) {
+                    const int code = code_at(j);
+                    if (code >= t_def) break;                        // certain crossing
+                    if (code == key && settle(j)) break;
+                    ++j;
+                }
+            } else {
+                while (j < len && code_at(j) < key) ++j;
+            }
+            // ---- next row word
+            if (j < len) {
+                const uint32_t mword = j < 32 ? h.z : h.w;          // inline mask, the half that holds bit j
+                const uint32_t below = j < 32 ? 0u : static_cast<uint32_t>(__popc(h.z));
+                if (j < 64 && ((mword >> (j & 31)) & 1u)) {
+                    const uint32_t rank = below + static_cast<uint32_t>(__popc(mword & ((1u << (j & 31)) - 1u)));
+                    next = lds32(at(static_cast<uint32_t>(v2_used_bytes(len)) + 4u * rank));
+                } else {
+                    next = ldg_word(p.edge4 + static_cast<size_t>(lds32(at(16))) * 4 + j);
+                }
+            }
+        } else {
+            // a block longer than the slot (a few long rows of a ragged graph: the slot is sized for the typical
+            // row) is searched where it lies, in global memory; its header did fit
+            const unsigned char *blk = p.rows2 + (static_cast<size_t>(s.word & kWordOffMask) << 5);
+            const unsigned char *hi = blk + kV2Header;
+            const unsigned char *lo = hi + len;
+            for (int st = 1 << (log_n - 1); st >= 1; st >>= 1) {
+                const int probe = j + st - 1;
+                if (probe < len && static_cast<int>(hi[probe]) < key_hi) j += st;
+            }
+            auto code_at = [&](int jj) { return (static_cast<int>(hi[jj]) << 4) | ((static_cast<int>(lo[jj >> 1]) >> ((jj & 1) * 4)) & 15); };
+            if constexpr (CDFM == kModeExact) {
+                while (j < len) {
+                    const int code = code_at(j);
+                    if (code >= t_def) break;
+                    if (code == key && settle(j)) break;
+                    ++j;
+                }
+            } else {
+                while (j < len && code_at(j) < key) ++j;
+            }
+            if (j < len) {
+                const unsigned long long mask = (static_cast<unsigned long long>(h.w) << 32) | h.z;
+                if (j < 64 && ((mask >> j) & 1ull)) {
+                    const int rank = __popcll(mask & ((1ull << j) - 1ull));
+                    next = *reinterpret_cast<const uint32_t *>(blk + v2_used_bytes(len) + 4 * rank);
+                } else {
+                    next = ldg_word(p.edge4 + static_cast<size_t>(*reinterpret_cast<const uint32_t *>(blk + 16)) * 4 + j);
+                }
+            }
+        }
+        if (j >= len && p.nocross) atomicAdd(p.nocross, 1ull);       // stays where it is (reference: IndexError at :49)
+        return next;
+    };
+
+    // a warp's batch: NW sets of 32 consecutive walkers
+    for (int64_t wbase = (static_cast<int64_t>(blockIdx.x) * nthreads + (threadIdx.x & ~31)) * NW; wbase < p.n_walkers; wbase += stride) {
+        V2Walker<MODE> s[NW];
+#pragma unroll
+        for (int k = 0; k < NW; ++k) {
+            s[k].w = wbase + k * 32 + lane;
+            s[k].active = s[k].w < p.n_walkers;
+            uint64_t gw = static_cast<uint64_t>(p.walker_begin + s[k].w);
+            s[k].round = p.round;
+            if (s[k].active) {                                        // else word = 0: the first block / nothing is copied
+                int32_t root;
+                if (p.replay) {
+                    const ReplayItem it = p.replay[s[k].w];
+                    gw = static_cast<uint64_t>(it.walker);
+                    s[k].round = it.round;
+                    root = it.root;
+                } else {
+                    root = p.roots[gw / static_cast<uint64_t>(p.sims_per_root)];
+                }
+                s[k].word = p.word[root];
+            }
+            s[k].gw_lo = static_cast<uint32_t>(gw);
+            s[k].gw_hi = static_cast<uint32_t>(gw >> 32);
+            s[k].out_row = (p.out_seq && s[k].active) ? p.out_seq + s[k].w * p.ld : nullptr;
+            s[k].urow = (!native && s[k].active) ? p.uniforms + s[k].w * static_cast<int64_t>(nt) : nullptr;
+        }
+        issue_copy(s[0].word, IC<0>{});
+        if constexpr (NW > 1) issue_copy(s[NW - 1].word, IC<NW - 1>{});
+        if (native && nt > 0) {
+#pragma unroll
+            for (int k = 0; k < NW; ++k) s[k].x = philox4x32_10(make_uint4(s[k].gw_lo, s[k].gw_hi, 0u, s[k].round), pkey);
+        }
+        int t = 0;
+
+        // one step of all NW sets; Q = t % 4 is static.  Returns true after the last column has been written.
+        auto step = [&](auto Q) -> bool {
+            constexpr int q = decltype(Q)::value;
+            const bool last = t == nt;
+            auto one = [&](auto K) {
+                constexpr int k = decltype(K)::value;
+                if (NW == 1 || last) asm volatile("cp.async.wait_group 0;" ::: "memory");
+                else asm volatile("cp.async.wait_group %0;" ::"n"(NW - 1) : "memory");          // the older group: this set's copy
+                __syncwarp();
+                const uint32_t next = process(s[k], K, Q, t);
+                if (!last) {
+                    s[k].word = next;
+                    __syncwarp();                                     // every lane is done with its slot
+                    issue_copy(next, K);
+                }
+            };
+            one(IC<0>{});
+            if constexpr (NW > 1) one(IC<NW - 1>{});
+            if (last) return true;
             ++t;
-            __syncwarp();                                                         // every lane is done with its slot
-            issue_copy(word);
-            if constexpr ((q & 1) != 0)                                           // t is even now: the uniforms of transitions t, t + 1
-                if (native) x = philox4x32_10(make_uint4(gw_lo, gw_hi, static_cast<uint32_t>(t >> 1), p.round), pkey);
+            if constexpr ((q & 1) != 0) {                             // t is even now: the uniforms of transitions t, t + 1
+                if (native) {
+#pragma unroll
+                    for (int k = 0; k < NW; ++k)
+                        s[k].x = philox4x32_10(make_uint4(s[k].gw_lo, s[k].gw_hi, static_cast<uint32_t>(t >> 1), s[k].round), pkey);
+                }
+            }
             return false;
         };
         while (true) {
@@ -296,7 +350,9 @@ __global__ void __launch_bounds__(1024, 1) walk_v2_kernel(const WalkParams p, co
             if (step(IC<2>{})) break;
             if (step(IC<3>{})) break;
         }
-        if (active) dg.finish(p, w, cell);
+#pragma unroll
+        for (int k = 0; k < NW; ++k)
+            if (s[k].active) s[k].dg.finish(p, s[k].w, s[k].cell);
     }
 }
 
@@ -308,51 +364,63 @@ __global__ void __launch_bounds__(1024, 1) walk_v2_kernel(const WalkParams p, co
 // above 256 bytes (23.1 G at C5 against 24.4 G for the 16-bit rows of walk_tma.cu: few entries of a 200-entry row
 // fit the slack, so most steps still need the second gather).
 constexpr int64_t kV2L1Cells = 16384;      // below: L1-allocating row copies (see walk_v2_kernel)
+constexpr int kV2AutoNW = 1;               // walkers per thread the auto variant takes where two are instantiated
 
 struct V2Config {
     int cpr;            // 16-byte chunks per slot
+    int nw;             // walkers (slots) per thread
+    int ctas;           // CTAs per SM
     int threads;
     int log_n;
     int flavor;         // v2::kUniform / kRagged / kOversize
+    int l1_rows;        // row copies allocate in L1 (small graphs)
     size_t smem;
 };
 
-// variant: 0 = auto; 9500 + T/32 = T threads per CTA
+// variant: 0 = auto; 9500 + T/32 = one walker per thread, T threads per CTA; 9600 + T/32 = two walkers per thread
 inline bool v2_config(const cyp_graph *g, int variant, int64_t n_walkers, int sm_count, V2Config *out) {
     if (!g->v2_ok) return false;
+    int nw = kV2AutoNW, ctas = 1;
+    if (variant > 9700) { ctas = 2; nw = 1; variant -= 200; }
+    else if (variant > 9600) { nw = 2; variant -= 100; }
+    else if (variant > 9500) nw = 1;
     const int block = g->v2_slot_sectors * 32;          // covers (almost) every row (cyp_graph::v2_slot_sectors, rows_v2.cu)
     if (block > 256) return false;                       // long rows: walk_tma.cu
     int cpr = 2;
     while (cpr * 16 < block) cpr <<= 1;
     const int stride = 16 * cpr;
-    const size_t budget = 226 * 1024 - 1024;
-    int threads = static_cast<int>(budget / stride) / 32 * 32;
-    if (threads > 1024) threads = 1024;
+    const int flavor = g->v2_max_sectors * 32 > stride ? v2::kOversize : (g->v2_uniform ? v2::kUniform : v2::kRagged);
+    int l1_rows = g->n < kV2L1Cells ? 1 : 0;
+    if (const char *e = getenv("CYP_V2_L1")) l1_rows = atoi(e) ? 1 : 0;
+    if (!(cpr == 8 && flavor == v2::kUniform && !l1_rows)) nw = 1, ctas = 1;       // the only shape instantiated with two walkers per thread / two CTAs per SM
+    const size_t budget = (226 * 1024 - 1024) / ctas - (ctas > 1 ? 1024 : 0);
+    int threads = static_cast<int>(budget / (stride * nw)) / 32 * 32;
+    const int tmax = ctas == 2 ? 640 : (nw == 1 ? 1024 : 896);
+    if (threads > tmax) threads = tmax;
     if (variant > 9500) {
         threads = (variant - 9500) * 32 < threads ? (variant - 9500) * 32 : threads;
     } else if (n_walkers > 0 && sm_count > 0) {
         // wave balancing: every warp runs as many 32-walker batches as with the largest CTA, with no more warps than that needs
-        const int64_t batches = (n_walkers + 31) / 32;
-        const int64_t per_round = static_cast<int64_t>(sm_count) * (threads / 32);
+        const int64_t batches = (n_walkers + 32 * nw - 1) / (32 * nw);
+        const int64_t per_round = static_cast<int64_t>(sm_count) * ctas * (threads / 32);
         const int64_t rounds = (batches + per_round - 1) / per_round;
-        const int64_t warps = (batches + static_cast<int64_t>(sm_count) * rounds - 1) / (static_cast<int64_t>(sm_count) * rounds);
+        const int64_t warps = (batches + static_cast<int64_t>(sm_count) * ctas * rounds - 1) / (static_cast<int64_t>(sm_count) * ctas * rounds);
         if (warps * 32 < threads) threads = static_cast<int>(warps) * 32;
     }
     if (threads < 32) threads = 32;
     int log_n = 1;
     while ((1 << log_n) < g->max_len) ++log_n;
-    const int flavor = g->v2_max_sectors * 32 > stride ? v2::kOversize : (g->v2_uniform ? v2::kUniform : v2::kRagged);
-    *out = V2Config{cpr, threads, log_n, flavor, static_cast<size_t>(threads) * stride};
+    *out = V2Config{cpr, nw, ctas, threads, log_n, flavor, l1_rows, static_cast<size_t>(threads) * stride * nw};
     return true;
 }
 
-template <int CPR, int CDFM, int MODE, int FLAVOR, bool L1ROWS>
+template <int CPR, int CDFM, int MODE, int FLAVOR, bool L1ROWS, int NW = 1, int CTAS = 1>
 static int launch_v2_kernel(const WalkParams &p, const V2Config &c, int sm_count, cudaStream_t stream) {
-    auto kernel = walk_v2_kernel<CPR, CDFM, MODE, FLAVOR, L1ROWS>;
+    auto kernel = walk_v2_kernel<CPR, CDFM, MODE, FLAVOR, L1ROWS, NW, CTAS>;
     // the opt-in to > 48 KB of dynamic shared memory is a per-device attribute of the function
     CYP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c.smem)));
-    const int64_t need = (p.n_walkers + c.threads - 1) / c.threads;
-    const unsigned grid = static_cast<unsigned>(need < sm_count ? need : sm_count);       // persistent CTAs
+    const int64_t need = (p.n_walkers + c.threads * NW - 1) / (c.threads * NW);
+    const unsigned grid = static_cast<unsigned>(need < sm_count * CTAS ? need : sm_count * CTAS);       // persistent CTAs
     if (grid == 0) return CYP_OK;
     static const bool trace = getenv("CYP_TRACE") != nullptr;
     if (trace) {
@@ -370,12 +438,17 @@ static int launch_v2_kernel(const WalkParams &p, const V2Config &c, int sm_count
 template <int CPR, int CDFM, int MODE>
 static int launch_v2_flavor(const WalkParams &p, const V2Config &c, int sm_count, cudaStream_t stream) {
     // small graphs (L1-allocating copies) always take the predicated copies: 5 instantiations, not 6
-    if (p.l1_rows) {
+    if (c.l1_rows) {
         return c.flavor == v2::kOversize ? launch_v2_kernel<CPR, CDFM, MODE, v2::kOversize, true>(p, c, sm_count, stream)
                                          : launch_v2_kernel<CPR, CDFM, MODE, v2::kRagged, true>(p, c, sm_count, stream);
     }
     switch (c.flavor) {
-        case v2::kUniform: return launch_v2_kernel<CPR, CDFM, MODE, v2::kUniform, false>(p, c, sm_count, stream);
+        case v2::kUniform:
+            if constexpr (CPR == 8) {
+                if (c.nw == 2) return launch_v2_kernel<CPR, CDFM, MODE, v2::kUniform, false, 2>(p, c, sm_count, stream);
+                if (c.ctas == 2) return launch_v2_kernel<CPR, CDFM, MODE, v2::kUniform, false, 1, 2>(p, c, sm_count, stream);
+            }
+            return launch_v2_kernel<CPR, CDFM, MODE, v2::kUniform, false>(p, c, sm_count, stream);
         case v2::kRagged: return launch_v2_kernel<CPR, CDFM, MODE, v2::kRagged, false>(p, c, sm_count, stream);
         default: return launch_v2_kernel<CPR, CDFM, MODE, v2::kOversize, false>(p, c, sm_count, stream);
     }

@@ -187,7 +187,7 @@ def sampling(data, auto_adjust=True, matrix_key="T_forward", cluster_key="louvai
              rounds_limit=10, traj_number=200, sim_number=500, end_point_probability=0.99, root_cell_probability=0.99,
              end_points=None, root_cells=None, end_clusters=None, root_clusters=None, min_clusters=2, max_iter=200,
              tol=1e-3, normalize=False, unique=True, num_cores=1, copy=False, *, seed=0, cdf_mode="reference",
-             device=None, dist="auto", uniforms=None, _backend=None):
+             device=None, dist="auto", _backend=None):
     """Markov sampling of cell sequences from root cells to terminal regions on a B200.
 
     Positional arguments, defaults, errors and outputs are those of `cytopath.sampling`
@@ -207,8 +207,6 @@ def sampling(data, auto_adjust=True, matrix_key="T_forward", cluster_key="louvai
         Shard every round's walkers over the ranks of an initialised torch.distributed
         group (one process per GPU).  All ranks must call with the same arguments; all ranks
         receive the same outputs.
-    uniforms : callable(round, walker_begin, n_walkers, n_transitions) -> float64 array, optional
-        Replaces the Philox stream (test hook used to drive the reference with shared numbers).
 
     Writes adata.uns['run_info'] and adata.uns['samples'] ('cell_sequences' int32,
     'transition_score' float32, 'cluster_sequences' <U8/<U32) and returns `adata` if `copy`.
@@ -254,14 +252,14 @@ def sampling(data, auto_adjust=True, matrix_key="T_forward", cluster_key="louvai
         return _sampling_on_graph(adata, copy, world, backend, graph, C, device, auto_adjust, matrix_key, cluster_key, max_steps,
                                   min_sim_ratio, rounds_limit, traj_number, sim_number, end_point_probability,
                                   root_cell_probability, end_points, root_cells, end_clusters, root_clusters, min_clusters,
-                                  max_iter, tol, unique, seed, uniforms)
+                                  max_iter, tol, unique, seed)
     finally:
         graph.close()
 
 
 def _sampling_on_graph(adata, copy, world, backend, graph, C, device, auto_adjust, matrix_key, cluster_key, max_steps,
                        min_sim_ratio, rounds_limit, traj_number, sim_number, end_point_probability, root_cell_probability,
-                       end_points, root_cells, end_clusters, root_clusters, min_clusters, max_iter, tol, unique, seed, uniforms):
+                       end_points, root_cells, end_clusters, root_clusters, min_clusters, max_iter, tol, unique, seed):
     """Everything of `sampling` after the transition matrix has been accepted (:189-412)."""
     n = C.shape[0]
     try:
@@ -334,14 +332,13 @@ def _sampling_on_graph(adata, copy, world, backend, graph, C, device, auto_adjus
     try:
         return _run_rounds(adata, copy, world, graph, session, roots, end_cells, end_slot_of_point, end_point_clusters,
                            end_clusters_, trunc, max_steps, traj_number, sim_number, min_sim_ratio, rounds_limit,
-                           unique, uniforms, device)
+                           unique, device)
     finally:
         session.close()
 
 
 def _run_rounds(adata, copy, world, graph, session, roots, end_cells, end_slot_of_point, end_point_clusters,
-                end_clusters_, trunc, max_steps, traj_number, sim_number, min_sim_ratio, rounds_limit, unique,
-                uniforms, device):
+                end_clusters_, trunc, max_steps, traj_number, sim_number, min_sim_ratio, rounds_limit, unique, device):
     n_roots = len(roots)
     n_slots = int(end_slot_of_point.max()) + 1
     sim_number_ = max(int(sim_number / n_roots), 1)                    # :285
@@ -362,11 +359,8 @@ def _run_rounds(adata, copy, world, graph, session, roots, end_cells, end_slot_o
         sim_number_ *= 2                                              # :299
         total = n_roots * sim_number_
         w0, w1 = _shard(total, world.rank, world.size)
-        u = None
-        if uniforms is not None:
-            u = np.ascontiguousarray(uniforms(rnd, w0, w1 - w0, max_steps - 1), dtype=np.float64)
         row0 = session.rows()
-        st = session.round(rnd, sim_number_, w0, w1, u)
+        st = session.round(rnd, sim_number_, w0, w1)
         if world.size > 1 and unique:
             _prune_across_ranks(world, session, device)
         _, walker, slot = session.fetch_index(row0)

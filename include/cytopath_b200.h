@@ -158,18 +158,22 @@ typedef struct cyp_round_stats {
     float ms_walk;            /* step kernel, CUDA events */
     float ms_filter;          /* filter + dedup + compaction kernels */
     int32_t n_chunks;         /* pieces the round was walked in (1 unless it did not fit the free HBM) */
+    int64_t n_replayed;       /* walkers walked a second time to compare sequences with equal hashes */
 } cyp_round_stats;
 
-/* Walkers [walker_begin, walker_end) of round `round` with sims_per_root walkers per root.
- * h_uniforms as in cyp_walk (rows relative to walker_begin), or NULL. */
+/* Walkers [walker_begin, walker_end) of round `round` with sims_per_root walkers per root. */
 int cyp_session_round(cyp_session *s, uint32_t round, int64_t sims_per_root, int64_t walker_begin,
-                      int64_t walker_end, const double *h_uniforms, cyp_round_stats *stats);
+                      int64_t walker_end, cyp_round_stats *stats);
 /* Rows kept so far, then per kept row: round, walker id, end-point slot (store order =
  * round-major, walker order within a round, i.e. the accumulation order of :335-340). */
 int cyp_session_rows(const cyp_session *s, int64_t *n_rows);
 int cyp_session_fetch_index(const cyp_session *s, int64_t row_begin, int64_t n_rows, int32_t *h_round,
                             int64_t *h_walker, int32_t *h_end_slot);
-/* Gather store rows (by store row index) into int32 [n_rows, max_steps] on the host. */
+/* h_counts [n_end_slots]: how many of the kept rows [row_begin, row_begin + n_rows) end on each end point (:341-354). */
+int cyp_session_slot_counts(const cyp_session *s, int64_t row_begin, int64_t n_rows, int64_t *h_counts);
+/* Kept rows (by row index) as int32 [n_rows, max_steps] on the host.  The session stores 16 bytes per kept sequence
+ * (round, walker, end-point slot), not the sequence: the rows are produced by walking those walkers again -- the
+ * uniform stream is keyed by (walker, step, round), so the replay is bit-identical. */
 int cyp_session_fetch_rows(const cyp_session *s, const int64_t *h_rows, int64_t n_rows, int32_t *h_seq);
 
 /* Multi-GPU de-duplication support (walkers sharded by contiguous id blocks).  After a

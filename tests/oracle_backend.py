@@ -43,11 +43,11 @@ class Session:
         self.records = np.empty((0, 3), np.uint64)
         self.row0 = 0
 
-    def round(self, round_idx, sims_per_root, walker_begin, walker_end, uniforms=None):
+    def round(self, round_idx, sims_per_root, walker_begin, walker_end):
         W = walker_end - walker_begin
         starts = self.roots[np.arange(walker_begin, walker_end) // sims_per_root]
         seq = cwalk.walk(self.g.C, self.g._cdf, starts, self.max_steps - 1, seed=self.seed, round_idx=round_idx,
-                         walker_begin=walker_begin, uniforms=uniforms)
+                         walker_begin=walker_begin)
         cs = np.sort(self.code[seq], axis=1)
         distinct = 1 + (np.diff(cs, axis=1) != 0).sum(axis=1)
         ok = distinct >= self.min_clusters
