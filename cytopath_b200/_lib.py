@@ -27,7 +27,11 @@ EXPORTS = [
     "cyp_session_create", "cyp_session_destroy", "cyp_session_round", "cyp_session_rows",
     "cyp_session_fetch_index", "cyp_session_fetch_rows", "cyp_session_slot_counts", "cyp_session_round_records",
     "cyp_session_round_prune", "cyp_session_set_hash_bits", "cyp_session_set_chunk_walkers",
-    "cyp_hausdorff_matrix", "cyp_directionality_scores",
+    "cyp_hausdorff_matrix", "cyp_directionality_scores", "cyp_graph_power_iteration",
+    "cyp_group_create_local", "cyp_group_unique_id", "cyp_group_create_rank", "cyp_group_destroy", "cyp_group_info",
+    "cyp_group_graph", "cyp_group_session", "cyp_group_graph_create", "cyp_group_session_create", "cyp_group_round",
+    "cyp_group_rows", "cyp_group_fetch_index", "cyp_group_digest", "cyp_group_select", "cyp_group_set_chunk_walkers",
+    "cyp_group_broadcast_bytes", "cyp_gather_ceiling",
 ]
 
 
@@ -38,6 +42,27 @@ class RoundStats(ctypes.Structure):
         ("dedup_passes", ctypes.c_int32), ("ms_walk", ctypes.c_float), ("ms_filter", ctypes.c_float),
         ("n_chunks", ctypes.c_int32), ("n_replayed", ctypes.c_int64),
     ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class GroupRoundStats(ctypes.Structure):
+    _fields_ = [
+        ("n_walkers", ctypes.c_int64), ("n_pass_clusters", ctypes.c_int64), ("n_terminal", ctypes.c_int64),
+        ("n_kept", ctypes.c_int64), ("n_nocrossing", ctypes.c_int64), ("n_replayed", ctypes.c_int64),
+        ("total_rows", ctypes.c_int64), ("exchange_bytes", ctypes.c_int64),
+        ("ms_walk", ctypes.c_float), ("ms_filter", ctypes.c_float), ("ms_local", ctypes.c_float), ("ms_exchange", ctypes.c_float),
+        ("n_chunks", ctypes.c_int32), ("dedup_passes", ctypes.c_int32),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class GroupSelectStats(ctypes.Structure):
+    _fields_ = [("gather_bytes", ctypes.c_int64), ("ms_locate_replay", ctypes.c_float), ("ms_gather", ctypes.c_float),
+                ("ms_fetch", ctypes.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -85,7 +110,7 @@ def load():
     L.cyp_graph_fetch_fused.argtypes = [vp, vp, vp, vp]
     L.cyp_graph_fetch_cdf.argtypes = [vp, vp]
     L.cyp_graph_build_ms.argtypes = [vp, P(ctypes.c_float)]
-    L.cyp_power_iteration.argtypes = [ci, i64, i64, vp, vp, vp, vp, vp, i32, vp, vp]
+    L.cyp_power_iteration.argtypes = [ci, i64, i64, vp, vp, vp, vp, vp, i32, vp, vp, vp]
     L.cyp_walk.argtypes = [vp, vp, i64, i64, i64, i64, i32, u64, u32, vp, vp, P(i64)]
     L.cyp_walk_device.argtypes = [vp, vp, i64, i64, i64, i64, i32, u64, u32, vp, vp, vp, ci, vp]
     L.cyp_walk_variant_name.argtypes = [vp, ci]
@@ -104,9 +129,29 @@ def load():
     L.cyp_session_set_chunk_walkers.argtypes = [vp, i64]
     L.cyp_directionality_scores.argtypes = [ci, i64, i32, vp, vp, vp, vp, i64, vp, i64, vp, vp, vp, vp, P(ctypes.c_float)]
     L.cyp_hausdorff_matrix.argtypes = [ci, vp, i64, i32, i32, ci, vp, P(ctypes.c_float)]
+    L.cyp_graph_power_iteration.argtypes = [vp, vp, vp, i32, vp, vp]
+    L.cyp_group_create_local.argtypes = [ci, vp, P(vp)]
+    L.cyp_group_unique_id.argtypes = [vp]
+    L.cyp_group_create_rank.argtypes = [vp, ci, ci, ci, P(vp)]
+    L.cyp_group_destroy.argtypes = [vp]
+    L.cyp_group_info.argtypes = [vp, P(ci), P(ci), P(ci), P(ci)]
+    L.cyp_group_graph.argtypes = [vp, ci]
+    L.cyp_group_graph.restype = vp
+    L.cyp_group_session.argtypes = [vp, ci]
+    L.cyp_group_session.restype = vp
+    L.cyp_group_graph_create.argtypes = [vp, i64, i64, vp, vp, vp, ci, ci, ci, P(ctypes.c_float), P(ctypes.c_float)]
+    L.cyp_group_session_create.argtypes = [vp, vp, i64, vp, i32, i32, vp, i32, i32, ci, u64]
+    L.cyp_group_round.argtypes = [vp, u32, i64, vp, P(GroupRoundStats)]
+    L.cyp_group_rows.argtypes = [vp, P(i64)]
+    L.cyp_group_fetch_index.argtypes = [vp, i64, i64, vp, vp, vp]
+    L.cyp_group_digest.argtypes = [vp, vp]
+    L.cyp_group_select.argtypes = [vp, i64, vp, vp, vp, vp, P(GroupSelectStats)]
+    L.cyp_group_set_chunk_walkers.argtypes = [vp, i64]
+    L.cyp_group_broadcast_bytes.argtypes = [vp, vp, i64, ci]
+    L.cyp_gather_ceiling.argtypes = [ci, i64, i32, P(ctypes.c_double)]
     for name in EXPORTS:
         fn = getattr(L, name)
-        if name not in ("cyp_last_error", "cyp_walk_variant_name"):
+        if name not in ("cyp_last_error", "cyp_walk_variant_name", "cyp_group_graph", "cyp_group_session"):
             fn.restype = ci
     _lib = L
     return L
@@ -126,6 +171,13 @@ def device_count() -> int:
 def release_cached_memory(device: int = -1) -> None:
     """Give the device memory the library keeps for reuse back to the driver (device < 0: all devices)."""
     check(load().cyp_release_cached_memory(device))
+
+
+def gather_ceiling(working_set_bytes: int, gather_bytes: int = 128, device: int = 0) -> float:
+    """Independent random gathers/s of `gather_bytes` out of `working_set_bytes` (cyp_gather_ceiling)."""
+    out = ctypes.c_double()
+    check(load().cyp_gather_ceiling(device, int(working_set_bytes), int(gather_bytes), ctypes.byref(out)))
+    return out.value
 
 
 def require_device(device: int = 0):
@@ -148,7 +200,7 @@ def ptr(a):
     return ctypes.c_void_p(int(a))          # raw address (e.g. torch.Tensor.data_ptr())
 
 
-def power_iteration(T, init, stationary, max_iter: int, device: int = 0, return_state: bool = False):
+def power_iteration(T, init, stationary, max_iter: int, device: int = 0, return_state: bool = False, history=None):
     """eps history of iterate_state_probability (markov_chain_sampler.py:62-87) computed on the GPU (K4).
     T: scipy sparse or dense n x n matrix as stored in adata.uns[matrix_key] (not normalised, like :73)."""
     from scipy import sparse
@@ -162,8 +214,10 @@ def power_iteration(T, init, stationary, max_iter: int, device: int = 0, return_
     stationary = np.ascontiguousarray(stationary, dtype=np.float64)
     eps = np.empty(max_iter, dtype=np.float64)
     state = np.empty(n, dtype=np.float64) if return_state else None
+    if history is not None:
+        assert history.shape == (max_iter, n) and history.dtype == np.float64 and history.flags["C_CONTIGUOUS"]
     check(load().cyp_power_iteration(device, n, val.shape[0], ptr(col_ptr), ptr(row_idx), ptr(val), ptr(init),
-                                     ptr(stationary), max_iter, ptr(eps), ptr(state)))
+                                     ptr(stationary), max_iter, ptr(eps), ptr(state), ptr(history)))
     return (eps, state) if return_state else eps
 
 
@@ -206,6 +260,15 @@ def hausdorff_matrix(coords, metric: str = "euclidean", device: int = 0, return_
 class Graph:
     """Device-resident transition graph: CSR + per-row CDF (K1).  Mirrors what
     `matrix_prep` (markov_chain_sampler.py:11-31) returns, minus the ELL padding."""
+
+    _owner = True
+
+    @classmethod
+    def view(cls, handle, n: int, nnz: int, cdf_mode: int, device: int):
+        """A Graph object over a handle somebody else owns (a group's graph): close() does not destroy it."""
+        g = cls.__new__(cls)
+        g._h, g.n, g.nnz, g.cdf_mode, g.device, g._owner, g.indptr = ctypes.c_void_p(handle), n, nnz, cdf_mode, device, False, None
+        return g
 
     def __init__(self, C, cdf_mode: int = CDF_REFERENCE, device: int = 0):
         """C: canonical scipy CSR (sorted columns, no duplicates, no explicit zeros), float64 or float32
@@ -291,10 +354,19 @@ class Graph:
             check(load().cyp_transition_scores(self._h, ptr(seq), seq.shape[0], seq.shape[1], ptr(out)))
         return out
 
+    def power_iteration(self, init, stationary, max_iter: int, return_state: bool = False):
+        """eps history of iterate_state_probability (:62-87) on the matrix this graph already holds in HBM (K4)."""
+        init = np.ascontiguousarray(init, dtype=np.float64)
+        stationary = np.ascontiguousarray(stationary, dtype=np.float64)
+        eps = np.empty(max_iter, dtype=np.float64)
+        state = np.empty(self.n, dtype=np.float64) if return_state else None
+        check(load().cyp_graph_power_iteration(self._h, ptr(init), ptr(stationary), max_iter, ptr(eps), ptr(state)))
+        return (eps, state) if return_state else eps
+
     def close(self):
-        if self._h:
+        if self._h and self._owner:
             load().cyp_graph_destroy(self._h)
-            self._h = ctypes.c_void_p()
+        self._h = ctypes.c_void_p()
 
     def __del__(self):
         try:
@@ -386,3 +458,189 @@ class Session:
             self.close()
         except Exception:
             pass
+
+
+def nccl_path():
+    """The NCCL the group layer should bind when the process has none loaded yet: torch's bundled copy if it is
+    installed (found without importing torch), else whatever `libnccl.so.2` resolves to."""
+    if os.environ.get("CYP_NCCL_PATH"):
+        return os.environ["CYP_NCCL_PATH"]
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for root in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(root, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                return cand
+    except Exception:
+        pass
+    return ""
+
+
+class Group:
+    """The devices that share one `sampling()` run (include/cytopath_b200.h, "multi-GPU"): either N devices driven by
+    this process (`Group(devices=[...])`) or this process's single device as rank `rank` of `world` processes
+    (`Group(unique_id=..., rank=, world=, device=)`).  Owns the replicated graph and the per-device sessions."""
+
+    def __init__(self, devices=None, *, unique_id: bytes | None = None, rank: int = 0, world: int = 1, device: int = 0):
+        L = load()
+        self._h = ctypes.c_void_p()
+        self.graph = None
+        if (devices is not None and len(devices) > 1) or world > 1:
+            path = nccl_path()
+            if path:
+                os.environ.setdefault("CYP_NCCL_PATH", path)
+        if unique_id is not None or world > 1:
+            require_device(device)
+            buf = (ctypes.c_uint8 * 128).from_buffer_copy(unique_id) if unique_id is not None else None
+            check(L.cyp_group_create_rank(buf, rank, world, device, ctypes.byref(self._h)))
+        else:
+            devs = np.ascontiguousarray([0] if devices is None else list(devices), dtype=np.int32)
+            require_device(int(devs.max()))
+            check(L.cyp_group_create_local(len(devs), ptr(devs), ctypes.byref(self._h)))
+        w, nl, fr, ver = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        check(L.cyp_group_info(self._h, ctypes.byref(w), ctypes.byref(nl), ctypes.byref(fr), ctypes.byref(ver)))
+        self.world, self.n_local, self.first_rank, self.nccl_version = w.value, nl.value, fr.value, ver.value
+        self.n_end_slots = self.max_steps = 0
+
+    @staticmethod
+    def unique_id() -> bytes:
+        path = nccl_path()
+        if path:
+            os.environ.setdefault("CYP_NCCL_PATH", path)
+        buf = (ctypes.c_uint8 * 128)()
+        check(load().cyp_group_unique_id(buf))
+        return bytes(buf)
+
+    @property
+    def rank(self) -> int:
+        return self.first_rank
+
+    def create_graph(self, C, cdf_mode: int, root_rank: int = 0, shape=None) -> dict:
+        """K1 on `root_rank` from its canonical CSR `C`, then a broadcast of the device arrays.  Processes that do not
+        host the root rank may pass C=None with shape=(n_cells, nnz)."""
+        L = load()
+        bms, xms = ctypes.c_float(), ctypes.c_float()
+        if C is not None:
+            indptr = np.ascontiguousarray(C.indptr, dtype=np.int64)
+            indices = np.ascontiguousarray(C.indices, dtype=np.int32)
+            f32 = C.data.dtype == np.float32
+            data = np.ascontiguousarray(C.data, dtype=np.float32 if f32 else np.float64)
+            n, nnz = int(C.shape[0]), int(data.shape[0])
+            args = (ptr(indptr), ptr(indices), ptr(data), int(f32))
+        else:
+            n, nnz = int(shape[0]), int(shape[1])
+            args = (None, None, None, 0)
+        check(L.cyp_group_graph_create(self._h, n, nnz, *args, cdf_mode, root_rank, ctypes.byref(bms), ctypes.byref(xms)))
+        h = L.cyp_group_graph(self._h, 0)
+        dev = ctypes.c_int()
+        check(L.cyp_graph_info(h, None, None, None, None, ctypes.byref(dev), None))
+        self.graph = Graph.view(h, n, nnz, cdf_mode, dev.value)
+        return {"ms_build": bms.value, "ms_broadcast": xms.value}
+
+    def create_session(self, root_cells, cell_code, n_codes: int, min_clusters: int, end_slot_of_cell, n_end_slots: int,
+                       max_steps: int, unique: bool, seed: int):
+        roots = np.ascontiguousarray(root_cells, dtype=np.int32)
+        code = np.ascontiguousarray(cell_code, dtype=np.int32)
+        slot = np.ascontiguousarray(end_slot_of_cell, dtype=np.int32)
+        assert code.shape[0] == self.graph.n and slot.shape[0] == self.graph.n
+        self.n_end_slots, self.max_steps = int(n_end_slots), int(max_steps)
+        check(load().cyp_group_session_create(self._h, ptr(roots), roots.shape[0], ptr(code), n_codes, min_clusters, ptr(slot),
+                                              n_end_slots, max_steps, int(bool(unique)), seed))
+
+    def power_iteration_matrix(self, T, init, stationary, max_iter: int):
+        """K4 on an upload of `T` (the stored matrix differs from the one the graph was built from)."""
+        return power_iteration(T, init, stationary, max_iter, self.graph.device)
+
+    def session_handle(self, local_index: int = 0):
+        return load().cyp_group_session(self._h, local_index)
+
+    def round(self, round_idx: int, sims_per_root: int, want_slot_counts: bool = True):
+        """One sampling round over the whole group.  Returns (stats dict, per-slot counts of the sequences it added)."""
+        st = GroupRoundStats()
+        counts = np.zeros(self.n_end_slots, dtype=np.int64) if want_slot_counts else None
+        rc = load().cyp_group_round(self._h, round_idx, sims_per_root, ptr(counts), ctypes.byref(st))
+        if rc == E_NOCROSSING:
+            raise IndexError("index 0 is out of bounds for axis 0 with size 0")
+        check(rc)
+        return st.as_dict(), counts
+
+    def rows(self) -> int:
+        n = ctypes.c_int64()
+        check(load().cyp_group_rows(self._h, ctypes.byref(n)))
+        return n.value
+
+    def fetch_index(self, row_begin: int = 0, n_rows: int | None = None):
+        if n_rows is None:
+            n_rows = self.rows() - row_begin
+        rnd, walker, slot = np.empty(n_rows, np.int32), np.empty(n_rows, np.int64), np.empty(n_rows, np.int32)
+        if n_rows:
+            check(load().cyp_group_fetch_index(self._h, row_begin, n_rows, ptr(rnd), ptr(walker), ptr(slot)))
+        return rnd, walker, slot
+
+    def digest(self) -> tuple:
+        d = np.zeros(2, dtype=np.uint64)
+        check(load().cyp_group_digest(self._h, ptr(d)))
+        return int(d[0]), int(d[1])
+
+    def select(self, slots, offsets, scores: bool = True):
+        """Rows (and transition scores) of the picks: pick k = the offsets[k]-th kept sequence ending on slots[k]."""
+        slots = np.ascontiguousarray(slots, dtype=np.int32)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        seq = np.empty((slots.shape[0], self.max_steps), dtype=np.int32)
+        score = np.empty(slots.shape[0], dtype=np.float32) if scores else None
+        st = GroupSelectStats()
+        if slots.shape[0]:
+            check(load().cyp_group_select(self._h, slots.shape[0], ptr(slots), ptr(offsets), ptr(seq), ptr(score), ctypes.byref(st)))
+        return seq, score, st.as_dict()
+
+    def set_chunk_walkers(self, walkers: int):
+        check(load().cyp_group_set_chunk_walkers(self._h, walkers))
+
+    def broadcast(self, array: np.ndarray, root_rank: int = 0) -> np.ndarray:
+        """In place: the bytes of `array` on `root_rank` reach every process of the group."""
+        assert array.flags["C_CONTIGUOUS"]
+        check(load().cyp_group_broadcast_bytes(self._h, ptr(array), array.nbytes, root_rank))
+        return array
+
+    def close(self):
+        if self._h:
+            if self.graph is not None:
+                self.graph.close()
+            load().cyp_group_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def open_group(device=None, devices=None, dist="auto") -> Group:
+    """The group `sampling()` runs on: `devices=[...]` -> this process drives them all; an initialised
+    torch.distributed group (one process per GPU, `dist` True or 'auto') -> one rank per process, the NCCL id travels
+    through torch's store; else one device."""
+    import sys
+    if devices is not None:
+        devs = [int(d) for d in devices]
+        if not devs:
+            raise ValueError("devices must name at least one CUDA device")
+        return Group(devices=devs)
+    if dist is True or (dist == "auto" and "torch.distributed" in sys.modules):
+        try:
+            import torch.distributed as td
+        except Exception:
+            if dist is True:
+                raise
+            td = None
+        if td is not None and td.is_available() and td.is_initialized() and td.get_world_size() > 1:
+            rank, world = td.get_rank(), td.get_world_size()
+            if device is None:
+                device = int(os.environ.get("LOCAL_RANK", "0"))
+            box = [Group.unique_id() if rank == 0 else None]
+            td.broadcast_object_list(box, src=0)
+            return Group(unique_id=box[0], rank=rank, world=world, device=int(device))
+        if dist is True:
+            raise RuntimeError("dist=True but torch.distributed is not initialised with more than one rank")
+    return Group(devices=[0 if device is None else int(device)])

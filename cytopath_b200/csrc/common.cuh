@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/cytopath_b200.h"
@@ -163,6 +164,7 @@ struct cyp_graph {
     int64_t v2_sectors = 0;              // total sectors of d_rows2
     unsigned char *d_rows2 = nullptr;    // [v2_sectors * 32]
     unsigned char *d_rows2_base = nullptr;   // the allocation d_rows2 lies in (d_rows2 = base + placement offset)
+    int64_t rows2_bytes = 0;                 // bytes of d_rows2 (blocks + slack for whole-slot copies past the last block)
     uint32_t *d_edge4 = nullptr;         // [v2_edge_units * 4] row words of all targets, rows padded to 4 words
     int64_t v2_edge_units = 0;
     uint32_t *d_word = nullptr;          // [n] row word of every cell (the roots start from it)
@@ -186,6 +188,19 @@ cudaError_t v2_upload(cyp_graph *g, V2Build *b, cudaStream_t stream);
 cudaError_t v2_launch(cyp_graph *g, V2Build *b, int64_t row_begin, int64_t row_end, cudaStream_t stream);
 cudaError_t v2_finish(cyp_graph *g, V2Build *b, bool codes_ok);
 void v2_release(cyp_graph *g, V2Build *b);
+// graph.cu, for the multi-device layer (group.cu): a graph built on one device is replicated by broadcasting its
+// device arrays over NVLink instead of uploading the CSR from the host once per GPU.
+struct GraphWire {                 // the host-side fields of a cyp_graph, as they travel to the other ranks
+    int32_t cdf_mode, max_len, q16_ok, monotone, v2_ok, v2_max_sectors, v2_slot_sectors, v2_uniform, has_edge_records, pad_;
+    int64_t n, nnz, padded, v2_sectors, v2_edge_units, rows2_bytes;
+    double mean_len, row_sum_min, row_sum_max;
+    float build_ms, pad2_;
+};
+GraphWire graph_wire(const cyp_graph *g);
+// allocates (does not fill) the device arrays of a graph described by `w` on `device`
+int graph_alloc_like(const GraphWire &w, int device, cyp_graph **out);
+// (pointer, bytes) of every device array of the graph, in an order that only depends on the wire fields
+void graph_device_arrays(const cyp_graph *g, std::vector<std::pair<void *, size_t>> *out);
 // graph.cu: builds d_q16 and d_edge (the arrays of the step kernels other than walk_v2.cu) if they do not exist yet.
 // Synchronous, default stream; call before launching one of those kernels.
 int ensure_edge_records(const cyp_graph *g);

@@ -211,6 +211,7 @@ build_cdf_kernel(int64_t row_begin, int64_t n, const int64_t *__restrict__ row_p
             if (j < len) {
                 const int64_t q = s_src[lo] + j;
                 const int32_t c = raw_col[q];
+                if (c < 0 || c >= n) atomicOr(negative_flag, 4);          // not a cell: the create call fails
                 cdf[dst0 + p] = finish_cdf<CdfT>(s_val[q - src0]);
                 const uint16_t code = cdf_code<CdfT>(s_val[q - src0], negative_flag);     // also checks the code range
                 col[dst0 + p] = c;
@@ -240,6 +241,7 @@ build_cdf_kernel(int64_t row_begin, int64_t n, const int64_t *__restrict__ row_p
             if (v < 0.0) atomicOr(negative_flag, 1);
             acc = __dadd_rn(acc, v);
             const int32_t c = raw_col[a + j];
+            if (c < 0 || c >= n) atomicOr(negative_flag, 4);
             cdf[dst + j] = finish_cdf<CdfT>(acc);
             const uint16_t code = cdf_code<CdfT>(acc, negative_flag);
             col[dst + j] = c;
@@ -342,6 +344,78 @@ int ensure_edge_records(const cyp_graph *cg) {
     return CYP_OK;
 }
 
+GraphWire graph_wire(const cyp_graph *g) {
+    GraphWire w{};
+    w.cdf_mode = g->cdf_mode; w.max_len = g->max_len; w.q16_ok = g->q16_ok; w.monotone = g->monotone;
+    w.v2_ok = g->v2_ok; w.v2_max_sectors = g->v2_max_sectors; w.v2_slot_sectors = g->v2_slot_sectors; w.v2_uniform = g->v2_uniform;
+    w.has_edge_records = g->d_edge != nullptr ? 1 : 0;
+    w.n = g->n; w.nnz = g->nnz; w.padded = g->padded; w.v2_sectors = g->v2_sectors; w.v2_edge_units = g->v2_edge_units;
+    w.rows2_bytes = g->rows2_bytes;
+    w.mean_len = g->mean_len; w.row_sum_min = g->row_sum_min; w.row_sum_max = g->row_sum_max;
+    w.build_ms = g->build_ms;
+    return w;
+}
+
+void graph_device_arrays(const cyp_graph *g, std::vector<std::pair<void *, size_t>> *out) {
+    const size_t cdf_elem = (g->cdf_mode == CYP_CDF_EXACT) ? 8 : 4;
+    const size_t padded = static_cast<size_t>(g->padded), n = static_cast<size_t>(g->n);
+    out->clear();
+    out->emplace_back(g->d_row, sizeof(RowInfo) * n);
+    out->emplace_back(g->d_cdf, cdf_elem * padded);
+    out->emplace_back(g->d_col, sizeof(int32_t) * padded);
+    out->emplace_back(g->d_val, sizeof(double) * padded);
+    out->emplace_back(g->d_row_ptr, sizeof(int64_t) * (n + 1));
+    if (g->v2_ok) {
+        out->emplace_back(g->d_rows2, static_cast<size_t>(g->rows2_bytes));
+        out->emplace_back(g->d_edge4, sizeof(uint32_t) * 4 * static_cast<size_t>(g->v2_edge_units + 1));
+        out->emplace_back(g->d_word, sizeof(uint32_t) * n);
+    }
+    if (g->d_edge) {
+        out->emplace_back(g->d_q16, sizeof(uint16_t) * padded);
+        out->emplace_back(g->d_edge, sizeof(EdgeRec) * padded);
+    }
+}
+
+static void graph_free(cyp_graph *g);
+
+int graph_alloc_like(const GraphWire &w, int device, cyp_graph **out) {
+    *out = nullptr;
+    DeviceGuard guard(device);
+    cyp_graph *g = new cyp_graph();
+    g->device = device;
+    g->cdf_mode = w.cdf_mode; g->n = w.n; g->nnz = w.nnz; g->padded = w.padded; g->max_len = w.max_len; g->mean_len = w.mean_len;
+    g->q16_ok = w.q16_ok; g->monotone = w.monotone; g->build_ms = w.build_ms;
+    g->row_sum_min = w.row_sum_min; g->row_sum_max = w.row_sum_max;
+    g->v2_ok = w.v2_ok; g->v2_max_sectors = w.v2_max_sectors; g->v2_slot_sectors = w.v2_slot_sectors; g->v2_uniform = w.v2_uniform;
+    g->v2_sectors = w.v2_sectors; g->v2_edge_units = w.v2_edge_units; g->rows2_bytes = w.rows2_bytes;
+    const size_t cdf_elem = (w.cdf_mode == CYP_CDF_EXACT) ? 8 : 4;
+    const size_t padded = static_cast<size_t>(w.padded), n = static_cast<size_t>(w.n);
+    cudaError_t e = dev_alloc(&g->d_row, sizeof(RowInfo) * n);
+    if (e == cudaSuccess) e = dev_alloc(&g->d_cdf, cdf_elem * padded);
+    if (e == cudaSuccess) e = dev_alloc(&g->d_col, sizeof(int32_t) * padded);
+    if (e == cudaSuccess) e = dev_alloc(&g->d_val, sizeof(double) * padded);
+    if (e == cudaSuccess) e = dev_alloc(&g->d_row_ptr, sizeof(int64_t) * (n + 1));
+    g->device_bytes = static_cast<int64_t>(sizeof(RowInfo) * n + sizeof(int64_t) * (n + 1) + (cdf_elem + sizeof(int32_t) + sizeof(double)) * padded);
+    if (e == cudaSuccess && w.v2_ok) {
+        e = dev_alloc(&g->d_rows2_base, static_cast<size_t>(w.rows2_bytes));
+        g->d_rows2 = g->d_rows2_base;
+        if (e == cudaSuccess) e = dev_alloc(&g->d_edge4, sizeof(uint32_t) * 4 * static_cast<size_t>(w.v2_edge_units + 1));
+        if (e == cudaSuccess) e = dev_alloc(&g->d_word, sizeof(uint32_t) * n);
+        g->device_bytes += static_cast<int64_t>(w.rows2_bytes + sizeof(uint32_t) * 4 * (w.v2_edge_units + 1) + sizeof(uint32_t) * n);
+    }
+    if (e == cudaSuccess && w.has_edge_records) {
+        e = dev_alloc(&g->d_q16, sizeof(uint16_t) * padded);
+        if (e == cudaSuccess) e = dev_alloc(&g->d_edge, sizeof(EdgeRec) * padded);
+        g->device_bytes += static_cast<int64_t>((sizeof(uint16_t) + sizeof(EdgeRec)) * padded);
+    }
+    if (e != cudaSuccess) {
+        graph_free(g);
+        return fail(e == cudaErrorMemoryAllocation ? CYP_E_NOMEM : CYP_E_CUDA, std::string("graph_alloc_like: ") + cudaGetErrorString(e));
+    }
+    *out = g;
+    return CYP_OK;
+}
+
 }  // namespace cyp
 
 using namespace cyp;
@@ -371,6 +445,7 @@ extern "C" int cyp_device_count(int *n) {
     return CYP_OK;
 }
 
+namespace cyp {
 static void graph_free(cyp_graph *g) {
     if (!g) return;
     DeviceGuard guard(g->device);
@@ -386,6 +461,7 @@ static void graph_free(cyp_graph *g) {
     dev_free(g->d_word);
     delete g;
 }
+}  // namespace cyp
 
 // cyp_graph_create: upload + K1 + K1b as a pipeline.  The CSR arrays travel in chunks of rows on a copy stream; the
 // host lays out the rows meanwhile; K1 and K1b of a chunk start as soon as the chunk has landed, so at atlas scale
@@ -568,6 +644,7 @@ static int graph_create_impl(int device, int64_t n_cells, int64_t nnz, const int
     // ---- 5. what K1 found out
     int negative = 0;
     G_CUDA(cudaMemcpy(&negative, d_flag, sizeof(int), cudaMemcpyDeviceToHost));
+    if (negative & 4) return cleanup(CYP_E_INVALID, "cyp_graph_create: column index out of range [0, n_cells)");
     g->monotone = (negative & 1) ? 0 : 1;
     g->q16_ok = (negative == 0) ? 1 : 0;
     {

@@ -37,7 +37,7 @@ __device__ __forceinline__ int code12(CdfT c, int *bad) {
 
 template <typename CdfT>
 __global__ void __launch_bounds__(256)
-build_rows_v2_kernel(int64_t row_begin, int64_t row_end, const RowInfo *__restrict__ rows, const CdfT *__restrict__ cdf, const double *__restrict__ val,
+build_rows_v2_kernel(int64_t row_begin, int64_t row_end, int64_t n_cells, const RowInfo *__restrict__ rows, const CdfT *__restrict__ cdf, const double *__restrict__ val,
                      const int32_t *__restrict__ col, const uint32_t *__restrict__ word, const uint32_t *__restrict__ ebase,
                      int extra, unsigned char *__restrict__ rows2, uint32_t *__restrict__ edge4, int *__restrict__ bad_flag) {
     const int64_t r = row_begin + ((static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5);
@@ -62,7 +62,8 @@ build_rows_v2_kernel(int64_t row_begin, int64_t row_end, const RowInfo *__restri
         if (j < len) {
             code = code12<CdfT>(cdf[off + j], &bad);
             blk[kV2Header + j] = static_cast<unsigned char>(code >> 4);
-            e4[j] = word[col[off + j]];
+            const int32_t cc = col[off + j];
+            e4[j] = (cc >= 0 && cc < n_cells) ? word[cc] : 0u;         // a column out of range fails the create call (graph.cu)
         }
         const int lo = code & 15;
         const int lo_next = __shfl_down_sync(0xffffffffu, lo, 1);       // lane parity == entry parity (j0 is a multiple of 32)
@@ -87,7 +88,10 @@ build_rows_v2_kernel(int64_t row_begin, int64_t row_end, const RowInfo *__restri
     }
     uint32_t *inl = reinterpret_cast<uint32_t *>(blk + used);
     for (int j = lane; j < 64 && j < len; j += 32)
-        if ((mask >> j) & 1ull) inl[__popcll(mask & ((1ull << j) - 1ull))] = word[col[off + j]];
+        if ((mask >> j) & 1ull) {
+            const int32_t cc = col[off + j];
+            inl[__popcll(mask & ((1ull << j) - 1ull))] = (cc >= 0 && cc < n_cells) ? word[cc] : 0u;
+        }
     if (lane == 0) {
         *reinterpret_cast<int32_t *>(blk) = static_cast<int32_t>(r);
         *reinterpret_cast<uint16_t *>(blk + 4) = static_cast<uint16_t>(len);
@@ -202,10 +206,10 @@ cudaError_t v2_launch(cyp_graph *g, V2Build *b, int64_t row_begin, int64_t row_e
     const int threads = 256;
     const unsigned grid = static_cast<unsigned>((rows * 32 + threads - 1) / threads);
     if (g->cdf_mode == CYP_CDF_EXACT)
-        build_rows_v2_kernel<double><<<grid, threads, 0, stream>>>(row_begin, row_end, g->d_row, static_cast<const double *>(g->d_cdf), g->d_val,
+        build_rows_v2_kernel<double><<<grid, threads, 0, stream>>>(row_begin, row_end, g->n, g->d_row, static_cast<const double *>(g->d_cdf), g->d_val,
                                                                    g->d_col, g->d_word, b->d_ebase, b->extra, g->d_rows2, g->d_edge4, b->d_bad);
     else
-        build_rows_v2_kernel<float><<<grid, threads, 0, stream>>>(row_begin, row_end, g->d_row, static_cast<const float *>(g->d_cdf), g->d_val,
+        build_rows_v2_kernel<float><<<grid, threads, 0, stream>>>(row_begin, row_end, g->n, g->d_row, static_cast<const float *>(g->d_cdf), g->d_val,
                                                                   g->d_col, g->d_word, b->d_ebase, b->extra, g->d_rows2, g->d_edge4, b->d_bad);
     return cudaGetLastError();
 }
@@ -221,6 +225,7 @@ cudaError_t v2_finish(cyp_graph *g, V2Build *b, bool codes_ok) {
         g->v2_max_sectors = b->max_sectors;
         g->v2_slot_sectors = b->slot_sectors;
         g->v2_uniform = b->uniform;
+        g->rows2_bytes = static_cast<int64_t>(b->rows_bytes);
         g->device_bytes += static_cast<int64_t>(b->rows_bytes + sizeof(uint32_t) * 4 * (b->units + 1) + sizeof(uint32_t) * g->n);
         g->v2_ok = 1;
     }

@@ -225,15 +225,29 @@ __global__ void __launch_bounds__(CTAS == 2 ? 640 : (NW == 1 ? 1024 : 896), CTAS
                 const int lo = lds8(slot_k | ((static_cast<uint32_t>(jj >> 1) + lo0) & SMASK));
                 return (hi << 4) | ((lo >> ((jj & 1) * 4)) & 15);
             };
+            // The entries whose upper byte equals the key's form a short run (usually none or one).  Both candidates
+            // are read at once and the common outcomes -- the first decides, or it is below the key and the second
+            // above -- are taken without a branch: a `while` here makes the few lanes that need a second look run the
+            // loop body one lane at a time (ncu r02: 63 of 321 warp instructions per step).
+            const int c0 = j < len ? code_at(j) : 0x7fff;
+            const int c1 = j + 1 < len ? code_at(j + 1) : 0x7fff;
             if constexpr (CDFM == kModeExact) {
-                while (j < len) {
-                    const int code = code_at(j);
-                    if (code >= t_def) break;                        // certain crossing
-                    if (code == key && settle(j)) break;
-                    ++j;
+                if (c0 == key || (c0 < key && c1 <= key)) {          // an undecided compare, or a longer run: the general loop
+                    while (j < len) {
+                        const int code = code_at(j);
+                        if (code >= t_def) break;                    // certain crossing
+                        if (code == key && settle(j)) break;
+                        ++j;
+                    }
+                } else {
+                    j += c0 < key ? 1 : 0;
                 }
             } else {
-                while (j < len && code_at(j) < key) ++j;
+                if (c0 < key && c1 < key) {
+                    while (j < len && code_at(j) < key) ++j;
+                } else {
+                    j += c0 < key ? 1 : 0;
+                }
             }
             // ---- next row word
             if (j < len) {

@@ -19,13 +19,10 @@ per-process `np.random.rand` (:43); `num_cores` is accepted and ignored.
 from __future__ import annotations
 
 import math
-import os
-import sys
 import warnings
 
 import numpy as np
 from scipy import sparse
-from scipy.spatial.distance import cosine
 
 from . import _lib
 
@@ -46,17 +43,12 @@ def check_convergence_criteria(eps_history, tol=1e-5):
     return int(over[-1]) + 2
 
 
-def iterate_state_probability(adata, matrix_key="T_forward", init=None, stationary=None, max_iter=1000, tol=1e-5):
-    """Power iteration p <- p @ T with cosine distance to `stationary` (:62-87).  Returns
-    (history[:converged], history, converged) like the reference."""
-    T = adata.uns[matrix_key]
+def iterate_state_probability(adata, matrix_key="T_forward", init=None, stationary=None, max_iter=1000, tol=1e-5, *, device=0):
+    """Power iteration p <- p @ T with cosine distance to `stationary` (:62-87) on the GPU (K4).  Returns
+    (history[:converged], history, converged) like the reference; `sampling` itself only needs `converged` and never
+    materialises the [max_iter, n] history."""
     history = np.empty((max_iter, adata.shape[0]))
-    eps_history = np.empty(max_iter)
-    p = init
-    for i in range(max_iter):
-        history[i] = p
-        p = p @ T
-        eps_history[i] = cosine(p, stationary)
+    eps_history = _lib.power_iteration(adata.uns[matrix_key], init, stationary, max_iter, device, history=history)
     converged = check_convergence_criteria(eps_history, tol=tol)
     if isinstance(converged, int) and converged < max_iter:
         print("Tolerance reached after {} iterations of {}.".format(converged, max_iter))
@@ -64,27 +56,6 @@ def iterate_state_probability(adata, matrix_key="T_forward", init=None, stationa
         print("Max number ({}) of iterations reached.".format(max_iter))
         converged = max_iter
     return history[:converged], history, converged
-
-
-def _auto_max_steps(T, init, stationary, max_iter, tol, backend=None, device=0):
-    """The only thing `sampling` keeps from iterate_state_probability is its last element
-    (:275-278): max_steps.  The power iteration runs on the GPU (K4, cyp_power_iteration) without
-    the [max_iter, n] history buffer (1.6 GB at 1M cells); test backends without a device run the
-    reference's scipy expression."""
-    if backend is not None and hasattr(backend, "power_iteration"):
-        eps_history = backend.power_iteration(T, init, stationary, max_iter, device)
-    else:
-        eps_history = np.empty(max_iter)
-        p = np.asarray(init, dtype=np.float64)
-        for i in range(max_iter):
-            p = p @ T
-            eps_history[i] = cosine(p, stationary)
-    converged = check_convergence_criteria(eps_history, tol=tol)
-    if isinstance(converged, int) and converged < max_iter:
-        print("Tolerance reached after {} iterations of {}.".format(converged, max_iter))
-        return converged
-    print("Max number ({}) of iterations reached.".format(max_iter))
-    return max_iter
 
 
 # ------------------------------------------------------------------------------------ a7
@@ -125,70 +96,13 @@ def _listify(x):
     return x
 
 
-_NCCL_CONNECTED = False
-
-
-class _World:
-    """torch.distributed plumbing for walker sharding (one process per GPU).  World size 1
-    when torch.distributed is not initialised."""
-
-    def __init__(self, use_dist):
-        self.rank, self.size, self.dist, self.torch = 0, 1, None, None
-        if use_dist is False:
-            return
-        if use_dist == "auto" and "torch.distributed" not in sys.modules:
-            return                      # nobody initialised a process group: do not pay `import torch` (seconds)
-        try:
-            import torch
-            import torch.distributed as dist
-        except Exception:
-            if use_dist is True:
-                raise
-            return
-        if dist.is_available() and dist.is_initialized():
-            self.rank, self.size, self.dist, self.torch = dist.get_rank(), dist.get_world_size(), dist, torch
-            global _NCCL_CONNECTED
-            if self.size > 1 and not _NCCL_CONNECTED and dist.get_backend() == "nccl":
-                # NCCL connects its peer-to-peer transports at the first collective; if that happens after the graph
-                # and the trajectory buffers are allocated, the step kernel runs ~25 % slower (measured on 2 x B200,
-                # profiles/r01_multi_gpu_probe.md).  So: one tiny collective before anything is allocated.
-                dist.all_reduce(torch.zeros(1, device=torch.device("cuda", torch.cuda.current_device())))
-                torch.cuda.synchronize()
-                _NCCL_CONNECTED = True
-        elif use_dist is True:
-            raise RuntimeError("dist=True but torch.distributed is not initialised")
-
-    def all_gather_object(self, obj):
-        if self.size == 1:
-            return [obj]
-        out = [None] * self.size
-        self.dist.all_gather_object(out, obj)
-        return out
-
-    def device(self, idx):
-        backend = self.dist.get_backend() if self.size > 1 else "nccl"
-        return self.torch.device("cuda", idx) if backend == "nccl" else self.torch.device("cpu")
-
-
-class _DevPtr:
-    """Zero-copy view of raw device memory for torch (CUDA array interface v2)."""
-
-    def __init__(self, ptr, n_u64):
-        self.__cuda_array_interface__ = {"shape": (n_u64,), "typestr": "<i8", "data": (ptr, False), "version": 2}
-
-
-def _shard(n_walkers, rank, size):
-    """Contiguous block of walker ids for `rank` (lower ranks hold lower ids)."""
-    return (n_walkers * rank) // size, (n_walkers * (rank + 1)) // size
-
-
 # ------------------------------------------------------------------------------------ sampling
 def sampling(data, auto_adjust=True, matrix_key="T_forward", cluster_key="louvain", max_steps=10, min_sim_ratio=0.6,
              rounds_limit=10, traj_number=200, sim_number=500, end_point_probability=0.99, root_cell_probability=0.99,
              end_points=None, root_cells=None, end_clusters=None, root_clusters=None, min_clusters=2, max_iter=200,
              tol=1e-3, normalize=False, unique=True, num_cores=1, copy=False, *, seed=0, cdf_mode="reference",
-             device=None, dist="auto", _backend=None):
-    """Markov sampling of cell sequences from root cells to terminal regions on a B200.
+             device=None, devices=None, dist="auto", _backend=None, _group=None, _rows=True):
+    """Markov sampling of cell sequences from root cells to terminal regions on B200 GPUs.
 
     Positional arguments, defaults, errors and outputs are those of `cytopath.sampling`
     (reference cytopath/markov_chain_sampler.py:89-146).  Keyword-only extras:
@@ -202,11 +116,15 @@ def sampling(data, auto_adjust=True, matrix_key="T_forward", cluster_key="louvai
         -- at 1e9+ steps even a float32 rounding error of 1e-7 is hit, so pass normalize=True with float32
         matrices (the 3-decimal rounding of 'reference' mode closes such gaps by itself).
     device : int, optional
-        CUDA device; defaults to LOCAL_RANK under torchrun, else 0.
+        CUDA device of a single-GPU run (default 0; LOCAL_RANK under torchrun).
+    devices : sequence of int, optional
+        Several GPUs driven by THIS process -- a plain function call, no launcher: every round's walkers are cut
+        into one block per device, the graph is built on the first device and broadcast to the others over NVLink,
+        the devices exchange 24-byte records of the kept sequences with NCCL all-gathers (the reference's joblib
+        fan-out, :306-319).  The result is bit-identical for any number of devices.
     dist : 'auto' | bool
-        Shard every round's walkers over the ranks of an initialised torch.distributed
-        group (one process per GPU).  All ranks must call with the same arguments; all ranks
-        receive the same outputs.
+        One process per GPU (torchrun): every process calls `sampling` with the same arguments, every process
+        receives the same outputs.  'auto' uses an initialised torch.distributed group if there is one.
 
     Writes adata.uns['run_info'] and adata.uns['samples'] ('cell_sequences' int32,
     'transition_score' float32, 'cluster_sequences' <U8/<U32) and returns `adata` if `copy`.
@@ -227,39 +145,55 @@ def sampling(data, auto_adjust=True, matrix_key="T_forward", cluster_key="louvai
     except Exception:
         raise ValueError("Transition matrix must be of shape num_cells x num_cells")
 
-    world = _World(dist)
-    if device is None:
-        device = int(os.environ.get("LOCAL_RANK", "0")) if world.size > 1 else 0
     backend = _backend if _backend is not None else _lib
-
-    C = _canonical_csr(M)
-    n = C.shape[0]
-    if normalize:                                                          # :176-180
-        row_sums = _row_sums(C)
-        with np.errstate(divide="ignore", invalid="ignore"):
-            C = sparse.csr_matrix((C.data.astype(np.float64, copy=False) / np.repeat(row_sums, np.diff(C.indptr)),
-                                   C.indices, C.indptr), shape=C.shape)
-        C.eliminate_zeros()
-    # a1 (K1): upload + CDF build.  The row sums of the normalisation check (:181-187) come back from the
-    # same kernel, so the host never walks the 50M-entry value array.
-    graph = backend.Graph(C, _CDF_MODES[cdf_mode], device)
-    session = None
+    group = _group if _group is not None else backend.open_group(device=device, devices=devices, dist=dist)
     try:
+        C = _canonical_csr(M)
+        pristine = C is M                 # the stored matrix IS what is sampled from: K4 can reuse the graph's copy
+        if normalize:                                                          # :176-180
+            row_sums = _row_sums(C)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                C = sparse.csr_matrix((C.data.astype(np.float64, copy=False) / np.repeat(row_sums, np.diff(C.indptr)),
+                                       C.indices, C.indptr), shape=C.shape)
+            C.eliminate_zeros()
+            pristine = False
+        # a1 (K1): upload + CDF build on the group's first rank, broadcast of the device arrays to the others.  The
+        # row sums of the normalisation check (:181-187) come back from the same kernel, so the host never walks
+        # the 50M-entry value array.
+        timing = {"graph": group.create_graph(C, _CDF_MODES[cdf_mode])}
         if not normalize:
-            lo, hi = graph.row_sum_range() if hasattr(graph, "row_sum_range") else (lambda r: (r.min(), r.max()))(_row_sums(C))
+            lo, hi = group.graph.row_sum_range()
             if not (hi <= 1.0 + 1e-3 and lo >= 1.0 - 1e-3):
                 raise ValueError("Transition matrix has not been normalized. Either pass normalize==True or provide a row sum normalized matrix.")
-        return _sampling_on_graph(adata, copy, world, backend, graph, C, device, auto_adjust, matrix_key, cluster_key, max_steps,
+        return _sampling_on_graph(adata, copy, group, C, pristine, auto_adjust, matrix_key, cluster_key, max_steps,
                                   min_sim_ratio, rounds_limit, traj_number, sim_number, end_point_probability,
                                   root_cell_probability, end_points, root_cells, end_clusters, root_clusters, min_clusters,
-                                  max_iter, tol, unique, seed)
+                                  max_iter, tol, unique, seed, timing, _rows)
     finally:
-        graph.close()
+        if _group is None:
+            group.close()
 
 
-def _sampling_on_graph(adata, copy, world, backend, graph, C, device, auto_adjust, matrix_key, cluster_key, max_steps,
+def _auto_max_steps(group, T, pristine, init, stationary, max_iter, tol):
+    """The only thing `sampling` keeps from iterate_state_probability is its last element (:275-278): max_steps.
+    The power iteration runs on the GPU (K4) without the [max_iter, n] history buffer (1.6 GB at 1M cells): on the
+    matrix the graph already holds when that is the stored matrix, else on an upload of adata.uns[matrix_key]."""
+    if pristine:
+        eps_history = group.graph.power_iteration(init, stationary, max_iter)
+    else:
+        eps_history = group.power_iteration_matrix(T, init, stationary, max_iter)
+    converged = check_convergence_criteria(eps_history, tol=tol)
+    if isinstance(converged, int) and converged < max_iter:
+        print("Tolerance reached after {} iterations of {}.".format(converged, max_iter))
+        return converged
+    print("Max number ({}) of iterations reached.".format(max_iter))
+    return max_iter
+
+
+def _sampling_on_graph(adata, copy, group, C, pristine, auto_adjust, matrix_key, cluster_key, max_steps,
                        min_sim_ratio, rounds_limit, traj_number, sim_number, end_point_probability, root_cell_probability,
-                       end_points, root_cells, end_clusters, root_clusters, min_clusters, max_iter, tol, unique, seed):
+                       end_points, root_cells, end_clusters, root_clusters, min_clusters, max_iter, tol, unique, seed, timing,
+                       want_rows=True):
     """Everything of `sampling` after the transition matrix has been accepted (:189-412)."""
     n = C.shape[0]
     try:
@@ -311,15 +245,14 @@ def _sampling_on_graph(adata, copy, world, backend, graph, C, device, auto_adjus
         print("Number of required simulations per end point (traj_number) set to {}".format(traj_number))
         sim_number = math.ceil(traj_number * len(end_clusters_) * np.log2(n_roots + 1))
         print("Number of initial simulations (sim_number) set to {}".format(sim_number))
-        max_steps = _auto_max_steps(adata.uns[matrix_key],
+        max_steps = _auto_max_steps(group, adata.uns[matrix_key], pristine,
                                     (adata.obs["root_cells"] / adata.obs["root_cells"].sum()).values,
-                                    (adata.obs["end_points"] / adata.obs["end_points"].sum()).values, max_iter, tol,
-                                    backend, device)
+                                    (adata.obs["end_points"] / adata.obs["end_points"].sum()).values, max_iter, tol)
         print("Number of initial simulation steps (max_steps) set to {}".format(max_steps))
     max_steps = int(max_steps)
 
     # -- device-side state
-    trunc = np.array([c[:8] for c in clusters], dtype="U8")     # labels are stored into a U8 array (:39,:51)
+    trunc = _truncated_labels(adata.obs[cluster_key])            # labels are stored into a U8 array (:39,:51)
     code_names, cell_code = np.unique(trunc, return_inverse=True)
     # end-point slots: one slot per distinct end-point cell; the reference scans end points in
     # list order (:348-349, :390-391), duplicates in the list count twice.
@@ -327,27 +260,34 @@ def _sampling_on_graph(adata, copy, world, backend, graph, C, device, auto_adjus
     end_slot_of_cell = np.full(n, -1, dtype=np.int32)
     end_slot_of_cell[slot_cells] = np.arange(len(slot_cells), dtype=np.int32)
 
-    session = backend.Session(graph, roots, cell_code, len(code_names), int(min_clusters), end_slot_of_cell,
-                              len(slot_cells), max_steps, bool(unique), int(seed))
+    group.create_session(roots, cell_code, len(code_names), int(min_clusters), end_slot_of_cell,
+                         len(slot_cells), max_steps, bool(unique), int(seed))
+    return _run_rounds(adata, copy, group, roots, end_slot_of_point, end_point_clusters, end_clusters_, trunc,
+                       max_steps, traj_number, sim_number, min_sim_ratio, rounds_limit, timing, slot_cells, want_rows)
+
+
+def _truncated_labels(col) -> np.ndarray:
+    """Per-cell cluster label cut to 8 characters, as a '<U8' array: what markov_sim stores (:39,:51).  Done per
+    category, not per cell (a million Python string slices otherwise)."""
     try:
-        return _run_rounds(adata, copy, world, graph, session, roots, end_cells, end_slot_of_point, end_point_clusters,
-                           end_clusters_, trunc, max_steps, traj_number, sim_number, min_sim_ratio, rounds_limit,
-                           unique, device)
-    finally:
-        session.close()
+        cats = np.array([str(c)[:8] for c in col.cat.categories], dtype="U8")
+        codes = np.asarray(col.cat.codes)
+        if cats.size and codes.min() >= 0:
+            return cats[codes]
+    except Exception:
+        pass
+    return np.array([str(c)[:8] for c in np.asarray(col.astype(str).values, dtype=object)], dtype="U8")
 
 
-def _run_rounds(adata, copy, world, graph, session, roots, end_cells, end_slot_of_point, end_point_clusters,
-                end_clusters_, trunc, max_steps, traj_number, sim_number, min_sim_ratio, rounds_limit, unique, device):
+def _run_rounds(adata, copy, group, roots, end_slot_of_point, end_point_clusters, end_clusters_, trunc, max_steps,
+                traj_number, sim_number, min_sim_ratio, rounds_limit, timing, slot_cells, want_rows=True):
     n_roots = len(roots)
     n_slots = int(end_slot_of_point.max()) + 1
     sim_number_ = max(int(sim_number / n_roots), 1)                    # :285
     # per terminal cluster: the end-point slots in the order the reference scans them
     cluster_slots = [end_slot_of_point[end_point_clusters == name] for name in end_clusters_]
 
-    # global index of the kept rows, accumulation order (:335-340): per round, per rank, walker order
-    g_owner, g_local_row, g_slot = [], [], []
-    slot_counts = np.zeros(n_slots, dtype=np.int64)
+    slot_counts = np.zeros(n_slots, dtype=np.int64)                   # kept sequences per end point, all rounds
     traj_num = [0]
     count = 0
     stats = []
@@ -357,24 +297,12 @@ def _run_rounds(adata, copy, world, graph, session, roots, end_cells, end_slot_o
         rnd = count
         count += 1
         sim_number_ *= 2                                              # :299
-        total = n_roots * sim_number_
-        w0, w1 = _shard(total, world.rank, world.size)
-        row0 = session.rows()
-        st = session.round(rnd, sim_number_, w0, w1)
-        if world.size > 1 and unique:
-            _prune_across_ranks(world, session, device)
-        _, walker, slot = session.fetch_index(row0)
-        st["n_kept"] = int(len(walker))
+        # a2 + a3 + a6: K2, K3, the cross-rank first-occurrence prune; what comes back is the histogram of the
+        # end points of the sequences this round kept (:341-354) -- the sequences stay on the devices as records
+        st, counts = group.round(rnd, sim_number_)
         stats.append(st)
-        round_slots = []
-        for r, (r0, sl) in enumerate(world.all_gather_object((row0, slot))):   # rank order = walker order
-            g_owner.append(np.full(len(sl), r, dtype=np.int32))
-            g_local_row.append(np.arange(r0, r0 + len(sl), dtype=np.int64))
-            g_slot.append(sl)
-            round_slots.append(sl)
-        round_slots = np.concatenate(round_slots)
-        slot_counts += np.bincount(round_slots, minlength=n_slots)
-        traj_num = [int(slot_counts[cs].sum()) for cs in cluster_slots]   # :341-354 (list duplicates count twice)
+        slot_counts += counts
+        traj_num = [int(slot_counts[cs].sum()) for cs in cluster_slots]   # list duplicates count twice, like :348-349
 
         ratio_obtained = np.round(sum(traj_num) / (sim_number_ * n_roots), 6)      # :357-358
         ratio_min = np.round(min(traj_num) / traj_number, 4)
@@ -388,81 +316,40 @@ def _run_rounds(adata, copy, world, graph, session, roots, end_cells, end_slot_o
             print("{} % of simulations reached atleast one endpoint. Generating {} additional samples.".format(np.round(ratio_obtained * 100, 4), sim_number_))
     print("Sampling done.")
 
-    # -- final selection (:378-403).  Candidates of a terminal cluster are ordered by end point
-    # (list order), then by accumulation order; the draw is np.random.randint with replacement.
-    owner = np.concatenate(g_owner) if g_owner else np.empty(0, np.int32)
-    local_row = np.concatenate(g_local_row) if g_local_row else np.empty(0, np.int64)
-    slot_all = np.concatenate(g_slot) if g_slot else np.empty(0, np.int32)
-    order = np.argsort(slot_all, kind="stable")                       # accumulation order inside each slot
-    starts = np.concatenate([[0], np.cumsum(np.bincount(slot_all, minlength=n_slots))])
-    picked = []
+    # -- final selection (:378-403).  The candidates of a terminal cluster are ordered by end point (list order), then
+    # by accumulation order; the draw is np.random.randint with replacement from the global numpy RNG.  Candidate
+    # idx of a cluster is the (idx - first candidate of its end point)-th kept sequence of that end point: the
+    # devices resolve that against their index and replay the sequences.  With several processes rank 0 draws and
+    # the others receive its numbers (their own global RNGs are not seeded alike).
+    pick_slot, pick_off = [], []
     for cs in cluster_slots:
-        cand = np.concatenate([order[starts[s]:starts[s + 1]] for s in cs]) if len(cs) else np.empty(0, np.int64)
-        idx_range = np.random.randint(cand.shape[0], size=traj_number)    # :395
-        picked.append(cand[idx_range])
-    picked = np.concatenate(picked)
-
-    cell_sequences = _collect_rows(world, session, owner[picked], local_row[picked], max_steps, device)
+        ends = np.cumsum(slot_counts[cs])
+        draw = np.empty(traj_number, dtype=np.int64)
+        if group.rank == 0:
+            draw[:] = np.random.randint(int(ends[-1]) if len(ends) else 0, size=traj_number)    # :395
+        if group.world > 1:
+            group.broadcast(draw)
+        k = np.searchsorted(ends, draw, side="right")
+        pick_slot.append(cs[k])
+        pick_off.append(draw - (ends[k] - slot_counts[cs][k]))
+    pick_slot, pick_off = np.concatenate(pick_slot), np.concatenate(pick_off)
     adata.uns["run_info"]["simulation_steps"] = max_steps             # :406-407
     adata.uns["run_info"]["didrun"] = True
+    if not want_rows:
+        # a caller that only looks at where the selected sequences END (utils.undirected_simulations, utils.py:92):
+        # the last cell of a pick is its end point, so no sequence has to be produced at all
+        adata.uns["run_info"]["b200"] = {"rounds": stats, "world_size": group.world, "timing": timing,
+                                         "final_cells": slot_cells[pick_slot].astype(np.int32),
+                                         "kernel": group.graph.variant_name() if hasattr(group.graph, "variant_name") else ""}
+        return adata if copy else None
+    cell_sequences, scores, sel = group.select(pick_slot, pick_off)
+
     width = "U8" if n_roots == 1 else "U32"                           # markov_sim's own array (:39) vs the copy at :312
     adata.uns["samples"] = {
         "cell_sequences": cell_sequences,
-        "transition_score": graph.transition_scores(cell_sequences),
+        "transition_score": scores,
         "cluster_sequences": trunc[cell_sequences].astype(width),
     }
-    adata.uns["run_info"]["b200"] = {"rounds": stats, "world_size": world.size,
-                                     "kernel": graph.variant_name() if hasattr(graph, "variant_name") else ""}
+    adata.uns["run_info"]["b200"] = {"rounds": stats, "world_size": group.world, "select": sel, "timing": timing,
+                                     "kernel": group.graph.variant_name() if hasattr(group.graph, "variant_name") else ""}
     return adata if copy else None
-
-
-def _prune_across_ranks(world, session, device):
-    """Global first-occurrence de-duplication: all-gather the (hash, walker) records of the
-    rows every rank kept this round and drop local rows that lose to a lower walker id."""
-    torch, dist = world.torch, world.dist
-    ptr, n_local = session.round_records()
-    counts = world.all_gather_object(n_local)
-    n_max = max(counts)
-    if n_max == 0:
-        return
-    dev = world.device(device)
-    if dev.type == "cuda":
-        local = torch.zeros(n_max * 3, dtype=torch.int64, device=dev)
-        if n_local:
-            local[: n_local * 3] = torch.as_tensor(_DevPtr(ptr, n_local * 3), device=dev)
-    else:                                                              # gloo test backends hand out host arrays
-        local = torch.zeros(n_max * 3, dtype=torch.int64)
-        if n_local:
-            local[: n_local * 3] = torch.from_numpy(np.asarray(ptr).view(np.int64).reshape(-1))
-    gathered = [torch.empty_like(local) for _ in range(world.size)]
-    dist.all_gather(gathered, local)
-    flat = torch.cat([g[: c * 3] for g, c in zip(gathered, counts)])
-    n_all = int(sum(counts))
-    if dev.type == "cuda":
-        torch.cuda.synchronize(dev)
-        session.round_prune(flat.data_ptr(), n_all)
-    else:
-        session.round_prune(flat.numpy().view(np.uint64), n_all)
-
-
-def _collect_rows(world, session, owner, local_row, max_steps, device):
-    """Every rank gathers the selected rows it owns from its device store; the pieces are
-    exchanged with an all-gather so every rank ends up with the full output."""
-    mine = np.flatnonzero(owner == world.rank)
-    part = session.fetch_rows(local_row[mine])
-    if world.size == 1:
-        return part
-    torch, dist = world.torch, world.dist
-    dev = world.device(device)
-    counts = world.all_gather_object(len(mine))
-    n_max = max(max(counts), 1)
-    local = torch.zeros((n_max, max_steps), dtype=torch.int32, device=dev)
-    if len(mine):
-        local[: len(mine)] = torch.from_numpy(part).to(dev)
-    gathered = [torch.empty_like(local) for _ in range(world.size)]
-    dist.all_gather(gathered, local)
-    out = np.empty((len(owner), max_steps), dtype=np.int32)
-    for r in range(world.size):
-        pos = np.flatnonzero(owner == r)
-        out[pos] = gathered[r][: counts[r]].cpu().numpy()
-    return out

@@ -92,11 +92,17 @@ int cyp_graph_build_ms(const cyp_graph *g, float *ms);
  * adata.uns[matrix_key] (any column order; it is transposed on the device);
  * h_eps_history[i] = cosine distance between p after iteration i+1 and h_stationary (:73-76).
  * The caller derives max_steps with check_convergence_criteria (:54-60).
- * h_final_state (may be NULL) receives p after the last iteration. */
+ * h_final_state (may be NULL) receives p after the last iteration; h_history (may be NULL) is double [max_iter, n_cells]
+ * and receives p BEFORE every iteration (the `state_history` the reference returns, :65,:71). */
 int cyp_power_iteration(int device, int64_t n_cells, int64_t nnz, const int64_t *h_row_ptr,
                         const int32_t *h_col, const double *h_val, const double *h_init,
                         const double *h_stationary, int32_t max_iter, double *h_eps_history,
-                        double *h_final_state);
+                        double *h_final_state, double *h_history);
+
+/* Same on the matrix a graph already holds in HBM (no second upload): valid when adata.uns[matrix_key] is the canonical
+ * matrix the graph was built from. */
+int cyp_graph_power_iteration(const cyp_graph *g, const double *h_init, const double *h_stationary, int32_t max_iter,
+                              double *h_eps_history, double *h_final_state);
 
 /* ---- a2: markov_sim (markov_chain_sampler.py:35-52) --------------------------------
  * Walkers [walker_begin, walker_begin + n_walkers) of one round, each starting at
@@ -183,6 +189,69 @@ int cyp_session_fetch_rows(const cyp_session *s, const int64_t *h_rows, int64_t 
 int cyp_session_round_records(const cyp_session *s, uint64_t **d_records, int64_t *n_records);
 int cyp_session_round_prune(cyp_session *s, const uint64_t *d_all_records, int64_t n_all, int64_t *n_dropped);
 
+/* ---- a6 / multi-GPU: the joblib fan-out over root cells (markov_chain_sampler.py:306-319) as a group of devices ----
+ * A group shares one sampling() run: the walkers of every round are cut into contiguous id blocks, one per rank, the
+ * graph is replicated, and the ranks exchange 24-byte records of kept sequences over NCCL (all-gather), never rows.
+ * Two ways to form one: in ONE process that drives n devices (cyp_group_create_local: ncclCommInitAll, one host thread
+ * per device inside each call -- the boundary is a notebook function call), or one process per GPU
+ * (cyp_group_unique_id on rank 0, the 128 bytes sent to the others by any means, cyp_group_create_rank everywhere).
+ * A group of one device needs no NCCL and does not load it.  All ranks make the same calls with the same arguments. */
+typedef struct cyp_group cyp_group;
+int cyp_group_create_local(int n_devices, const int *devices, cyp_group **out);
+int cyp_group_unique_id(uint8_t *id128);
+int cyp_group_create_rank(const uint8_t *id128, int rank, int world, int device, cyp_group **out);
+int cyp_group_destroy(cyp_group *g);
+int cyp_group_info(const cyp_group *g, int *world, int *n_local, int *first_rank, int *nccl_version);
+/* The graph / session of the i-th local device (owned by the group). */
+cyp_graph *cyp_group_graph(const cyp_group *g, int local_index);
+cyp_session *cyp_group_session(const cyp_group *g, int local_index);
+/* a1 for a group: the rank `root_rank` builds the graph from its host CSR (cyp_graph_create / _f32; the other ranks
+ * may pass NULL arrays) and its device arrays are broadcast to every other device (ncclBroadcast over NVLink) instead
+ * of one host upload per GPU.  ms_build / ms_broadcast (may be NULL): host wall time of the two phases. */
+int cyp_group_graph_create(cyp_group *g, int64_t n_cells, int64_t nnz, const int64_t *h_row_ptr, const int32_t *h_col,
+                           const void *h_val, int val_is_f32, int cdf_mode, int root_rank, float *ms_build, float *ms_broadcast);
+/* cyp_session_create on every local device (same arguments on all ranks). */
+int cyp_group_session_create(cyp_group *g, const int32_t *h_root_cells, int64_t n_roots, const int32_t *h_cell_code,
+                             int32_t n_codes, int32_t min_clusters, const int32_t *h_end_slot_of_cell, int32_t n_end_slots,
+                             int32_t max_steps, int unique, uint64_t seed);
+
+typedef struct cyp_group_round_stats {
+    int64_t n_walkers, n_pass_clusters, n_terminal;   /* sums over all ranks */
+    int64_t n_kept;            /* sequences the round added to the global index (after the cross-rank first-occurrence prune) */
+    int64_t n_nocrossing, n_replayed;
+    int64_t total_rows;        /* global index size after this round */
+    int64_t exchange_bytes;    /* bytes every rank received through the round's all-gathers */
+    float ms_walk, ms_filter;  /* max over ranks of the device times of K2 / K3 */
+    float ms_local;            /* host wall time of the local rounds */
+    float ms_exchange;         /* host wall time of the cross-rank part: all-gathers, prune, index update */
+    int32_t n_chunks, dedup_passes;
+} cyp_group_round_stats;
+
+/* One sampling round (:299-354) over the whole group: rank r walks walkers [total r / world, total (r+1) / world) of
+ * the round's n_roots * sims_per_root, the first occurrence of every sequence survives group-wide, and every rank ends
+ * up with the global index of kept sequences (round, walker, end-point slot) in accumulation order (:335-340).
+ * h_slot_counts (may be NULL): int64 [n_end_slots], how many of the sequences this round added end on each end point. */
+int cyp_group_round(cyp_group *g, uint32_t round, int64_t sims_per_root, int64_t *h_slot_counts, cyp_group_round_stats *stats);
+int cyp_group_rows(const cyp_group *g, int64_t *n_rows);
+int cyp_group_fetch_index(const cyp_group *g, int64_t row_begin, int64_t n_rows, int32_t *h_round, int64_t *h_walker, int32_t *h_slot);
+/* Order-sensitive 128-bit digest of the global index: equal on every rank and for every way of cutting the rounds. */
+int cyp_group_digest(const cyp_group *g, uint64_t *digest2);
+
+typedef struct cyp_group_select_stats {
+    int64_t gather_bytes;      /* bytes of the all-gather of the selected sequences */
+    float ms_locate_replay, ms_gather, ms_fetch;
+} cyp_group_select_stats;
+
+/* The final draw's rows (:395-403).  Pick k is the h_offset[k]-th kept sequence, in accumulation order, that ends on
+ * end point h_slot[k] (:386-394).  The picks are split over the ranks, each rank replays its share, the int32
+ * sequences are all-gathered, and h_seq [n_pick, max_steps] (+ h_score [n_pick], the transition scores of :50,:52, may
+ * be NULL) are returned on every process. */
+int cyp_group_select(cyp_group *g, int64_t n_pick, const int32_t *h_slot, const int64_t *h_offset, int32_t *h_seq, float *h_score,
+                     cyp_group_select_stats *stats);
+int cyp_group_set_chunk_walkers(cyp_group *g, int64_t walkers);
+/* Host bytes of rank `root_rank` to every process of the group (e.g. the indices rank 0 drew with np.random, :395). */
+int cyp_group_broadcast_bytes(cyp_group *g, void *h_buf, int64_t n_bytes, int root_rank);
+
 /* Walkers per chunk of a round (0 = as many as the free HBM allows).  A round larger than a chunk is
  * walked piecewise; the first-occurrence de-duplication is then completed across the chunks, so the
  * result does not depend on the chunk size. */
@@ -195,6 +264,11 @@ int cyp_session_set_chunk_walkers(cyp_session *s, int64_t walkers);
  * as in the `hausdorff` package the reference calls.  kernel_ms (may be NULL): device time. */
 int cyp_hausdorff_matrix(int device, const double *h_coords, int64_t n_chains, int32_t chain_len, int32_t dim,
                          int metric, double *h_out, float *kernel_ms);
+
+/* Measurement aid (bench.py roofline.gather_ceiling_frac): gathers/s the device sustains for independent random reads
+ * of gather_bytes (32 / 64 / 128 / 256) contiguous bytes out of a working set of working_set_bytes -- the step kernel's
+ * access pattern without the dependency between a walker's steps. */
+int cyp_gather_ceiling(int device, int64_t working_set_bytes, int32_t gather_bytes, double *gathers_per_s);
 
 /* test hook: keep only the low `bits` bits of the 128-bit sequence hash (forces collisions) */
 int cyp_session_set_hash_bits(cyp_session *s, int bits);

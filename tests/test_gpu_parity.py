@@ -209,6 +209,31 @@ def test_k4_power_iteration_matches_scipy():
         assert check_convergence_criteria(got, tol=1e-3) == check_convergence_criteria(want, tol=1e-3)
 
 
+def test_k4_iterate_state_probability_returns_the_reference_history():
+    """The drop-in of iterate_state_probability (:62-87): state history bit-equal to the scipy loop, same `converged`;
+    and K4 on the matrix a graph already holds (no second upload) gives the same eps history."""
+    from scipy.spatial.distance import cosine
+    from cytopath_b200.sampler import iterate_state_probability, check_convergence_criteria
+    g = synth.branching_graph(n=300, k=10, n_branches=2, seed=5, workers=1)
+    ad = g.to_adata()
+    init = (ad.obs["root_cells"] / ad.obs["root_cells"].sum()).values
+    stat = (ad.obs["end_points"] / ad.obs["end_points"].sum()).values
+    h, full, c = run_quiet(iterate_state_probability, ad, init=init, stationary=stat, max_iter=50, tol=1e-3)
+    assert full.shape == (50, 300) and h.shape[0] == c
+    p, eps = init, np.empty(50)
+    for i in range(50):
+        np.testing.assert_array_equal(full[i], p)
+        p = p @ ad.uns["T_forward"]
+        eps[i] = cosine(p, stat)
+    want = check_convergence_criteria(eps, tol=1e-3)
+    assert c == (want if isinstance(want, int) and want < 50 else 50)
+    C = sp.canonical_csr(g.T)
+    graph = _lib.Graph(C, _lib.CDF_REFERENCE)
+    np.testing.assert_allclose(graph.power_iteration(init, stat, 50), eps, rtol=0, atol=1e-13)
+    np.testing.assert_array_equal(graph.power_iteration(init, stat, 50), _lib.power_iteration(C, init, stat, 50))
+    graph.close()
+
+
 # ---- K2 ---------------------------------------------------------------------------------
 def test_k2_matches_reference_markov_sim_golden():
     z = load("markov_sim_small")
@@ -506,6 +531,13 @@ def test_k3_round_filters_and_dedup_vs_oracle(hash_bits, n_codes, chunk):
     s.close(); g.close()
 
 
+class _DevPtr:
+    """Zero-copy view of raw device memory for torch (CUDA array interface v2)."""
+
+    def __init__(self, ptr, n_u64):
+        self.__cuda_array_interface__ = {"shape": (n_u64,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+
+
 def test_k3_not_unique_keeps_duplicates_and_sharded_prune():
     C = sp.canonical_csr(synth.branching_graph(n=80, k=4, n_branches=2, seed=5, workers=1, scale=2.0, noise=0.05).T)
     n = C.shape[0]
@@ -528,7 +560,7 @@ def test_k3_not_unique_keeps_duplicates_and_sharded_prune():
     recs = []
     for sess in (sa, sb):
         p, m = sess.round_records()
-        recs.append(torch.as_tensor(cytopath_b200.sampler._DevPtr(p, m * 3), device="cuda").clone())
+        recs.append(torch.as_tensor(_DevPtr(p, m * 3), device="cuda").clone())
     allr = torch.cat(recs)
     torch.cuda.synchronize()
     da = sa.round_prune(allr.data_ptr(), allr.numel() // 3)

@@ -15,7 +15,7 @@ from scipy import sparse
 
 import cytopath_b200
 from cytopath_b200 import synth
-from cytopath_b200.sampler import _canonical_csr, check_convergence_criteria, iterate_state_probability
+from cytopath_b200.sampler import _canonical_csr, check_convergence_criteria
 from tests import oracle_backend
 from tests.helpers import SAMPLING_CASES, adata_from_case, load
 
@@ -185,12 +185,6 @@ def test_convergence_helpers():
     for i, want in enumerate(z["result"]):
         got = check_convergence_criteria(z["p%d" % i], tol=1e-3)
         assert (-1 if got is None else got) == want
-    g, ad = small_adata()
-    init = (ad.obs["root_cells"] / ad.obs["root_cells"].sum()).values
-    stat = (ad.obs["end_points"] / ad.obs["end_points"].sum()).values
-    h, full, c = run_quiet(iterate_state_probability, ad, init=init, stationary=stat, max_iter=50, tol=1e-3)
-    assert full.shape == (50, 300) and h.shape[0] == c
-    np.testing.assert_array_equal(full[0], init)
 
 
 # ---- multi-rank sharding over gloo (world_size 2), CPU -----------------------------------
@@ -205,7 +199,8 @@ from tests.helpers import adata_from_case, load
 dist.init_process_group("gloo")
 z = load({case!r})
 ad, kw = adata_from_case(z)
-np.random.seed(int(z["np_seed"]))
+# only rank 0 has the golden run's numpy seed: the final draw (:395) must come from rank 0 on every rank
+np.random.seed(int(z["np_seed"]) + 7919 * dist.get_rank())
 with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
     warnings.simplefilter("ignore")
     cytopath_b200.sampling(ad, **kw, seed=int(z["seed"]), _backend=oracle_backend)
