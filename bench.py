@@ -33,9 +33,11 @@ WORKLOADS = {
     "c2": dict(n=5_780, k=30, branches=5, stems=2, walkers=710_000, max_steps=200, desc="configs[1] graph: 5,780 cells k=30, 200 steps"),
     "c3": dict(n=100_000, k=30, branches=8, stems=1, walkers=1_000_000, max_steps=200, desc="configs[2]: 100k cells k=30, 1M walkers x 200 steps (L2-resident)"),
     "c4": dict(n=1_000_000, k=50, branches=8, stems=1, layers=16, walkers=1_250_000, max_steps=500,
-               desc="configs[3]: 1M cells k=50 (51M nnz), 10M walkers x 500 steps / 8 GPUs = 1.25M walkers per GPU (HBM-bound)"),
-    "c5": dict(n=250_000, k=200, branches=0, stems=1, walkers=1_250_000, max_steps=200,
-               desc="configs[4]-shaped: cycling + convergent graph, 250k cells k=200 (50M nnz, long rows), 1.25M walkers x 200 steps per GPU"),
+               desc="configs[3]: 1M cells k=50 (51M nnz), 10M walkers x 500 steps / 8 GPUs = 1.25M walkers per GPU (HBM-bound); branching "
+                    "graph of SURVEY 8d with 8 branches x 16 interleaved kNN layers instead of B=16 (terminals stay reachable in 500 steps)"),
+    "c5": dict(n=250_000, k=200, branches=0, stems=1, walkers=1_250_000, max_steps=200, api_walkers_per_gpu=12_500_000,
+               desc="configs[4]: cycling + convergent graph with self-loops, 250k cells k=200 (50M nnz, long rows), roots / end points from the 0.99 "
+                    "probability thresholds; kernel loop 1.25M walkers x 200 steps per GPU, e2e_api 12.5M walkers per GPU (100M on 8 GPUs)"),
     "tiny": dict(n=20_000, k=30, branches=4, stems=1, walkers=100_000, max_steps=100, desc="developer smoke size"),
 }
 
@@ -220,6 +222,13 @@ def cpu_baseline_sample(C, g, roots, max_steps, cdf_mode, budget_s=12.0):
              "sample": "oracle/walk.c, %.2f s" % c_dt})
 
 
+def base_config(w, args, nnz=None):
+    """The workload, with the same keys in both arms (the driver compares them)."""
+    W = args.walkers or w["walkers"]
+    return {"workload": w["desc"], "cells": w["n"], "k": w["k"], "nnz": nnz, "walkers_per_gpu": W, "max_steps": w["max_steps"],
+            "cdf_mode": args.cdf_mode, "seed": args.seed}
+
+
 def run_reference(args, w):
     """Reference arm: the reference's CPU algorithm for this path (joblib fan-out of the
     pure-Python step loop, markov_chain_sampler.py:35-52,:306-308) on all host cores."""
@@ -250,7 +259,7 @@ def run_reference(args, w):
         "impl": "reference", "metric": "walker_steps_per_sec", "value": value, "unit": "walker-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if mode else "f32", "data": "synthetic",
-        "config": {"workload": w["desc"], "cells": w["n"], "k": w["k"], "max_steps": max_steps, "cdf_mode": args.cdf_mode},
+        "config": base_config(w, args, int(C.nnz)),
         "cpu_baseline": {"value": value, "unit": "walker-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "walker-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -258,20 +267,43 @@ def run_reference(args, w):
     emit(line)
 
 
+def kernel_sass_sha16(kernel_name):
+    """Identity of the step kernel's machine code: sha256 of the SASS of the object file that holds it (cuobjdump; the
+    object bytes themselves are not reproducible, their SASS is).  profiles/ncu_traffic.json stores the same hash next
+    to every capture, so a capture only feeds `roofline` while the kernel it measured is the kernel that runs."""
+    import hashlib
+    obj = "walk_v2_exact.o" if "q12/f64" in kernel_name else "walk_v2_ref.o" if "q12/f32" in kernel_name else "walk_tma.o"
+    path = os.path.join(ROOT, "cytopath_b200", "lib", "obj", obj)
+    try:
+        out = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True, timeout=120).stdout
+    except Exception:
+        return None
+    keep = [l for l in out.splitlines() if l.strip() and not any(k in l for k in ("Fatbin", "===", "arch =", "code version", "host =", "compile_size", "identifier", "producer"))]
+    return hashlib.sha256("\n".join(keep).encode()).hexdigest()[:16] if keep else None
+
+
+def pinned_csr(C):
+    """The CSR arrays in page-locked host memory (what a caller that cares about upload time would hand over)."""
+    import torch
+    from scipy import sparse
+    ptr_ = torch.from_numpy(np.ascontiguousarray(C.indptr, dtype=np.int64)).pin_memory()
+    col = torch.from_numpy(np.ascontiguousarray(C.indices, dtype=np.int32)).pin_memory()
+    val = torch.from_numpy(np.ascontiguousarray(C.data, dtype=np.float64)).pin_memory()
+    P = sparse.csr_matrix((val.numpy(), col.numpy(), ptr_.numpy()), shape=C.shape, copy=False)
+    return P, (ptr_, col, val)
+
+
 def run_b200(args, w):
     import torch
     import torch.distributed as dist
+    import cytopath_b200
     from cytopath_b200 import _lib
 
     rank, local_rank, world = env_world()
-    no_dist = bool(os.environ.get("BENCH_NO_DIST"))          # diagnostic: ranks run unsynchronised, no NCCL
-    if world > 1 and not no_dist:
+    if world > 1:
         os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep NCCL's version banner off stdout (one JSON line only)
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        # Connect the NCCL transports NOW, before the graph and the trajectory buffers exist: when the first collective
-        # runs after those allocations, NCCL's peer-to-peer set-up re-maps them and K2 runs 25-28 % slower
-        # (13.5 vs 10.5 ms per step on both ranks, profiles/r01_multi_gpu_probe.md).
         dist.barrier()
         torch.cuda.synchronize()
     dev = torch.device("cuda", local_rank)
@@ -280,7 +312,22 @@ def run_b200(args, w):
     L = _lib.load()
     mode = _lib.CDF_EXACT if args.cdf_mode == "exact" else _lib.CDF_REFERENCE
 
-    g, C, roots = make_graph(w, world)
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    # The group first: its NCCL communicator (ncclCommInitRank; the id travels through torch's store) connects its
+    # transports before the graph and the round buffers are allocated (profiles/r01_multi_gpu_probe.md).
+    group = _lib.open_group(device=local_rank, dist=world > 1)
+    assert group.world == world and group.rank == rank
+
+    # rank 0 generates (or loads) the synthetic graph; the others read it from the cache it leaves behind
+    os.environ.setdefault("BENCH_GRAPH_CACHE", "/tmp/cyp_bench_graphs")
+    if rank == 0:
+        g, C, roots = make_graph(w, 1)
+    barrier()
+    if rank != 0:
+        g, C, roots = make_graph(w, 1)
     max_steps, nt = w["max_steps"], w["max_steps"] - 1
     W = args.walkers or w["walkers"]
     total = W * world
@@ -288,12 +335,10 @@ def run_b200(args, w):
     sims_per_root = -(-total // n_roots)
     w0 = rank * W
 
-    def barrier():
-        if world > 1 and not no_dist:
-            dist.barrier()
-
-    # ---- resident state: graph (K1), roots, trajectory buffer
-    graph = _lib.Graph(C, mode, local_rank)
+    # ---- resident state: graph (K1 on rank 0 + NVLink broadcast), roots, trajectory buffer
+    Cp, _pins = pinned_csr(C) if rank == 0 else (None, None)
+    gstat = group.create_graph(Cp, mode, 0, shape=(C.shape[0], C.nnz))
+    graph = group.graph
     info = graph.info()
     kernel_name = graph.variant_name(args.variant)
     d_roots = torch.tensor(roots, dtype=torch.int32, device=dev)
@@ -328,7 +373,7 @@ def run_b200(args, w):
     if world > 1:
         print("rank %d: %.3f ms per step (device time of its own K2 launches)" % (rank, ms / args.steps), file=sys.stderr)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1 and not no_dist:
+    if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     value = total * nt * args.steps / (ms_max * 1e-3)
@@ -342,34 +387,71 @@ def run_b200(args, w):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
     else:
         peak, peak_src = 6650.0, "fallback of B200_PROFILING.md"
-    achieved = W * nt * bytes_per_step / (ms_launch * 1e-3) / 1e9
-    # bytes the default kernel actually requests per walker-step (sector granular): the staged row + one edge-record sector + the store
-    inline_cov = None
+    alg_achieved = W * nt * bytes_per_step / (ms_launch * 1e-3) / 1e9
+    lay = graph.layout()
+    inline_cov, layout_bytes = None, None
     if "fused rows" in kernel_name:
-        block_bytes, inline_cov = fused_layout_stats(C, sample, graph.layout()["row_block_bytes"])
+        block_bytes, inline_cov = fused_layout_stats(C, sample, lay["row_block_bytes"])
         layout_bytes = block_bytes + (1.0 - inline_cov) * 32.0 + 4.0      # row block + a target-word sector when not inlined + the store
-    else:
-        row_elem = 2 if "q16" in kernel_name else elem
-        layout_bytes = np.ceil(row_elem * kbar / 32.0) * 32.0 + 32.0 + 4.0
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tpath):
-        rec = json.load(open(tpath)).get("%s|%s" % (args.workload, kernel_name))
-        if rec and W == w["walkers"]:
-            traffic = rec["dram_bytes_read"] + rec["dram_bytes_write"]
     assert int(d_miss.item()) == 0, "walkers hit rows without a CDF crossing"
 
     if args.kernel_only:
         if rank == 0:
             emit({"metric": "walker_steps_per_sec", "value": value, "ms_per_step": ms_max / args.steps,
-                  "kernel": kernel_name, "roofline_frac": achieved / peak, "kernel_only": True})
-        if world > 1 and not no_dist:
+                  "kernel": kernel_name, "algorithmic_frac": alg_achieved / peak, "kernel_only": True,
+                  "kernel_sass_sha16": kernel_sass_sha16(kernel_name)})
+        group.close()
+        if world > 1:
             dist.destroy_process_group()
         return
-    # ---- e2e through the C ABI with host buffers (pinned), every step: upload CSR + K1 + round (K2+K3) + read-back
-    row_ptr = torch.from_numpy(np.ascontiguousarray(C.indptr, dtype=np.int64)).pin_memory()
-    col = torch.from_numpy(np.ascontiguousarray(C.indices, dtype=np.int32)).pin_memory()
-    val = torch.from_numpy(np.ascontiguousarray(C.data, dtype=np.float64)).pin_memory()
+
+    # ---- the roofline the kernel cannot beat: measured DRAM / L2 traffic of the committed ncu capture (only while the
+    # kernel's machine code is the captured one) and the device's random-gather ceiling at the same footprint, measured now
+    roof = {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src, "ms_per_launch": ms_launch,
+            "algorithmic_equiv": {"achieved": alg_achieved, "frac": alg_achieved / peak, "bytes_per_walker_step": bytes_per_step,
+                                  "mean_visited_row_nnz": kbar,
+                                  "note": "SURVEY 8d's bytes (the full float64/float32 CDF row + 16 B per step) over the launch time: "
+                                          "what a kernel reading the reference's layout would have to move; the fused rows (12-bit codes, "
+                                          "inlined targets) request layout_bytes_per_walker_step instead, so this is not a bound"},
+            "layout_bytes_per_walker_step": layout_bytes, "inlined_target_share": inline_cov}
+    sha = kernel_sass_sha16(kernel_name) if rank == 0 else None
+    roof["kernel_sass_sha16"] = sha
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if rank == 0 and os.path.exists(tpath):
+        rec = json.load(open(tpath)).get("%s|%s" % (args.workload, kernel_name))
+        if rec and W == w["walkers"] and rec.get("kernel_sass_sha16") == sha and sha is not None:
+            traffic = rec["dram_bytes_read"] + rec["dram_bytes_write"]
+            roof["traffic_source"] = rec.get("capture")
+            if rec.get("l2_bytes"):
+                roof["l2_bytes_per_launch"] = rec["l2_bytes"]
+                roof["l2_achieved_gbs"] = rec["l2_bytes"] / (ms_launch * 1e-3) / 1e9
+                roof["l2_frac"] = (rec.get("lts_throughput_pct") or 0.0) / 100.0 or None
+                roof["l2_frac_source"] = "lts__throughput.avg.pct_of_peak_sustained_elapsed of the capture"
+        elif rec:
+            roof["traffic_source"] = "capture %s is of another build of the kernel (sass %s): not used" % (rec.get("capture"), rec.get("kernel_sass_sha16"))
+    roof["traffic"] = traffic
+    if traffic is not None:
+        roof["achieved"] = traffic / (ms_launch * 1e-3) / 1e9          # DRAM bytes of one launch (ncu) over this run's launch time
+        roof["frac"] = roof["dram_frac"] = roof["achieved"] / peak
+        roof["dram_bytes_per_walker_step"] = traffic / (W * nt)
+        roof["note"] = ("achieved = measured DRAM bytes per launch / launch time: the fraction of the HBM roofline the kernel uses. It is a "
+                        "dependent random-gather kernel: gather_ceiling_frac says how close it is to what the memory system gives that "
+                        "access pattern; algorithmic_equiv is the SURVEY 8d figure")
+    else:
+        roof["achieved"], roof["frac"], roof["dram_frac"] = alg_achieved, alg_achieved / peak, None
+        roof["note"] = "no ncu capture of this build of the kernel: achieved / frac are the algorithmic (SURVEY 8d) figures, not a bound"
+    if "fused rows" in kernel_name and rank == 0:
+        fp = int(lay["row_block_bytes"])
+        ceil_g = _lib.gather_ceiling(fp, 128, local_rank)
+        roof["gather_ceiling"] = {"gathers_per_s": ceil_g, "working_set_bytes": fp, "gather_bytes": 128,
+                                  "how": "cyp_gather_ceiling: 8 independent 128-byte random gathers in flight per 8 lanes, same footprint, same run"}
+        roof["gather_ceiling_frac"] = (W * nt / (ms_launch * 1e-3)) / ceil_g
+
+    # ---- e2e through the C ABI with HOST buffers, every step: the CSR from pinned host memory on rank 0 -> K1 -> NVLink
+    # broadcast of the built arrays -> per-device session -> one sampling round (K2 + K3, all-gather of the 24-byte
+    # records, cross-rank first-occurrence prune, all-gather of the index) -> final selection (replay of the picked
+    # walkers split over the ranks, all-gather of the int32 sequences) -> rows + scores on the host
     trunc = np.array([c[:8] for c in g.clusters], dtype="U8")
     code_names, cell_code = np.unique(trunc, return_inverse=True)
     cell_code = np.ascontiguousarray(cell_code, dtype=np.int32)
@@ -377,92 +459,136 @@ def run_b200(args, w):
     end_slot = np.full(C.shape[0], -1, dtype=np.int32)
     end_slot[end_cells] = np.arange(len(end_cells), dtype=np.int32)
     n_fetch = 2000
-    graph.close()
     del d_seq
     torch.cuda.empty_cache()
-
     e2e_ms = {}
-
-    trace = bool(os.environ.get("CYP_E2E_TRACE"))
+    last = {}
 
     def lap(name, t0):
         dt = (time.perf_counter() - t0) * 1e3
         e2e_ms[name] = e2e_ms.get(name, 0.0) + dt
-        if trace:
-            print("e2e %-14s %7.2f ms" % (name, dt), file=sys.stderr)
         return time.perf_counter()
 
-    def e2e_step(i):
-        gh, sh = ctypes.c_void_p(), ctypes.c_void_p()
+    def e2e_step(i, grp, root_csr, per_rank_walkers):
         t0 = time.perf_counter()
-        _lib.check(L.cyp_graph_create(local_rank, C.shape[0], C.nnz, ctypes.c_void_p(row_ptr.data_ptr()),
-                                      ctypes.c_void_p(col.data_ptr()), ctypes.c_void_p(val.data_ptr()), mode, ctypes.byref(gh)))
+        gs = grp.create_graph(root_csr, mode, 0, shape=(C.shape[0], C.nnz))
         t0 = lap("graph_create", t0)
-        _lib.check(L.cyp_session_create(gh, _lib.ptr(roots), n_roots, _lib.ptr(cell_code), len(code_names), 2,
-                                        _lib.ptr(end_slot), len(end_cells), max_steps, 1, args.seed, ctypes.byref(sh)))
+        grp.create_session(roots, cell_code, len(code_names), 2, end_slot, len(end_cells), max_steps, True, args.seed)
         t0 = lap("session_create", t0)
-        st = _lib.RoundStats()
-        _lib.check(L.cyp_session_round(sh, i, sims_per_root, w0, w0 + W, None, ctypes.byref(st)))
+        sims = -(-(per_rank_walkers * grp.world) // n_roots)
+        st, counts = grp.round(i, sims)
         t0 = lap("round", t0)
-        kept = st.n_kept
-        slot = np.empty(kept, dtype=np.int32)
-        walker = np.empty(kept, dtype=np.int64)
-        if kept:
-            _lib.check(L.cyp_session_fetch_index(sh, 0, kept, None, _lib.ptr(walker), _lib.ptr(slot)))
-        m = min(n_fetch, kept)
-        rows = np.ascontiguousarray(np.linspace(0, max(kept - 1, 0), m).astype(np.int64))
-        out = np.empty((m, max_steps), dtype=np.int32)
+        have = np.flatnonzero(counts)
+        m = min(n_fetch, int(st["n_kept"]))
         if m:
-            _lib.check(L.cyp_session_fetch_rows(sh, _lib.ptr(rows), m, _lib.ptr(out)))
-        t0 = lap("fetch", t0)
-        L.cyp_session_destroy(sh)
-        L.cyp_graph_destroy(gh)
-        lap("destroy", t0)
-        return st, kept * 12 + m * max_steps * 4
+            pick = have[np.arange(m) % len(have)].astype(np.int32)
+            off = np.minimum(np.arange(m) // len(have), counts[pick] - 1).astype(np.int64)
+            seq, score, sel = grp.select(pick, off)
+        else:
+            seq, sel = np.empty((0, max_steps), np.int32), {}
+        lap("select", t0)
+        last.update(graph=gs, round=st, select=sel, d2h=int(counts.nbytes + seq.nbytes + 4 * m))
+        return st
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    st, d2h = e2e_step(0)                                          # warm-up
+    e2e_step(0, group, Cp, W)                                      # warm-up
     e2e_ms.clear()
     torch.cuda.synchronize(); barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
-        st, d2h = e2e_step(1 + i)
+        st = e2e_step(1 + i, group, Cp, W)
     torch.cuda.synchronize(); barrier()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = total * nt * e2e_steps / float(t.item())
-    h2d = row_ptr.numel() * 8 + col.numel() * 4 + val.numel() * 8 + roots.nbytes + cell_code.nbytes + end_slot.nbytes
+    h2d = (C.indptr.shape[0] * 8 + C.nnz * 12) + (roots.nbytes + cell_code.nbytes + end_slot.nbytes) * world       # the CSR once (rank 0), the session arrays per rank
+    digest_n = group.digest()
+
+    # ---- parity self-check of the multi-GPU path: the global index of kept sequences of the last e2e round must be the one
+    # a single device computes for the same walker range (128-bit order-sensitive digest over (round, walker, slot))
+    multi = None
+    if world > 1:
+        dg = torch.tensor([digest_n[0] & 0x7FFFFFFFFFFFFFFF, digest_n[1] & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device=dev)
+        gathered = [torch.empty_like(dg) for _ in range(world)]
+        dist.all_gather(gathered, dg)
+        same_on_all = all(bool(torch.equal(x, gathered[0])) for x in gathered)
+        single_ok = None
+        if rank == 0:
+            solo = _lib.Group(devices=[local_rank])
+            e2e_keep, last_keep = dict(e2e_ms), dict(last)
+            e2e_step(e2e_steps, solo, Cp, W * world)              # the same round index over the whole walker range, one device
+            single_ok = solo.digest() == digest_n
+            solo.close()
+            e2e_ms.clear(); e2e_ms.update(e2e_keep); last.clear(); last.update(last_keep)
+        r, s_ = last["round"], last["select"]
+        multi = {"collectives": "ncclBroadcast(graph arrays) + per round ncclAllGather(stats), ncclAllGather(24-byte records), ncclAllGather(walker, slot) + "
+                                "ncclAllGather(selected int32 sequences)",
+                 "graph_broadcast_ms": last["graph"]["ms_broadcast"], "graph_broadcast_bytes": int(info["device_bytes"]),
+                 "round_exchange_bytes_per_rank": int(r["exchange_bytes"]), "round_exchange_ms": r["ms_exchange"], "round_local_ms": r["ms_local"],
+                 "select_gather_bytes": int(s_.get("gather_bytes", 0)), "select_gather_ms": s_.get("ms_gather"),
+                 "kept_global_last_round": int(r["n_kept"]), "replayed_last_round": int(r["n_replayed"]),
+                 "parity": {"digest": "%016x%016x" % digest_n, "same_on_all_ranks": same_on_all, "equals_single_device_run": single_ok},
+                 "nccl_version": group.nccl_version}
+        barrier()
+    group.close()
+
+    # ---- e2e_api: the public call, cytopath_b200.sampling(adata, ...) with auto_adjust on this workload's AnnData
+    api = None
+    if not args.no_api:
+        import contextlib
+        import io
+        ad = g.to_adata()
+        kw = dict(root_clusters=list(g.root_clusters), end_clusters=list(g.end_clusters)) if w["branches"] else {}
+        torch.cuda.synchronize(); barrier()
+        np.random.seed(0)
+        t0 = time.perf_counter()
+        if "api_walkers_per_gpu" in w:       # a fixed first round: sim_number / n_roots walkers per root, doubled at the start of the round (:285,:299)
+            kw.update(auto_adjust=False, sim_number=w["api_walkers_per_gpu"] * world // 2, max_steps=max_steps, traj_number=200)
+        else:
+            kw.update(auto_adjust=True)
+        with contextlib.redirect_stdout(io.StringIO()):
+            cytopath_b200.sampling(ad, cdf_mode=args.cdf_mode, seed=args.seed, device=local_rank, dist=world > 1, **kw)
+        api_s = time.perf_counter() - t0
+        t = torch.tensor([api_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        b = ad.uns["run_info"]["b200"]
+        steps_api = sum(int(r["n_walkers"]) for r in b["rounds"]) * (ad.uns["run_info"]["simulation_steps"] - 1)
+        api = {"value": steps_api / float(t.item()), "unit": "walker-steps/s", "wall_s": float(t.item()), "walker_steps": steps_api,
+               "rounds": len(b["rounds"]), "max_steps": int(ad.uns["run_info"]["simulation_steps"]),
+               "rows_out": int(ad.uns["samples"]["cell_sequences"].shape[0]),
+               "ms": {"graph_build": b["timing"]["graph"]["ms_build"], "graph_broadcast": b["timing"]["graph"]["ms_broadcast"],
+                      "rounds_local": sum(r["ms_local"] for r in b["rounds"]), "rounds_exchange": sum(r["ms_exchange"] for r in b["rounds"]),
+                      "k2": sum(r["ms_walk"] for r in b["rounds"]), "k3": sum(r["ms_filter"] for r in b["rounds"]),
+                      "select": sum(v for k, v in b["select"].items() if k.startswith("ms_"))},
+               "what": "cytopath_b200.sampling(adata, %s, %s) on the workload's AnnData (host scipy CSR in, uns['samples'] out); CUDA context already created" % (
+                   "auto_adjust=True" if kw.get("auto_adjust") else "sim_number=%d, max_steps=%d" % (kw["sim_number"], max_steps),
+                   "root_clusters/end_clusters" if w["branches"] else "root/end probabilities >= 0.99")}
 
     line = {
         "metric": "walker_steps_per_sec", "value": value, "unit": "walker-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64" if mode == _lib.CDF_EXACT else "f32", "data": "synthetic",
-        "config": {"workload": w["desc"], "cells": w["n"], "k": w["k"], "nnz": int(C.nnz), "walkers_per_gpu": W,
-                   "global_walkers": total, "max_steps": max_steps, "cdf_mode": args.cdf_mode, "seed": args.seed,
-                   "kernel": kernel_name,
-                   "parallelism": "walkers sharded by id over %d GPU(s), graph replicated" % world,
-                   "l2": "no flush: graph %.2f GB + %.2f GB of trajectories per step exceed the 126 MB L2" % (
-                       info["device_bytes"] / 1e9, W * max_steps * 4 / 1e9)},
+        "config": base_config(w, args, int(C.nnz)),
+        "kernel": kernel_name, "global_walkers": total,
+        "parallelism": "walkers sharded by id over %d GPU(s), graph built on rank 0 and broadcast over NVLink" % world,
+        "l2": "no flush: the step kernel walks %.2f GB of row blocks + target words and writes %.2f GB of trajectories per step, both above the 126 MB L2" % (
+            (lay["row_block_bytes"] + lay["target_word_bytes"]) / 1e9, W * max_steps * 4 / 1e9),
         "clocks": clk,
-        "e2e": {"value": e2e_value, "unit": "walker-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "steps": e2e_steps, "kept_rows_last_step": int(st.n_kept), "ms_walk": st.ms_walk, "ms_filter": st.ms_filter,
+        "e2e": {"value": e2e_value, "unit": "walker-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(last["d2h"]) * world,
+                "steps": e2e_steps, "kept_rows_last_step": int(st["n_kept"]), "ms_walk": st["ms_walk"], "ms_filter": st["ms_filter"],
                 "host_ms_per_step": {k: round(v / e2e_steps, 2) for k, v in e2e_ms.items()},
-                "what": "cyp_graph_create(pinned host CSR)+K1, cyp_session_round (K2+K3), fetch kept index + %d rows" % n_fetch},
+                "what": "cyp_group_graph_create (pinned host CSR on rank 0 + K1 + NVLink broadcast), cyp_group_session_create, cyp_group_round "
+                        "(K2 + K3 + NCCL exchange), cyp_group_select of %d sequences (replay + all-gather) with scores, to the host" % n_fetch},
         "gpu_launches": args.steps,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "bytes_per_walker_step": bytes_per_step,
-                     "mean_visited_row_nnz": kbar, "ms_per_launch": ms_launch,
-                     "layout_bytes_per_walker_step": layout_bytes,
-                     "layout_achieved": W * nt * layout_bytes / (ms_launch * 1e-3) / 1e9,
-                     "layout_frac": W * nt * layout_bytes / (ms_launch * 1e-3) / 1e9 / peak,
-                     "inlined_target_share": inline_cov,
-                     "note": "achieved uses SURVEY 8d's algorithmic bytes (full float64/float32 CDF row + 16 B); the default kernel "
-                             "reads fused rows (12-bit CDF codes, exact by construction, + the most probable targets inlined; "
-                             "DESIGN.md 4-5), so it requests layout_bytes per step and frac can exceed 1; traffic = dram read+write "
-                             "bytes of one launch from the committed ncu capture"},
+        "roofline": roof,
     }
+    if multi is not None:
+        line["multi_gpu"] = multi
+    if api is not None:
+        line["e2e_api"] = api
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu, cpu_c = cpu_baseline_sample(C, g, roots, max_steps, 1 if mode == _lib.CDF_EXACT else 0)
         line["cpu_baseline"] = cpu
@@ -471,7 +597,7 @@ def run_b200(args, w):
         line["cpu_baseline"] = None
     if rank == 0:
         emit(line)
-    if world > 1 and not no_dist:
+    if world > 1:
         dist.destroy_process_group()
 
 
@@ -509,6 +635,7 @@ def main():
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-api", action="store_true", help="skip the e2e_api leg (the public sampling() call)")
     ap.add_argument("--kernel-only", action="store_true", help="profiling runs: only the device-resident K2 loop")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

@@ -33,8 +33,8 @@ const char *walk_v2_name(const cyp_graph *g, int variant) {
     V2Config c;
     if (!v2_config(g, variant, 0, 0, &c)) return nullptr;
     static const char *flavor[] = {"uniform rows", "ragged rows", "ragged rows + long rows in HBM"};
-    snprintf(buf, sizeof(buf), "walk_v2_kernel<%s,fused rows,threads<=%d x %d walker%s%s,slot=%dB rotated,%s%s>", g->cdf_mode == CYP_CDF_EXACT ? "q12/f64" : "q12/f32",
-             c.threads, c.nw, c.nw > 1 ? "s" : "", c.ctas > 1 ? ",2 CTAs/SM" : "", 16 * c.cpr, flavor[c.flavor], c.l1_rows ? ",L1 rows" : "");
+    snprintf(buf, sizeof(buf), "walk_v2_kernel<%s,fused rows,threads<=%d%s,slot=%dB rotated,%s%s>", g->cdf_mode == CYP_CDF_EXACT ? "q12/f64" : "q12/f32",
+             c.threads, c.ctas > 1 ? " x 2 CTAs/SM" : "", 16 * c.cpr, flavor[c.flavor], c.l1_rows ? ",L1 rows" : "");
     return buf;
 }
 

@@ -85,10 +85,12 @@ using IC = std::integral_constant<int, N>;
 // same L2 lines at once and the L2 slices serialise them: 13.7 G walker-steps/s at 3,696 cells against 85 G at
 // 20k+ cells.  With L1 allocation the hot rows are served by the SM's own L1: 80 G at 3,696 .. 10,000 cells
 // (profiles/r01_small_graphs.log); above ~16k cells the L1-bypassing copies are the faster ones.
-// NW = walkers per thread, each with its own slot (slot index = thread * NW + k).  With NW = 2 the warp alternates
-// between its two sets of 32 walkers: while it searches the rows of one set, the copies of the other set are in
-// flight (cp.async groups, wait_group NW - 1), so a warp-step no longer waits for the slowest of its 32 row copies
-// AND the slowest of its target gathers with nothing else to do.
+// CTAS = CTAs per SM: 1 x 1024 threads (up to 64 registers) or 2 x 640 threads (48 registers, a few spills in the
+// filter modes): 25 % more walkers in flight.  Measured (profiles/r02_k2_experiments.md): +7.6 % at C4 exact (rows out
+// of HBM: latency to hide), -4.6 % at C3 (rows in L2: the register diet costs more than the extra warps give).
+// Tried in round 2 and dropped: two walkers per thread with a slot each, the warp alternating between its two sets
+// while the other set's copies are in flight (53.7 G with 2 x 896 walkers per SM against 60.3 G: a warp's serial
+// dependent chain, not the exposed memory latency, is what limits a step -- ncu: 2,330 of 4,240 cycles per warp-step).
 template <int MODE>
 struct V2Walker {
     uint32_t word = 0u;          // row word of the row being copied / searched
@@ -102,10 +104,10 @@ struct V2Walker {
     WalkerDigest<MODE> dg;
 };
 
-template <int CPR, int CDFM, int MODE, int FLAVOR, bool L1ROWS, int NW, int CTAS = 1>
-__global__ void __launch_bounds__(CTAS == 2 ? 640 : (NW == 1 ? 1024 : 896), CTAS) walk_v2_kernel(const WalkParams p, const int log_n /* 2^log_n >= longest row */) {
+template <int CPR, int CDFM, int MODE, int FLAVOR, bool L1ROWS, int CTAS>
+__global__ void __launch_bounds__(CTAS == 2 ? 640 : 1024, CTAS) walk_v2_kernel(const WalkParams p, const int log_n /* 2^log_n >= longest row */) {
     using namespace v2;
-    static_assert(NW == 1 || NW == 2, "one or two walkers per thread");
+    constexpr int NW = 1;                                  // walkers (slots) per thread
     constexpr int SLOT = 16 * CPR;
     constexpr uint32_t SMASK = SLOT - 1;
     constexpr int LPB = CPR >= 8 ? 1 : 8 / CPR;            // lanes whose slots share one 128-byte bank row
@@ -225,29 +227,17 @@ __global__ void __launch_bounds__(CTAS == 2 ? 640 : (NW == 1 ? 1024 : 896), CTAS
                 const int lo = lds8(slot_k | ((static_cast<uint32_t>(jj >> 1) + lo0) & SMASK));
                 return (hi << 4) | ((lo >> ((jj & 1) * 4)) & 15);
             };
-            // The entries whose upper byte equals the key's form a short run (usually none or one).  Both candidates
-            // are read at once and the common outcomes -- the first decides, or it is below the key and the second
-            // above -- are taken without a branch: a `while` here makes the few lanes that need a second look run the
-            // loop body one lane at a time (ncu r02: 63 of 321 warp instructions per step).
-            const int c0 = j < len ? code_at(j) : 0x7fff;
-            const int c1 = j + 1 < len ? code_at(j + 1) : 0x7fff;
+            // (reading both candidates of the short run of entries whose upper byte equals the key's at once, to keep the
+            // warp converged, is slower: 59.1 vs 60.7 G at C4, profiles/r02_k2_experiments.md)
             if constexpr (CDFM == kModeExact) {
-                if (c0 == key || (c0 < key && c1 <= key)) {          // an undecided compare, or a longer run: the general loop
-                    while (j < len) {
-                        const int code = code_at(j);
-                        if (code >= t_def) break;                    // certain crossing
-                        if (code == key && settle(j)) break;
-                        ++j;
-                    }
-                } else {
-                    j += c0 < key ? 1 : 0;
+                while (j < len) {
+                    const int code = code_at(j);
+                    if (code >= t_def) break;                        // certain crossing
+                    if (code == key && settle(j)) break;
+                    ++j;
                 }
             } else {
-                if (c0 < key && c1 < key) {
-                    while (j < len && code_at(j) < key) ++j;
-                } else {
-                    j += c0 < key ? 1 : 0;
-                }
+                while (j < len && code_at(j) < key) ++j;
             }
             // ---- next row word
             if (j < len) {
@@ -378,7 +368,6 @@ __global__ void __launch_bounds__(CTAS == 2 ? 640 : (NW == 1 ? 1024 : 896), CTAS
 // above 256 bytes (23.1 G at C5 against 24.4 G for the 16-bit rows of walk_tma.cu: few entries of a 200-entry row
 // fit the slack, so most steps still need the second gather).
 constexpr int64_t kV2L1Cells = 16384;      // below: L1-allocating row copies (see walk_v2_kernel)
-constexpr int kV2AutoNW = 1;               // walkers per thread the auto variant takes where two are instantiated
 
 struct V2Config {
     int cpr;            // 16-byte chunks per slot
@@ -391,13 +380,14 @@ struct V2Config {
     size_t smem;
 };
 
-// variant: 0 = auto; 9500 + T/32 = one walker per thread, T threads per CTA; 9600 + T/32 = two walkers per thread
+// variant: 0 = auto; 9500 + T/32 = one CTA of T threads per SM; 9700 + T/32 = two CTAs of T threads per SM
 inline bool v2_config(const cyp_graph *g, int variant, int64_t n_walkers, int sm_count, V2Config *out) {
     if (!g->v2_ok) return false;
-    int nw = kV2AutoNW, ctas = 1;
-    if (variant > 9700) { ctas = 2; nw = 1; variant -= 200; }
-    else if (variant > 9600) { nw = 2; variant -= 100; }
-    else if (variant > 9500) nw = 1;
+    const int nw = 1;
+    // auto: two CTAs per SM where the rows come out of HBM (fused rows above half the L2) and the key is an integer (exact mode)
+    int ctas = (g->cdf_mode == CYP_CDF_EXACT && g->rows2_bytes > (64ll << 20)) ? 2 : 1;
+    if (variant > 9700) { ctas = 2; variant -= 200; }
+    else if (variant > 9500) ctas = 1;
     const int block = g->v2_slot_sectors * 32;          // covers (almost) every row (cyp_graph::v2_slot_sectors, rows_v2.cu)
     if (block > 256) return false;                       // long rows: walk_tma.cu
     int cpr = 2;
@@ -406,10 +396,10 @@ inline bool v2_config(const cyp_graph *g, int variant, int64_t n_walkers, int sm
     const int flavor = g->v2_max_sectors * 32 > stride ? v2::kOversize : (g->v2_uniform ? v2::kUniform : v2::kRagged);
     int l1_rows = g->n < kV2L1Cells ? 1 : 0;
     if (const char *e = getenv("CYP_V2_L1")) l1_rows = atoi(e) ? 1 : 0;
-    if (!(cpr == 8 && flavor == v2::kUniform && !l1_rows)) nw = 1, ctas = 1;       // the only shape instantiated with two walkers per thread / two CTAs per SM
+    if (!(cpr == 8 && flavor == v2::kUniform && !l1_rows)) ctas = 1;       // the only shape instantiated with two CTAs per SM
     const size_t budget = (226 * 1024 - 1024) / ctas - (ctas > 1 ? 1024 : 0);
     int threads = static_cast<int>(budget / (stride * nw)) / 32 * 32;
-    const int tmax = ctas == 2 ? 640 : (nw == 1 ? 1024 : 896);
+    const int tmax = ctas == 2 ? 640 : 1024;
     if (threads > tmax) threads = tmax;
     if (variant > 9500) {
         threads = (variant - 9500) * 32 < threads ? (variant - 9500) * 32 : threads;
@@ -428,9 +418,10 @@ inline bool v2_config(const cyp_graph *g, int variant, int64_t n_walkers, int sm
     return true;
 }
 
-template <int CPR, int CDFM, int MODE, int FLAVOR, bool L1ROWS, int NW = 1, int CTAS = 1>
+template <int CPR, int CDFM, int MODE, int FLAVOR, bool L1ROWS, int CTAS = 1>
 static int launch_v2_kernel(const WalkParams &p, const V2Config &c, int sm_count, cudaStream_t stream) {
-    auto kernel = walk_v2_kernel<CPR, CDFM, MODE, FLAVOR, L1ROWS, NW, CTAS>;
+    constexpr int NW = 1;
+    auto kernel = walk_v2_kernel<CPR, CDFM, MODE, FLAVOR, L1ROWS, CTAS>;
     // the opt-in to > 48 KB of dynamic shared memory is a per-device attribute of the function
     CYP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c.smem)));
     const int64_t need = (p.n_walkers + c.threads * NW - 1) / (c.threads * NW);
@@ -459,8 +450,7 @@ static int launch_v2_flavor(const WalkParams &p, const V2Config &c, int sm_count
     switch (c.flavor) {
         case v2::kUniform:
             if constexpr (CPR == 8) {
-                if (c.nw == 2) return launch_v2_kernel<CPR, CDFM, MODE, v2::kUniform, false, 2>(p, c, sm_count, stream);
-                if (c.ctas == 2) return launch_v2_kernel<CPR, CDFM, MODE, v2::kUniform, false, 1, 2>(p, c, sm_count, stream);
+                if (c.ctas == 2) return launch_v2_kernel<CPR, CDFM, MODE, v2::kUniform, false, 2>(p, c, sm_count, stream);
             }
             return launch_v2_kernel<CPR, CDFM, MODE, v2::kUniform, false>(p, c, sm_count, stream);
         case v2::kRagged: return launch_v2_kernel<CPR, CDFM, MODE, v2::kRagged, false>(p, c, sm_count, stream);

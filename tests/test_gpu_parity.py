@@ -293,18 +293,17 @@ def test_k2_bit_exact_vs_oracle_all_variants(gname, mode, omode, monkeypatch):
                                          ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
             torch.cuda.synchronize()
             np.testing.assert_array_equal(out.cpu().numpy(), wnt, err_msg="%s nt=%d" % (g.variant_name(variant), n_t))
-    # fused-row flavour (12-bit codes, inlined targets): 32 / 128 / 512 / 1024 threads per CTA, one (95xx) or two (96xx) walkers
-    # per thread; L1-allocating and L1-bypassing row copies; 62, 63 and 64 columns
-    for variant, l1 in ((9501, "1"), (9504, "0"), (9516, "1"), (9532, "0"), (9601, "0"), (9608, "0"), (9628, "0")):
+    # fused-row flavour (12-bit codes, inlined targets): 32 / 128 / 512 / 1024 threads per CTA, one (95xx) or two (97xx) CTAs
+    # per SM; L1-allocating and L1-bypassing row copies; 62, 63 and 64 columns
+    for variant, l1 in ((9501, "1"), (9504, "0"), (9516, "1"), (9532, "0"), (9701, "0"), (9708, "0"), (9720, "0")):
         monkeypatch.setenv("CYP_V2_L1", l1)
         if gname == "k200":
             assert g.variant_name(variant) == "not applicable"       # blocks above 256 bytes: walk_tma.cu
             continue
         assert "walk_v2_kernel" in g.variant_name(variant), g.variant_name(variant)
-        if variant > 9600:
-            name = g.variant_name(variant)                            # two walkers per thread: uniform 128-byte blocks only
-            assert ("x 2 walkers" in name) == ("slot=128B" in name and "uniform rows" in name), name
-            assert "x 2 walkers" in name or gname != "k50"
+        if variant > 9700:
+            name = g.variant_name(variant)                            # two CTAs per SM: uniform 128-byte blocks only
+            assert ("x 2 CTAs/SM" in name) == ("slot=128B" in name and "uniform rows" in name), name
         for n_t in (nt, 62, 63):
             wnt = want if n_t == nt else cwalk.walk(C, cdf, np.repeat(roots, sims), n_t, seed=seed, round_idx=rnd, strict=False)
             out = torch.full((len(roots) * sims, n_t + 1), -7, dtype=torch.int32, device="cuda")
@@ -449,6 +448,28 @@ def test_undirected_simulations_cuda_matches_reference(name):
     check_undirected(name)
 
 
+def test_f1_fused_mode_needs_no_sequences():
+    """undirected_simulations(store_samples=False): log_terminal_state_freq equals the reference's (utils.py:92-95)
+    without a single sequence being produced; also at 300k cells with every cell a root (K2 runs without a
+    trajectory buffer, the sessions keep 16-byte records)."""
+    import json
+    for name in ("undirected_all_cells", "undirected_subset"):
+        z = load(name)
+        ad, _ = adata_from_case(dict(z, kwargs=np.asarray(json.dumps({"cluster_key": "louvain"}))))
+        kw = json.loads(str(z["kwargs"]))
+        np.random.seed(int(z["np_seed"]))
+        run_quiet(cytopath_b200.undirected_simulations, ad, **kw, seed=int(z["seed"]), store_samples=False)
+        np.testing.assert_array_equal(np.asarray(ad.obs["log_terminal_state_freq"], dtype=np.float64), z["log_terminal_state_freq"])
+        assert "undirected_samples" not in ad.uns
+    gph = synth.branching_graph(n=300_000, k=20, n_branches=6, seed=2)
+    ad = gph.to_adata()
+    np.random.seed(1)
+    run_quiet(cytopath_b200.undirected_simulations, ad, max_steps=60, seed=3, store_samples=False)
+    f = np.asarray(ad.obs["log_terminal_state_freq"], dtype=np.float64)
+    visited = np.isfinite(f)
+    assert 1000 < visited.sum() < 300_000 and abs(np.expm1(f[visited]).sum() - 1.0) < 1e-9      # frequencies of 300k selected sequences
+
+
 def test_k2_randomised_shapes_vs_oracle():
     """40 random (graph, mode, roots, walkers, steps, seed, round, shard) combinations through the default kernel."""
     rng = np.random.default_rng(2024)
@@ -538,7 +559,9 @@ class _DevPtr:
         self.__cuda_array_interface__ = {"shape": (n_u64,), "typestr": "<i8", "data": (ptr, False), "version": 2}
 
 
-def test_k3_not_unique_keeps_duplicates_and_sharded_prune():
+@pytest.mark.parametrize("hash_bits", [128, 5])
+def test_k3_not_unique_keeps_duplicates_and_sharded_prune(hash_bits):
+    """... and with the hash cut to 5 bits the cross-shard prune must tell colliding sequences apart by replaying them."""
     C = sp.canonical_csr(synth.branching_graph(n=80, k=4, n_branches=2, seed=5, workers=1, scale=2.0, noise=0.05).T)
     n = C.shape[0]
     code = np.zeros(n, dtype=np.int32)
@@ -555,6 +578,7 @@ def test_k3_not_unique_keeps_duplicates_and_sharded_prune():
     import torch
     sa, _ = make_session(C, g, roots, code, 1, end_cells, 5, True, 9)
     sb, _ = make_session(C, g, roots, code, 1, end_cells, 5, True, 9)
+    sa.set_hash_bits(hash_bits); sb.set_hash_bits(hash_bits)
     sa.round(0, 300, 0, 500)
     sb.round(0, 300, 500, 1200)
     recs = []
@@ -633,9 +657,45 @@ def test_full_size_c4_properties():
     assert (np.asarray(C[src, dst]).ravel() > 0).all()
     np.testing.assert_array_equal(sample[:, 0], roots[(np.arange(0, W, 2500)) // sims])
     cdf = cwalk.build_cdf(C, 1)
-    for w_id in (0, 2500, 1_247_500):
-        want = cwalk.walk(C, cdf, roots[w_id // sims:w_id // sims + 1], nt, seed=1234, walker_begin=w_id)[0]
-        np.testing.assert_array_equal(sample[w_id // 2500], want)
+    for a, b in ((0, 60_000), (1_210_000, 1_250_000)):                    # 100k walkers x 499 transitions against the C oracle
+        starts = roots[np.arange(a, b) // sims]
+        want = cwalk.walk(C, cdf, starts, nt, seed=1234, walker_begin=a)
+        np.testing.assert_array_equal(outs[0][a:b].cpu().numpy(), want)
+    g.close()
+
+
+@pytest.mark.parametrize("wl,mode,omode", [("c2", _lib.CDF_REFERENCE, 0), ("c3", _lib.CDF_EXACT, 1), ("c5", _lib.CDF_EXACT, 1)])
+def test_bench_sizes_c2_c3_c5_sampled_vs_oracle(wl, mode, omode):
+    """The other BASELINE.json configs at bench.py's sizes (5,780 cells x 710k walkers x 200 steps; 100k cells x 1M
+    walkers x 200 steps; 250k cells k=200 x 1.25M walkers x 200 steps): the default kernel for each graph shape
+    (fused rows with L1 copies / fused rows / 16-bit rows with bulk copies) against the C oracle on two blocks of
+    10,000 walkers, plus the per-walker checksum of a re-walked sub-range."""
+    import ctypes
+    import torch
+    import bench
+    w = bench.WORKLOADS[wl]
+    gph, C, roots = bench.make_graph(w, 1)
+    W, nt = w["walkers"], w["max_steps"] - 1
+    sims = -(-W // len(roots))
+    L = _lib.load()
+    g = _lib.Graph(C, mode)
+    d_roots = torch.tensor(roots, dtype=torch.int32, device="cuda")
+    sptr = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    out = torch.empty((W, nt + 1), dtype=torch.int32, device="cuda")
+    miss = torch.zeros(1, dtype=torch.int64, device="cuda")
+    _lib.check(L.cyp_walk_device(g.handle, d_roots.data_ptr(), len(roots), sims, 0, W, nt, 4321, 3, None, out.data_ptr(), miss.data_ptr(), 0, sptr))
+    torch.cuda.synchronize()
+    assert int(miss.item()) == 0
+    cdf = cwalk.build_cdf(C, omode)
+    for a in (0, W - 10_000):
+        starts = roots[np.arange(a, a + 10_000) // sims]
+        want = cwalk.walk(C, cdf, starts, nt, seed=4321, round_idx=3, walker_begin=a)
+        np.testing.assert_array_equal(out[a:a + 10_000].cpu().numpy(), want, err_msg=g.variant_name(0))
+    weights = torch.arange(1, nt + 2, device="cuda", dtype=torch.int64)
+    part = torch.empty((5000, nt + 1), dtype=torch.int32, device="cuda")
+    _lib.check(L.cyp_walk_device(g.handle, d_roots.data_ptr(), len(roots), sims, W // 2, 5000, nt, 4321, 3, None, part.data_ptr(), None, 0, sptr))
+    torch.cuda.synchronize()
+    assert torch.equal((part.to(torch.int64) * weights).sum(dim=1), (out[W // 2:W // 2 + 5000].to(torch.int64) * weights).sum(dim=1))
     g.close()
 
 
