@@ -426,8 +426,9 @@ def run_b200(args, w):
             if rec.get("l2_bytes"):
                 roof["l2_bytes_per_launch"] = rec["l2_bytes"]
                 roof["l2_achieved_gbs"] = rec["l2_bytes"] / (ms_launch * 1e-3) / 1e9
-                roof["l2_frac"] = (rec.get("lts_throughput_pct") or 0.0) / 100.0 or None
-                roof["l2_frac_source"] = "lts__throughput.avg.pct_of_peak_sustained_elapsed of the capture"
+                roof["l2_frac"] = (rec.get("lts_sectors_pct") or 0.0) / 100.0 or None
+                roof["l2_hit_rate"] = (rec.get("lts_hit_rate_pct") or 0.0) / 100.0 or None
+                roof["l2_frac_source"] = "lts__t_sectors.sum.pct_of_peak_sustained_elapsed of the capture (L2 sector bandwidth used)"
         elif rec:
             roof["traffic_source"] = "capture %s is of another build of the kernel (sass %s): not used" % (rec.get("capture"), rec.get("kernel_sass_sha16"))
     roof["traffic"] = traffic
@@ -559,6 +560,7 @@ def run_b200(args, w):
         api = {"value": steps_api / float(t.item()), "unit": "walker-steps/s", "wall_s": float(t.item()), "walker_steps": steps_api,
                "rounds": len(b["rounds"]), "max_steps": int(ad.uns["run_info"]["simulation_steps"]),
                "rows_out": int(ad.uns["samples"]["cell_sequences"].shape[0]),
+               "host_ms": {k: round(v, 1) for k, v in b["timing"].get("host_ms", {}).items()},
                "ms": {"graph_build": b["timing"]["graph"]["ms_build"], "graph_broadcast": b["timing"]["graph"]["ms_broadcast"],
                       "rounds_local": sum(r["ms_local"] for r in b["rounds"]), "rounds_exchange": sum(r["ms_exchange"] for r in b["rounds"]),
                       "k2": sum(r["ms_walk"] for r in b["rounds"]), "k3": sum(r["ms_filter"] for r in b["rounds"]),

@@ -28,7 +28,7 @@ EXPORTS = [
     "cyp_session_fetch_index", "cyp_session_fetch_rows", "cyp_session_slot_counts", "cyp_session_round_records",
     "cyp_session_round_prune", "cyp_session_set_hash_bits", "cyp_session_set_chunk_walkers",
     "cyp_hausdorff_matrix", "cyp_directionality_scores", "cyp_graph_power_iteration",
-    "cyp_group_create_local", "cyp_group_unique_id", "cyp_group_create_rank", "cyp_group_destroy", "cyp_group_info",
+    "cyp_group_create_local", "cyp_group_unique_id", "cyp_group_create_rank", "cyp_group_destroy", "cyp_group_release", "cyp_group_info",
     "cyp_group_graph", "cyp_group_session", "cyp_group_graph_create", "cyp_group_session_create", "cyp_group_round",
     "cyp_group_rows", "cyp_group_fetch_index", "cyp_group_digest", "cyp_group_select", "cyp_group_set_chunk_walkers",
     "cyp_group_broadcast_bytes", "cyp_gather_ceiling",
@@ -134,6 +134,7 @@ def load():
     L.cyp_group_unique_id.argtypes = [vp]
     L.cyp_group_create_rank.argtypes = [vp, ci, ci, ci, P(vp)]
     L.cyp_group_destroy.argtypes = [vp]
+    L.cyp_group_release.argtypes = [vp]
     L.cyp_group_info.argtypes = [vp, P(ci), P(ci), P(ci), P(ci)]
     L.cyp_group_graph.argtypes = [vp, ci]
     L.cyp_group_graph.restype = vp
@@ -502,6 +503,7 @@ class Group:
         check(L.cyp_group_info(self._h, ctypes.byref(w), ctypes.byref(nl), ctypes.byref(fr), ctypes.byref(ver)))
         self.world, self.n_local, self.first_rank, self.nccl_version = w.value, nl.value, fr.value, ver.value
         self.n_end_slots = self.max_steps = 0
+        self._cached = False
 
     @staticmethod
     def unique_id() -> bytes:
@@ -604,17 +606,41 @@ class Group:
         return array
 
     def close(self):
+        """Releases the device memory of the run.  A multi-GPU group keeps its NCCL communicators (forming them costs a
+        few hundred ms) and stays in the module's cache for the next `sampling()` call; `destroy()` ends it."""
         if self._h:
             if self.graph is not None:
                 self.graph.close()
+                self.graph = None
+            if self._cached:
+                check(load().cyp_group_release(self._h))
+            else:
+                self.destroy()
+
+    def destroy(self):
+        if self._h:
+            if self.graph is not None:
+                self.graph.close()
+                self.graph = None
             load().cyp_group_destroy(self._h)
             self._h = ctypes.c_void_p()
+            for k in [k for k, v in _GROUPS.items() if v is self]:
+                del _GROUPS[k]
 
     def __del__(self):
         try:
-            self.close()
+            self.destroy()
         except Exception:
             pass
+
+
+_GROUPS = {}          # multi-GPU groups kept between sampling() calls: (kind, ...) -> Group
+
+
+def close_groups():
+    """Ends the cached multi-GPU groups (their NCCL communicators)."""
+    for g in list(_GROUPS.values()):
+        g.destroy()
 
 
 def open_group(device=None, devices=None, dist="auto") -> Group:
@@ -626,7 +652,13 @@ def open_group(device=None, devices=None, dist="auto") -> Group:
         devs = [int(d) for d in devices]
         if not devs:
             raise ValueError("devices must name at least one CUDA device")
-        return Group(devices=devs)
+        if len(devs) == 1:
+            return Group(devices=devs)
+        key = ("local", tuple(devs))
+        if key not in _GROUPS:
+            _GROUPS[key] = Group(devices=devs)
+            _GROUPS[key]._cached = True
+        return _GROUPS[key]
     if dist is True or (dist == "auto" and "torch.distributed" in sys.modules):
         try:
             import torch.distributed as td
@@ -638,9 +670,13 @@ def open_group(device=None, devices=None, dist="auto") -> Group:
             rank, world = td.get_rank(), td.get_world_size()
             if device is None:
                 device = int(os.environ.get("LOCAL_RANK", "0"))
-            box = [Group.unique_id() if rank == 0 else None]
-            td.broadcast_object_list(box, src=0)
-            return Group(unique_id=box[0], rank=rank, world=world, device=int(device))
+            key = ("rank", rank, world, int(device))
+            if key not in _GROUPS:
+                box = [Group.unique_id() if rank == 0 else None]
+                td.broadcast_object_list(box, src=0)
+                _GROUPS[key] = Group(unique_id=box[0], rank=rank, world=world, device=int(device))
+                _GROUPS[key]._cached = True
+            return _GROUPS[key]
         if dist is True:
             raise RuntimeError("dist=True but torch.distributed is not initialised with more than one rank")
     return Group(devices=[0 if device is None else int(device)])

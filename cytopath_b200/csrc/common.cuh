@@ -37,6 +37,9 @@ void dev_release_cached(int dev);     // dev < 0: all devices
 template <typename T>
 inline cudaError_t dev_alloc(T **p, size_t bytes) { return dev_alloc(reinterpret_cast<void **>(p), bytes); }
 
+// SMs of the current device (cached per host thread and device; the library may drive several devices from one process)
+int current_sm_count();
+
 struct DeviceGuard {
     int prev = -1;
     explicit DeviceGuard(int dev) {

@@ -7,6 +7,7 @@
 // rintf(c*1000)/1000 in float32 (np.round(decimals=3), :31).  Output goes to the
 // sector-aligned row layout described in common.cuh.
 #include <algorithm>
+#include <atomic>
 #include <cfloat>
 #include <cstdio>
 #include <cstring>
@@ -25,30 +26,63 @@ int fail(int code, const std::string &msg) {
     return code;
 }
 
+int current_sm_count() {
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (dev != cached_dev) {
+        if (cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
 // Blocks of 64 MB and more are additionally kept in an exact-size cache when they are freed: the CUDA pool hands
 // memory back quickly, but for multi-GB requests it often has to re-map physical pages into a new contiguous
 // virtual range (3-5 ms per 2.5 GB block at C4, and far worse when several processes of one box do it at
-// once), while sampling() and every step of a benchmark ask for the same few sizes again and again.
-// cyp_release_cached_memory() empties the cache and trims the pool.
+// once), while sampling() and every step of a benchmark ask for the same few sizes again and again.  The cache is
+// bounded (6 GB and 16 blocks per device) and ages out (a block nobody asked for during 512 allocations is freed);
+// cyp_release_cached_memory() empties it and trims the pool.
 namespace {
-struct BigBlock { void *p; size_t bytes; int dev; };
+struct BigBlock { void *p; size_t bytes; int dev; uint64_t stamp; };
 std::mutex g_big_mutex;
 std::vector<BigBlock> g_big_free;
 std::unordered_map<void *, BigBlock> g_big_live;
+uint64_t g_alloc_clock = 0;                          // dev_alloc calls so far
 constexpr size_t kBigBlock = 64ull << 20;
-constexpr size_t kBigCacheEntries = 32;
+constexpr size_t kBigCacheEntries = 16;
+constexpr size_t kBigCacheBytes = 6ull << 30;        // per device: what a notebook that shares the GPU may lose to the cache
+constexpr uint64_t kBigCacheAge = 512;               // a cached block nobody asked for during this many allocations goes back
+
+void big_free_now(const BigBlock &b) {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (cur != b.dev) cudaSetDevice(b.dev);
+    cudaFreeAsync(b.p, nullptr);
+    if (cur != b.dev && cur >= 0) cudaSetDevice(cur);
+}
 
 void big_cache_flush(int dev) {            // dev < 0: all devices.  Caller holds the mutex.
     std::vector<BigBlock> keep;
     for (const BigBlock &b : g_big_free) {
         if (dev >= 0 && b.dev != dev) { keep.push_back(b); continue; }
-        int cur = -1;
-        cudaGetDevice(&cur);
-        if (cur != b.dev) cudaSetDevice(b.dev);
-        cudaFreeAsync(b.p, nullptr);
-        if (cur != b.dev && cur >= 0) cudaSetDevice(cur);
+        big_free_now(b);
     }
     g_big_free.swap(keep);
+}
+
+// the cap and the age-out.  Caller holds the mutex.
+void big_cache_trim(int dev) {
+    std::vector<BigBlock> keep;
+    size_t bytes = 0, entries = 0;
+    for (auto it = g_big_free.rbegin(); it != g_big_free.rend(); ++it) {          // newest first
+        const bool mine = it->dev == dev;
+        const bool stale = g_alloc_clock - it->stamp > kBigCacheAge;
+        if (mine && (stale || bytes + it->bytes > kBigCacheBytes || entries + 1 > kBigCacheEntries)) { big_free_now(*it); continue; }
+        if (mine) { bytes += it->bytes; ++entries; }
+        keep.push_back(*it);
+    }
+    g_big_free.assign(keep.rbegin(), keep.rend());
 }
 }  // namespace
 
@@ -65,29 +99,33 @@ void dev_release_cached(int dev) {
 }
 
 cudaError_t dev_alloc(void **p, size_t bytes) {
-    static bool pool_ready[64] = {false};
+    static std::atomic<bool> pool_ready[64];
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    if (dev >= 0 && dev < 64 && !pool_ready[dev]) {
+    if (dev >= 0 && dev < 64 && !pool_ready[dev].load()) {
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
             uint64_t keep = ~0ull;
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }
-        pool_ready[dev] = true;
+        pool_ready[dev].store(true);
     }
     *p = nullptr;
-    if (bytes >= kBigBlock) {
+    {
         std::lock_guard<std::mutex> lock(g_big_mutex);
-        for (size_t i = 0; i < g_big_free.size(); ++i) {
-            if (g_big_free[i].dev == dev && g_big_free[i].bytes == bytes) {
-                *p = g_big_free[i].p;
-                g_big_live[*p] = g_big_free[i];
-                g_big_free.erase(g_big_free.begin() + i);
-                return cudaSuccess;
+        ++g_alloc_clock;
+        if (bytes >= kBigBlock) {
+            for (size_t i = 0; i < g_big_free.size(); ++i) {
+                if (g_big_free[i].dev == dev && g_big_free[i].bytes == bytes) {
+                    *p = g_big_free[i].p;
+                    g_big_live[*p] = g_big_free[i];
+                    g_big_free.erase(g_big_free.begin() + i);
+                    return cudaSuccess;
+                }
             }
         }
+        if ((g_alloc_clock & 63) == 0 && !g_big_free.empty()) big_cache_trim(dev);
     }
     e = cudaMallocAsync(p, bytes ? bytes : 1, nullptr);
     if (e == cudaErrorMemoryAllocation) {          // give the cached blocks back and try once more
@@ -101,7 +139,7 @@ cudaError_t dev_alloc(void **p, size_t bytes) {
     }
     if (e == cudaSuccess && bytes >= kBigBlock) {
         std::lock_guard<std::mutex> lock(g_big_mutex);
-        g_big_live[*p] = BigBlock{*p, bytes, dev};
+        g_big_live[*p] = BigBlock{*p, bytes, dev, g_alloc_clock};
     }
     return e;
 }
@@ -111,12 +149,12 @@ void dev_free(void *p) {
         std::lock_guard<std::mutex> lock(g_big_mutex);
         auto it = g_big_live.find(p);
         if (it != g_big_live.end()) {
-            const BigBlock b = it->second;
+            BigBlock b = it->second;
             g_big_live.erase(it);
-            if (g_big_free.size() < kBigCacheEntries) {
-                g_big_free.push_back(b);          // reusable in default-stream order, like cudaFreeAsync(p, 0)
-                return;
-            }
+            b.stamp = g_alloc_clock;
+            g_big_free.push_back(b);              // reusable in default-stream order, like cudaFreeAsync(p, 0)
+            big_cache_trim(b.dev);                // at most kBigCacheBytes / kBigCacheEntries per device stay
+            return;
         }
     }
     cudaFreeAsync(p, nullptr);

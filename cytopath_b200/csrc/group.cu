@@ -352,6 +352,21 @@ extern "C" int cyp_group_destroy(cyp_group *g) {
     return CYP_OK;
 }
 
+// Frees the graphs, sessions and indices but keeps the communicators: a group is expensive to form (ncclCommInit*),
+// so a host that calls sampling() repeatedly keeps its group and releases the device memory between calls.
+extern "C" int cyp_group_release(cyp_group *g) {
+    if (!g) return CYP_OK;
+    for (int i = 0; i < g->n_local; ++i) {
+        DeviceGuard guard(g->devices[i]);
+        if (g->sessions[i]) { cyp_session_destroy(g->sessions[i]); g->sessions[i] = nullptr; }
+        if (g->graphs[i]) { cyp_graph_destroy(g->graphs[i]); g->graphs[i] = nullptr; }
+        dev_free(g->index[i].d_round); dev_free(g->index[i].d_walker); dev_free(g->index[i].d_slot);
+        g->index[i] = cyp_group::Index{};
+    }
+    g->g_rows = 0;
+    return CYP_OK;
+}
+
 extern "C" int cyp_group_info(const cyp_group *g, int *world, int *n_local, int *first_rank, int *nccl_version) {
     CYP_REQUIRE(g != nullptr, "cyp_group_info: NULL group");
     if (world) *world = g->world;

@@ -154,14 +154,11 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const WalkParams p) 
 template <typename CdfT, int G, int UNROLL, int MODE>
 static int launch_one(const WalkParams &p, cudaStream_t stream) {
     auto kernel = walk_kernel<CdfT, G, UNROLL, MODE>;
-    static int blocks_per_sm = 0, sm_count = 0;          // per instantiation, one device type per process
-    if (blocks_per_sm == 0) {
-        int dev = 0;
-        CYP_CUDA(cudaGetDevice(&dev));
-        CYP_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-        CYP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, kWalkThreads, 0));
-        if (blocks_per_sm < 1) blocks_per_sm = 1;
-    }
+    const int sm_count = current_sm_count();
+    if (sm_count <= 0) return fail(CYP_E_CUDA, "launch_walk: no CUDA device");
+    int blocks_per_sm = 0;
+    CYP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, kWalkThreads, 0));
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
     const int64_t groups_per_block = kWalkThreads / G;
     const int64_t need = (p.n_walkers + groups_per_block - 1) / groups_per_block;
     const int64_t resident = static_cast<int64_t>(sm_count) * blocks_per_sm;   // grid-stride over walkers
@@ -187,12 +184,7 @@ template <typename CdfT>
 static int launch_variant(const WalkParams &p, WalkVariant v, WalkMode mode, cudaStream_t stream) {
 #define CYP_V(G_, U_) \
     if (v.lanes == G_ && v.unroll == U_) return launch_mode<CdfT, G_, U_>(p, mode, stream);
-    CYP_V(1, 2) CYP_V(1, 4)
-    CYP_V(2, 2) CYP_V(2, 4)
-    CYP_V(4, 2) CYP_V(4, 4)
-    CYP_V(8, 2) CYP_V(8, 4)
-    CYP_V(16, 2) CYP_V(16, 4)
-    CYP_V(32, 2) CYP_V(32, 4)
+    CYP_V(1, 4) CYP_V(2, 4) CYP_V(4, 4) CYP_V(8, 4) CYP_V(16, 4) CYP_V(32, 4)
 #undef CYP_V
     return fail(CYP_E_INVALID, "launch_walk: unknown kernel variant (lanes*100+unroll)");
 }
@@ -207,7 +199,7 @@ WalkVariant pick_walk_variant(const cyp_graph *g, int variant) {
     // one chunk (lanes * unroll * 16 bytes) should cover a typical row
     const int vec = (g->cdf_mode == CYP_CDF_EXACT) ? 2 : 4;
     const double want = g->mean_len;
-    static const WalkVariant table[] = {{1, 2}, {1, 4}, {2, 4}, {4, 4}, {8, 4}, {16, 4}, {32, 4}};
+    static const WalkVariant table[] = {{1, 4}, {2, 4}, {4, 4}, {8, 4}, {16, 4}, {32, 4}};
     for (const WalkVariant &v : table)
         if (v.lanes * v.unroll * vec >= want) return v;
     return WalkVariant{32, 4};

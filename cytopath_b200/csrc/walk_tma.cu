@@ -351,17 +351,10 @@ static TmaConfig tma_config(const cyp_graph *g, int variant) {
 template <typename Row, int MODE, int COPY>
 static int launch_tma_one(const cyp_graph *g, const WalkParams &p, const TmaConfig &c, cudaStream_t stream) {
     auto kernel = walk_tma_kernel<Row, MODE, COPY>;
-    static int sm_count = 0;
-    static size_t smem_set = 0;
-    if (sm_count == 0) {
-        int dev = 0;
-        CYP_CUDA(cudaGetDevice(&dev));
-        CYP_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-    }
-    if (c.smem > smem_set) {
-        CYP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c.smem)));
-        smem_set = c.smem;
-    }
+    const int sm_count = current_sm_count();
+    if (sm_count <= 0) return fail(CYP_E_CUDA, "launch_walk_tma: no CUDA device");
+    // the opt-in to > 48 KB of dynamic shared memory is a per-device attribute of the function
+    CYP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c.smem)));
     int ctas_per_sm = 1;
     CYP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, c.threads, c.smem));
     if (ctas_per_sm < 1) ctas_per_sm = 1;

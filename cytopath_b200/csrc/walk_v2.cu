@@ -4,19 +4,8 @@
 
 namespace cyp {
 
-static int v2_sm_count() {
-    static thread_local int cached_dev = -1, cached = 0;
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-    if (dev != cached_dev) {
-        if (cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
-        cached_dev = dev;
-    }
-    return cached;
-}
-
 int launch_walk_v2(const cyp_graph *g, const WalkParams &p_in, WalkMode mode, int variant, cudaStream_t stream) {
-    const int sm_count = v2_sm_count();
+    const int sm_count = current_sm_count();
     V2Config c;
     if (sm_count <= 0 || !v2_config(g, variant, p_in.n_walkers, sm_count, &c)) return kNotApplicable;
     WalkParams p = p_in;

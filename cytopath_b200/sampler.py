@@ -19,6 +19,7 @@ per-process `np.random.rand` (:43); `num_cores` is accepted and ignored.
 from __future__ import annotations
 
 import math
+import time
 import warnings
 
 import numpy as np
@@ -146,8 +147,10 @@ def sampling(data, auto_adjust=True, matrix_key="T_forward", cluster_key="louvai
         raise ValueError("Transition matrix must be of shape num_cells x num_cells")
 
     backend = _backend if _backend is not None else _lib
+    t_start = time.perf_counter()
     group = _group if _group is not None else backend.open_group(device=device, devices=devices, dist=dist)
     try:
+        t_group = time.perf_counter()
         C = _canonical_csr(M)
         pristine = C is M                 # the stored matrix IS what is sampled from: K4 can reuse the graph's copy
         if normalize:                                                          # :176-180
@@ -160,7 +163,10 @@ def sampling(data, auto_adjust=True, matrix_key="T_forward", cluster_key="louvai
         # a1 (K1): upload + CDF build on the group's first rank, broadcast of the device arrays to the others.  The
         # row sums of the normalisation check (:181-187) come back from the same kernel, so the host never walks
         # the 50M-entry value array.
+        t_csr = time.perf_counter()
         timing = {"graph": group.create_graph(C, _CDF_MODES[cdf_mode])}
+        timing["host_ms"] = {"open_group": 1e3 * (t_group - t_start), "canonical_csr": 1e3 * (t_csr - t_group),
+                             "create_graph": 1e3 * (time.perf_counter() - t_csr)}
         if not normalize:
             lo, hi = group.graph.row_sum_range()
             if not (hi <= 1.0 + 1e-3 and lo >= 1.0 - 1e-3):
@@ -208,7 +214,8 @@ def _sampling_on_graph(adata, copy, group, C, pristine, auto_adjust, matrix_key,
     root_clusters, end_clusters = _listify(root_clusters), _listify(end_clusters)
 
     # -- roots, end points, terminal clusters (:217-262)
-    clusters = np.asarray(adata.obs[cluster_key].astype(str).values, dtype=object)
+    t_marks = [time.perf_counter()]
+    labels = _Labels(adata.obs[cluster_key])            # str(label) per cell, through the categories: no per-cell Python work
     adata.uns["run_info"] = {"cluster_key": cluster_key}
     if not root_cells:
         if not root_clusters:
@@ -229,7 +236,7 @@ def _sampling_on_graph(adata, copy, group, C, pristine, auto_adjust, matrix_key,
             end_points = np.asarray(np.where(np.asarray(adata.obs[cluster_key].isin(end_clusters))))[0]
     adata.uns["run_info"]["end_points"] = end_points
     end_cells = np.asarray(end_points, dtype=np.int64).reshape(-1)
-    end_point_clusters = clusters[end_cells].astype(str) if end_cells.size else np.empty(0, dtype=str)
+    end_point_clusters = labels.of(end_cells) if end_cells.size else np.empty(0, dtype=str)
     end_clusters_ = np.unique(end_point_clusters)
     if len(end_clusters_) == 0:
         raise ValueError("Terminal cluster set is empty.")
@@ -250,33 +257,58 @@ def _sampling_on_graph(adata, copy, group, C, pristine, auto_adjust, matrix_key,
                                     (adata.obs["end_points"] / adata.obs["end_points"].sum()).values, max_iter, tol)
         print("Number of initial simulation steps (max_steps) set to {}".format(max_steps))
     max_steps = int(max_steps)
+    t_marks.append(time.perf_counter())
 
     # -- device-side state
-    trunc = _truncated_labels(adata.obs[cluster_key])            # labels are stored into a U8 array (:39,:51)
-    code_names, cell_code = np.unique(trunc, return_inverse=True)
+    trunc, cell_code, n_codes = labels.truncated()               # labels are stored into a U8 array (:39,:51)
     # end-point slots: one slot per distinct end-point cell; the reference scans end points in
     # list order (:348-349, :390-391), duplicates in the list count twice.
     slot_cells, end_slot_of_point = np.unique(end_cells, return_inverse=True)
     end_slot_of_cell = np.full(n, -1, dtype=np.int32)
     end_slot_of_cell[slot_cells] = np.arange(len(slot_cells), dtype=np.int32)
 
-    group.create_session(roots, cell_code, len(code_names), int(min_clusters), end_slot_of_cell,
+    group.create_session(roots, cell_code, n_codes, int(min_clusters), end_slot_of_cell,
                          len(slot_cells), max_steps, bool(unique), int(seed))
+    t_marks.append(time.perf_counter())
+    timing["host_ms"].update(resolve_and_auto_adjust=1e3 * (t_marks[1] - t_marks[0]), labels_and_session=1e3 * (t_marks[2] - t_marks[1]))
     return _run_rounds(adata, copy, group, roots, end_slot_of_point, end_point_clusters, end_clusters_, trunc,
                        max_steps, traj_number, sim_number, min_sim_ratio, rounds_limit, timing, slot_cells, want_rows)
 
 
-def _truncated_labels(col) -> np.ndarray:
-    """Per-cell cluster label cut to 8 characters, as a '<U8' array: what markov_sim stores (:39,:51).  Done per
-    category, not per cell (a million Python string slices otherwise)."""
-    try:
-        cats = np.array([str(c)[:8] for c in col.cat.categories], dtype="U8")
-        codes = np.asarray(col.cat.codes)
-        if cats.size and codes.min() >= 0:
-            return cats[codes]
-    except Exception:
-        pass
-    return np.array([str(c)[:8] for c in np.asarray(col.astype(str).values, dtype=object)], dtype="U8")
+class _Labels:
+    """The cluster label of every cell as the reference sees it (`adata.obs[cluster_key].astype(str)`, :217) and cut
+    to 8 characters (what markov_sim stores, :39,:51), computed per CATEGORY and expanded through the category codes:
+    a million cells cost a few array gathers instead of a million Python string operations."""
+
+    def __init__(self, col):
+        self.cats = self.codes = None
+        try:
+            cats = np.array([str(c) for c in col.cat.categories], dtype=object)
+            codes = np.asarray(col.cat.codes)
+            if cats.size and codes.size and codes.min() >= 0:
+                self.cats, self.codes = cats, codes
+        except Exception:
+            pass
+        if self.cats is None:                                    # not categorical after all, or missing values: per cell
+            self.full = np.asarray(col.astype(str).values, dtype=object)
+
+    def of(self, cells) -> np.ndarray:
+        out = self.cats[self.codes[cells]] if self.cats is not None else self.full[cells]
+        return out.astype(str)
+
+    def truncated(self):
+        """('<U8' label per cell, code of that label per cell, number of codes) -- codes number the distinct truncated
+        labels in sorted order, like np.unique(..., return_inverse=True)."""
+        if self.cats is not None:
+            cut = np.array([c[:8] for c in self.cats], dtype="U8")
+            names, cat_code = np.unique(cut, return_inverse=True)
+            present = np.zeros(len(names), dtype=bool)
+            present[cat_code[np.unique(self.codes)]] = True       # categories without cells do not count as labels
+            renum = np.cumsum(present) - 1
+            return cut[self.codes], renum[cat_code][self.codes].astype(np.int32), int(present.sum())
+        trunc = np.array([c[:8] for c in self.full], dtype="U8")
+        names, code = np.unique(trunc, return_inverse=True)
+        return trunc, code.astype(np.int32), len(names)
 
 
 def _run_rounds(adata, copy, group, roots, end_slot_of_point, end_point_clusters, end_clusters_, trunc, max_steps,
@@ -288,6 +320,7 @@ def _run_rounds(adata, copy, group, roots, end_slot_of_point, end_point_clusters
     cluster_slots = [end_slot_of_point[end_point_clusters == name] for name in end_clusters_]
 
     slot_counts = np.zeros(n_slots, dtype=np.int64)                   # kept sequences per end point, all rounds
+    t_rounds = time.perf_counter()
     traj_num = [0]
     count = 0
     stats = []
@@ -333,6 +366,7 @@ def _run_rounds(adata, copy, group, roots, end_slot_of_point, end_point_clusters
         pick_slot.append(cs[k])
         pick_off.append(draw - (ends[k] - slot_counts[cs][k]))
     pick_slot, pick_off = np.concatenate(pick_slot), np.concatenate(pick_off)
+    timing["host_ms"]["rounds_and_draw"] = 1e3 * (time.perf_counter() - t_rounds)
     adata.uns["run_info"]["simulation_steps"] = max_steps             # :406-407
     adata.uns["run_info"]["didrun"] = True
     if not want_rows:
@@ -342,7 +376,9 @@ def _run_rounds(adata, copy, group, roots, end_slot_of_point, end_point_clusters
                                          "final_cells": slot_cells[pick_slot].astype(np.int32),
                                          "kernel": group.graph.variant_name() if hasattr(group.graph, "variant_name") else ""}
         return adata if copy else None
+    t_sel = time.perf_counter()
     cell_sequences, scores, sel = group.select(pick_slot, pick_off)
+    timing["host_ms"]["select"] = 1e3 * (time.perf_counter() - t_sel)
 
     width = "U8" if n_roots == 1 else "U32"                           # markov_sim's own array (:39) vs the copy at :312
     adata.uns["samples"] = {

@@ -201,6 +201,8 @@ int cyp_group_create_local(int n_devices, const int *devices, cyp_group **out);
 int cyp_group_unique_id(uint8_t *id128);
 int cyp_group_create_rank(const uint8_t *id128, int rank, int world, int device, cyp_group **out);
 int cyp_group_destroy(cyp_group *g);
+/* Frees the group's graphs, sessions and index (device memory) but keeps its communicators for the next run. */
+int cyp_group_release(cyp_group *g);
 int cyp_group_info(const cyp_group *g, int *world, int *n_local, int *first_rank, int *nccl_version);
 /* The graph / session of the i-th local device (owned by the group). */
 cyp_graph *cyp_group_graph(const cyp_group *g, int local_index);

@@ -3,7 +3,7 @@
 update profiles/ncu_traffic.json (dram bytes per launch, used by bench.py's roofline.traffic)."""
 import csv, io, json, os, subprocess, sys
 
-KEEP = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'dram__bytes.sum.per_second',
+KEEP = ['gpu__time_duration.sum', 'lts__t_sectors.sum.pct_of_peak_sustained_elapsed', 'lts__t_bytes.sum', 'lts__t_sectors.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'smsp__sass_l1tex_data_pipe_lsu_wavefronts_mem_shared_op_ldgsts.sum', 'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'dram__bytes.sum.per_second',
         'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'lts__t_sector_hit_rate.pct',
         'lts__throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__t_sector_hit_rate.pct', 'l1tex__m_xbar2l1tex_read_bytes.sum',
         'l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum', 'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum',
@@ -13,6 +13,7 @@ KEEP = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__average_warp_latency_per_inst_issued.ratio', 'sm__throughput.avg.pct_of_peak_sustained_elapsed']
 
 rep, name, title, key = sys.argv[1:5]
+sass_sha = sys.argv[5] if len(sys.argv) > 5 else None      # bench.py's kernel_sass_sha16 of the build that was profiled
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, vals = rows[0], rows[1], rows[2]
@@ -29,7 +30,20 @@ def to_bytes(h):
     return float(d[h]) * scale
 tj = os.path.join(root, 'profiles', 'ncu_traffic.json')
 t = json.load(open(tj)) if os.path.exists(tj) else {}
-t[key] = {'dram_bytes_read': to_bytes('dram__bytes_read.sum'), 'dram_bytes_write': to_bytes('dram__bytes_write.sum'),
+def first(*names):
+    for h in names:
+        if h in d and d[h] not in ('', 'n/a'):
+            return h
+    return None
+l2h = first('lts__t_bytes.sum', 'lts__t_sectors.sum')
+l2_bytes = None
+if l2h:
+    l2_bytes = to_bytes(l2h) if 'bytes' in l2h else float(d[l2h]) * 32.0
+t[key] = {'kernel_sass_sha16': sass_sha, 'l2_bytes': l2_bytes,
+          'lts_throughput_pct': float(d['lts__throughput.avg.pct_of_peak_sustained_elapsed']) if 'lts__throughput.avg.pct_of_peak_sustained_elapsed' in d else None,
+          'lts_sectors_pct': float(d['lts__t_sectors.sum.pct_of_peak_sustained_elapsed']) if 'lts__t_sectors.sum.pct_of_peak_sustained_elapsed' in d else None,
+          'lts_hit_rate_pct': float(d['lts__t_sector_hit_rate.pct']) if 'lts__t_sector_hit_rate.pct' in d else None,
+          'dram_bytes_read': to_bytes('dram__bytes_read.sum'), 'dram_bytes_write': to_bytes('dram__bytes_write.sum'),
           'duration_ms_under_ncu': float(d['gpu__time_duration.sum']) * {'ns': 1e-6, 'us': 1e-3, 'ms': 1, 's': 1e3}[u['gpu__time_duration.sum']],
           'capture': name + '.csv', 'title': title}
 json.dump(t, open(tj, 'w'), indent=1, sort_keys=True)

@@ -21,7 +21,7 @@ for mode in (0, 1):
     assert np.array_equal(g.walk(roots, 9, 30, seed=5), want)
     import torch
     t_roots = torch.tensor(d_roots, device="cuda")
-    for variant in (404, 802, 9004, 9204, 9304, 9308):
+    for variant in (404, 804, 9004, 9204, 9304, 9308):
         out = torch.zeros((72, 31), dtype=torch.int32, device="cuda")
         _lib.check(L.cyp_walk_device(g.handle, t_roots.data_ptr(), len(roots), 9, 0, 72, 30, 5, 0, None, out.data_ptr(), None,
                                      variant, None))

@@ -11,7 +11,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="c4")
 ap.add_argument("--cdf-mode", default="exact")
 ap.add_argument("--steps", type=int, default=3)
-ap.add_argument("--variants", default="404,802,804,1602,1604,3202,3204")
+ap.add_argument("--variants", default="404,804,1604,3204")
 ap.add_argument("--walkers", type=int, default=0)
 ap.add_argument("--sims-per-root", type=int, default=0)
 ap.add_argument("--walker-begin", type=int, default=0)
