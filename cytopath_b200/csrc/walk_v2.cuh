@@ -107,7 +107,6 @@ struct V2Walker {
 template <int CPR, int CDFM, int MODE, int FLAVOR, bool L1ROWS, int CTAS>
 __global__ void __launch_bounds__(CTAS == 2 ? 640 : 1024, CTAS) walk_v2_kernel(const WalkParams p, const int log_n /* 2^log_n >= longest row */) {
     using namespace v2;
-    constexpr int NW = 1;                                  // walkers (slots) per thread
     constexpr int SLOT = 16 * CPR;
     constexpr uint32_t SMASK = SLOT - 1;
     constexpr int LPB = CPR >= 8 ? 1 : 8 / CPR;            // lanes whose slots share one 128-byte bank row
@@ -115,49 +114,48 @@ __global__ void __launch_bounds__(CTAS == 2 ? 640 : 1024, CTAS) walk_v2_kernel(c
     extern __shared__ __align__(256) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int nthreads = blockDim.x;
-    const uint32_t slot_sm = smem_u32(smem_raw) + static_cast<uint32_t>(threadIdx.x) * (NW * SLOT);     // SLOT-aligned: OR-able
+    const uint32_t slot_sm = smem_u32(smem_raw) + static_cast<uint32_t>(threadIdx.x) * SLOT;     // SLOT-aligned: OR-able
     const uint32_t rot16 = static_cast<uint32_t>((lane / LPB) & (CPR - 1)) * 16u;
     const uint32_t r20 = kV2Header + rot16;
 
     // cooperative copy geometry: lane = (group, c); instruction i serves the row of lane gb + i: this lane fetches
     // logical chunk c of that row (source = row + 16 c) and writes it to the chunk (c + rot_i) % CPR of that row's
-    // slot (CPR precomputed shared-memory addresses; slot k of a thread is k * SLOT further)
+    // slot (CPR precomputed shared-memory addresses)
     const int c = lane & (CPR - 1);
     const int gb = lane & ~(CPR - 1);
     const unsigned char *const src_c = p.rows2 + c * 16;
     uint32_t dst[CPR];
 #pragma unroll
     for (int i = 0; i < CPR; ++i)
-        dst[i] = slot_sm + static_cast<uint32_t>(i - c) * (NW * SLOT) + (static_cast<uint32_t>(c + (((gb + i) / LPB) & (CPR - 1))) * 16u & SMASK);
+        dst[i] = slot_sm + static_cast<uint32_t>(i - c) * SLOT + (static_cast<uint32_t>(c + (((gb + i) / LPB) & (CPR - 1))) * 16u & SMASK);
 
     const int nt = p.nt;
     const bool vec_store = (p.ld & 3) == 0;
     const bool native = p.uniforms == nullptr;
-    const int64_t stride = static_cast<int64_t>(gridDim.x) * nthreads * NW;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * nthreads;
     const int depth = log_n < DEPTH ? log_n : DEPTH;
     const uint2 pkey = make_uint2(static_cast<uint32_t>(p.seed), static_cast<uint32_t>(p.seed >> 32));
 
-    auto issue_copy = [&](uint32_t word, auto K) {
-        constexpr uint32_t koff = decltype(K)::value * SLOT;
+    auto issue_copy = [&](uint32_t word) {
         if constexpr (FLAVOR == kUniform) {
             const uint32_t woff = word << 5;                           // byte offset of the block (the shift drops the sector count)
 #pragma unroll
-            for (int i = 0; i < CPR; ++i) cp_async16<L1ROWS>(dst[i] + koff, src_c + __shfl_sync(0xffffffffu, woff, i, CPR));
+            for (int i = 0; i < CPR; ++i) cp_async16<L1ROWS>(dst[i], src_c + __shfl_sync(0xffffffffu, woff, i, CPR));
         } else {
 #pragma unroll
             for (int i = 0; i < CPR; ++i) {
                 const uint32_t wd = __shfl_sync(0xffffffffu, word, i, CPR);
                 if ((wd >> kWordOffBits) > static_cast<uint32_t>(c >> 1))          // the block has this sector
-                    cp_async16<L1ROWS>(dst[i] + koff, src_c + (wd << 5));
+                    cp_async16<L1ROWS>(dst[i], src_c + (wd << 5));
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    // One transition of one walker whose row is in slot K: writes trajectory column t, returns the next row word.
-    auto process = [&](V2Walker<MODE> &s, auto K, auto Q, const int t) -> uint32_t {
+    // One transition of the walker whose row is in the slot: writes trajectory column t, returns the next row word.
+    auto process = [&](V2Walker<MODE> &s, auto Q, const int t) -> uint32_t {
         constexpr int q = decltype(Q)::value;
-        const uint32_t slot_k = slot_sm + decltype(K)::value * SLOT;
+        const uint32_t slot_k = slot_sm;
         auto at = [&](uint32_t x) { return slot_k | ((x + rot16) & SMASK); };        // address of row byte x of this slot
         uint32_t next = s.word;
         if (!s.active) return next;
@@ -285,67 +283,45 @@ __global__ void __launch_bounds__(CTAS == 2 ? 640 : 1024, CTAS) walk_v2_kernel(c
         return next;
     };
 
-    // a warp's batch: NW sets of 32 consecutive walkers
-    for (int64_t wbase = (static_cast<int64_t>(blockIdx.x) * nthreads + (threadIdx.x & ~31)) * NW; wbase < p.n_walkers; wbase += stride) {
-        V2Walker<MODE> s[NW];
-#pragma unroll
-        for (int k = 0; k < NW; ++k) {
-            s[k].w = wbase + k * 32 + lane;
-            s[k].active = s[k].w < p.n_walkers;
-            uint64_t gw = static_cast<uint64_t>(p.walker_begin + s[k].w);
-            s[k].round = p.round;
-            if (s[k].active) {                                        // else word = 0: the first block / nothing is copied
-                int32_t root;
-                if (p.replay) {
-                    const ReplayItem it = p.replay[s[k].w];
-                    gw = static_cast<uint64_t>(it.walker);
-                    s[k].round = it.round;
-                    root = it.root;
-                } else {
-                    root = p.roots[gw / static_cast<uint64_t>(p.sims_per_root)];
-                }
-                s[k].word = p.word[root];
+    for (int64_t wbase = static_cast<int64_t>(blockIdx.x) * nthreads + (threadIdx.x & ~31); wbase < p.n_walkers; wbase += stride) {
+        V2Walker<MODE> s;
+        s.w = wbase + lane;
+        s.active = s.w < p.n_walkers;
+        uint64_t gw = static_cast<uint64_t>(p.walker_begin + s.w);
+        s.round = p.round;
+        if (s.active) {                                               // else word = 0: the first block / nothing is copied
+            int32_t root;
+            if (p.replay) {
+                const ReplayItem it = p.replay[s.w];
+                gw = static_cast<uint64_t>(it.walker);
+                s.round = it.round;
+                root = it.root;
+            } else {
+                root = p.roots[gw / static_cast<uint64_t>(p.sims_per_root)];
             }
-            s[k].gw_lo = static_cast<uint32_t>(gw);
-            s[k].gw_hi = static_cast<uint32_t>(gw >> 32);
-            s[k].out_row = (p.out_seq && s[k].active) ? p.out_seq + s[k].w * p.ld : nullptr;
-            s[k].urow = (!native && s[k].active) ? p.uniforms + s[k].w * static_cast<int64_t>(nt) : nullptr;
+            s.word = p.word[root];
         }
-        issue_copy(s[0].word, IC<0>{});
-        if constexpr (NW > 1) issue_copy(s[NW - 1].word, IC<NW - 1>{});
-        if (native && nt > 0) {
-#pragma unroll
-            for (int k = 0; k < NW; ++k) s[k].x = philox4x32_10(make_uint4(s[k].gw_lo, s[k].gw_hi, 0u, s[k].round), pkey);
-        }
+        s.gw_lo = static_cast<uint32_t>(gw);
+        s.gw_hi = static_cast<uint32_t>(gw >> 32);
+        s.out_row = (p.out_seq && s.active) ? p.out_seq + s.w * p.ld : nullptr;
+        s.urow = (!native && s.active) ? p.uniforms + s.w * static_cast<int64_t>(nt) : nullptr;
+        issue_copy(s.word);
+        if (native && nt > 0) s.x = philox4x32_10(make_uint4(s.gw_lo, s.gw_hi, 0u, s.round), pkey);
         int t = 0;
 
-        // one step of all NW sets; Q = t % 4 is static.  Returns true after the last column has been written.
+        // one step; Q = t % 4 is static.  Returns true after the last column has been written.
         auto step = [&](auto Q) -> bool {
             constexpr int q = decltype(Q)::value;
-            const bool last = t == nt;
-            auto one = [&](auto K) {
-                constexpr int k = decltype(K)::value;
-                if (NW == 1 || last) asm volatile("cp.async.wait_group 0;" ::: "memory");
-                else asm volatile("cp.async.wait_group %0;" ::"n"(NW - 1) : "memory");          // the older group: this set's copy
-                __syncwarp();
-                const uint32_t next = process(s[k], K, Q, t);
-                if (!last) {
-                    s[k].word = next;
-                    __syncwarp();                                     // every lane is done with its slot
-                    issue_copy(next, K);
-                }
-            };
-            one(IC<0>{});
-            if constexpr (NW > 1) one(IC<NW - 1>{});
-            if (last) return true;
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            const uint32_t next = process(s, Q, t);
+            if (t == nt) return true;
+            s.word = next;
             ++t;
-            if constexpr ((q & 1) != 0) {                             // t is even now: the uniforms of transitions t, t + 1
-                if (native) {
-#pragma unroll
-                    for (int k = 0; k < NW; ++k)
-                        s[k].x = philox4x32_10(make_uint4(s[k].gw_lo, s[k].gw_hi, static_cast<uint32_t>(t >> 1), s[k].round), pkey);
-                }
-            }
+            __syncwarp();                                             // every lane is done with its slot
+            issue_copy(next);
+            if constexpr ((q & 1) != 0)                               // t is even now: the uniforms of transitions t, t + 1
+                if (native) s.x = philox4x32_10(make_uint4(s.gw_lo, s.gw_hi, static_cast<uint32_t>(t >> 1), s.round), pkey);
             return false;
         };
         while (true) {
@@ -354,9 +330,7 @@ __global__ void __launch_bounds__(CTAS == 2 ? 640 : 1024, CTAS) walk_v2_kernel(c
             if (step(IC<2>{})) break;
             if (step(IC<3>{})) break;
         }
-#pragma unroll
-        for (int k = 0; k < NW; ++k)
-            if (s[k].active) s[k].dg.finish(p, s[k].w, s[k].cell);
+        if (s.active) s.dg.finish(p, s.w, s.cell);
     }
 }
 
@@ -371,7 +345,6 @@ constexpr int64_t kV2L1Cells = 16384;      // below: L1-allocating row copies (s
 
 struct V2Config {
     int cpr;            // 16-byte chunks per slot
-    int nw;             // walkers (slots) per thread
     int ctas;           // CTAs per SM
     int threads;
     int log_n;
@@ -383,7 +356,6 @@ struct V2Config {
 // variant: 0 = auto; 9500 + T/32 = one CTA of T threads per SM; 9700 + T/32 = two CTAs of T threads per SM
 inline bool v2_config(const cyp_graph *g, int variant, int64_t n_walkers, int sm_count, V2Config *out) {
     if (!g->v2_ok) return false;
-    const int nw = 1;
     // auto: two CTAs per SM where the rows come out of HBM (fused rows above half the L2) and the key is an integer (exact mode)
     int ctas = (g->cdf_mode == CYP_CDF_EXACT && g->rows2_bytes > (64ll << 20)) ? 2 : 1;
     if (variant > 9700) { ctas = 2; variant -= 200; }
@@ -398,14 +370,14 @@ inline bool v2_config(const cyp_graph *g, int variant, int64_t n_walkers, int sm
     if (const char *e = getenv("CYP_V2_L1")) l1_rows = atoi(e) ? 1 : 0;
     if (!(cpr == 8 && flavor == v2::kUniform && !l1_rows)) ctas = 1;       // the only shape instantiated with two CTAs per SM
     const size_t budget = (226 * 1024 - 1024) / ctas - (ctas > 1 ? 1024 : 0);
-    int threads = static_cast<int>(budget / (stride * nw)) / 32 * 32;
+    int threads = static_cast<int>(budget / stride) / 32 * 32;
     const int tmax = ctas == 2 ? 640 : 1024;
     if (threads > tmax) threads = tmax;
     if (variant > 9500) {
         threads = (variant - 9500) * 32 < threads ? (variant - 9500) * 32 : threads;
     } else if (n_walkers > 0 && sm_count > 0) {
         // wave balancing: every warp runs as many 32-walker batches as with the largest CTA, with no more warps than that needs
-        const int64_t batches = (n_walkers + 32 * nw - 1) / (32 * nw);
+        const int64_t batches = (n_walkers + 31) / 32;
         const int64_t per_round = static_cast<int64_t>(sm_count) * ctas * (threads / 32);
         const int64_t rounds = (batches + per_round - 1) / per_round;
         const int64_t warps = (batches + static_cast<int64_t>(sm_count) * ctas * rounds - 1) / (static_cast<int64_t>(sm_count) * ctas * rounds);
@@ -414,17 +386,16 @@ inline bool v2_config(const cyp_graph *g, int variant, int64_t n_walkers, int sm
     if (threads < 32) threads = 32;
     int log_n = 1;
     while ((1 << log_n) < g->max_len) ++log_n;
-    *out = V2Config{cpr, nw, ctas, threads, log_n, flavor, l1_rows, static_cast<size_t>(threads) * stride * nw};
+    *out = V2Config{cpr, ctas, threads, log_n, flavor, l1_rows, static_cast<size_t>(threads) * stride};
     return true;
 }
 
 template <int CPR, int CDFM, int MODE, int FLAVOR, bool L1ROWS, int CTAS = 1>
 static int launch_v2_kernel(const WalkParams &p, const V2Config &c, int sm_count, cudaStream_t stream) {
-    constexpr int NW = 1;
     auto kernel = walk_v2_kernel<CPR, CDFM, MODE, FLAVOR, L1ROWS, CTAS>;
     // the opt-in to > 48 KB of dynamic shared memory is a per-device attribute of the function
     CYP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c.smem)));
-    const int64_t need = (p.n_walkers + c.threads * NW - 1) / (c.threads * NW);
+    const int64_t need = (p.n_walkers + c.threads - 1) / c.threads;
     const unsigned grid = static_cast<unsigned>(need < sm_count * CTAS ? need : sm_count * CTAS);       // persistent CTAs
     if (grid == 0) return CYP_OK;
     static const bool trace = getenv("CYP_TRACE") != nullptr;
