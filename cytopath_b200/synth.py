@@ -145,7 +145,7 @@ def branching_graph(n=3696, k=30, n_branches=4, seed=0, n_root_stems=1, self_loo
     return SynthGraph(T, clusters.astype(str), root_prob, end_prob, pos, root_clusters, end_clusters)
 
 
-def cycling_graph(n=20000, k=200, seed=0, workers=-1) -> SynthGraph:
+def cycling_graph(n=20000, k=200, seed=0, workers=-1, n_layers=1) -> SynthGraph:
     """Annulus (cycle, tangential velocity) feeding two arms that re-converge to one
     terminal region; self-loop on every row; long rows (k=200) for the wide-row path.
     Roots / end points come from smooth probability bumps so the reference's 0.99
@@ -173,7 +173,10 @@ def cycling_graph(n=20000, k=200, seed=0, workers=-1) -> SynthGraph:
     pos[m] = np.stack([1.0 + 0.5 * s[m], np.zeros(m.sum())], 1)
     vel[m] = np.array([1.0, 0.0])
     pos += rng.normal(0.0, 0.01, size=(n, 2))
-    T = _knn_transition(pos, vel, k, self_loops=True, workers=workers)
+    # n_layers interleaved, independent kNN graphs (see _knn_transition): hops n_layers times longer, so that the stem tip
+    # stays reachable from the far side of the cycle in a couple of hundred steps at 250k cells
+    layer = rng.integers(n_layers, size=n) if n_layers > 1 else None
+    T = _knn_transition(pos, vel, k, self_loops=True, workers=workers, layer=layer)
 
     names = {0: "cyc", 1: "armA", 2: "armB", 3: "term"}
     bins = np.minimum((s * 4).astype(int), 3)

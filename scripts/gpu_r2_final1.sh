@@ -4,7 +4,7 @@ mkdir -p gpurun_out; export BENCH_GRAPH_CACHE=/tmp/cyp_graphs
 if [ -z "$SKIP_TESTS" ]; then
 (timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log); tail -6 gpurun_out/pytest_gpu.log
 fi
-for wl in ${NCU_WORKLOADS:-c4}; do NCU_WORKLOAD=$wl NCU_TAG=r02_k2_$wl bash scripts/gpu_ncu_k2.sh; done
+for wl in ${NCU_WORKLOADS-c4}; do NCU_WORKLOAD=$wl NCU_TAG=r02_k2_$wl bash scripts/gpu_ncu_k2.sh; done
 if [ -n "$LAUNCH_LIST" ]; then
 python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/launch_plain.log 2>&1 && \
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02_launches_bench_c4.csv python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_launch.log 2>&1; tail -1 gpurun_out/ncu_launch.log | cut -c1-300
