@@ -337,8 +337,11 @@ def run_b200(args, w):
 
     # ---- resident state: graph (K1 on rank 0 + NVLink broadcast), roots, trajectory buffer
     Cp, _pins = pinned_csr(C) if rank == 0 else (None, None)
-    gstat = group.create_graph(Cp, mode, 0, shape=(C.shape[0], C.nnz))
-    graph = group.graph
+    if os.environ.get("BENCH_EACH_RANK_UPLOADS"):             # probe: every rank builds its own graph from the host CSR (round 1's way)
+        graph = _lib.Graph(C, mode, local_rank)
+    else:
+        gstat = group.create_graph(Cp, mode, 0, shape=(C.shape[0], C.nnz))
+        graph = group.graph
     info = graph.info()
     kernel_name = graph.variant_name(args.variant)
     d_roots = torch.tensor(roots, dtype=torch.int32, device=dev)

@@ -229,16 +229,30 @@ int group_finish_create(cyp_group *g) {
         G_CUDA(cudaStreamCreateWithFlags(&g->streams[i], cudaStreamNonBlocking));
     }
     if (g->world > 1) {
-        // NCCL connects its transports at the first collective.  Do it now, before the graph and the round buffers are
-        // allocated: when it happens after them K2 runs 25 % slower for the rest of the process
-        // (profiles/r01_multi_gpu_probe.md).
+        // NCCL connects its transports lazily, per collective and algorithm, at first use.  Do it now, before the graph and
+        // the round buffers are allocated: when it happens after them K2 runs 25 % slower for the rest of the process
+        // (profiles/r01_multi_gpu_probe.md).  So: every collective the group uses, in a small and a large size.
+        const char *warm = getenv("CYP_GROUP_WARM");
+        const bool full = !(warm && warm[0] == '0');
+        const size_t big = full ? (8u << 20) : 8;             // bytes per rank of the large all-gather
         std::vector<void *> bufs(g->n_local, nullptr);
         for (int i = 0; i < g->n_local; ++i) {
             DeviceGuard guard(g->devices[i]);
-            G_CUDA(cudaMalloc(&bufs[i], sizeof(int64_t) * g->world));
-            G_CUDA(cudaMemset(bufs[i], 0, sizeof(int64_t) * g->world));
+            G_CUDA(cudaMalloc(&bufs[i], big * g->world));
+            G_CUDA(cudaMemset(bufs[i], 0, big * g->world));
         }
         int rc = all_gather_inplace(g, bufs, 1, ncclInt64, sizeof(int64_t));
+        if (rc == CYP_OK && full) rc = all_gather_inplace(g, bufs, big / 8, ncclInt64, sizeof(int64_t));
+        if (rc == CYP_OK && full) rc = all_gather_inplace(g, bufs, big / 4, ncclInt32, sizeof(int32_t));
+        if (rc == CYP_OK && full) {
+            ncclResult_t r = g_nccl.GroupStart();
+            for (int i = 0; i < g->n_local && r == ncclSuccess; ++i) r = g_nccl.Broadcast(bufs[i], bufs[i], 128, ncclChar, 0, g->comms[i], g->streams[i]);
+            if (r == ncclSuccess) r = g_nccl.GroupEnd();
+            if (r == ncclSuccess) r = g_nccl.GroupStart();
+            for (int i = 0; i < g->n_local && r == ncclSuccess; ++i) r = g_nccl.Broadcast(bufs[i], bufs[i], big * g->world, ncclChar, 0, g->comms[i], g->streams[i]);
+            if (r == ncclSuccess) r = g_nccl.GroupEnd();
+            if (r != ncclSuccess) rc = fail(CYP_E_CUDA, std::string("NCCL warm-up: ") + g_nccl.GetErrorString(r));
+        }
         if (rc == CYP_OK) rc = sync_streams(g);
         for (int i = 0; i < g->n_local; ++i) {
             DeviceGuard guard(g->devices[i]);
@@ -452,13 +466,46 @@ extern "C" int cyp_group_graph_create(cyp_group *g, int64_t n_cells, int64_t nnz
     if (rc != CYP_OK) return rc;
     std::vector<std::vector<std::pair<void *, size_t>>> arrays(g->n_local);
     for (int i = 0; i < g->n_local; ++i) graph_device_arrays(g->graphs[i], &arrays[i]);
-    G_NCCL(g_nccl.GroupStart());
-    for (size_t a = 0; a < arrays[0].size(); ++a)
-        for (int i = 0; i < g->n_local; ++i)
-            G_NCCL(g_nccl.Broadcast(arrays[i][a].first, arrays[i][a].first, arrays[i][a].second, ncclChar, root_rank, g->comms[i], g->streams[i]));
-    G_NCCL(g_nccl.GroupEnd());
-    rc = sync_streams(g);
-    if (rc != CYP_OK) return rc;
+    const char *stage_env = getenv("CYP_BCAST_STAGE");
+    if (stage_env && stage_env[0] == '1') {
+        // developer switch: receivers take every array through one scratch buffer + a device copy, so that NCCL never touches the
+        // graph's own allocations
+        size_t max_bytes = 0;
+        for (auto &a : arrays[0]) max_bytes = std::max(max_bytes, a.second);
+        std::vector<void *> stage(g->n_local, nullptr);
+        for (int i = 0; i < g->n_local; ++i) {
+            if (i == root_local) continue;
+            DeviceGuard guard(g->devices[i]);
+            G_CUDA(cudaMalloc(&stage[i], max_bytes));
+        }
+        for (size_t a = 0; a < arrays[0].size(); ++a) {
+            G_NCCL(g_nccl.GroupStart());
+            for (int i = 0; i < g->n_local; ++i) {
+                void *buf = i == root_local ? arrays[i][a].first : stage[i];
+                G_NCCL(g_nccl.Broadcast(buf, buf, arrays[i][a].second, ncclChar, root_rank, g->comms[i], g->streams[i]));
+            }
+            G_NCCL(g_nccl.GroupEnd());
+            for (int i = 0; i < g->n_local; ++i) {
+                if (i == root_local) continue;
+                DeviceGuard guard(g->devices[i]);
+                G_CUDA(cudaMemcpyAsync(arrays[i][a].first, stage[i], arrays[i][a].second, cudaMemcpyDeviceToDevice, g->streams[i]));
+            }
+        }
+        rc = sync_streams(g);
+        for (int i = 0; i < g->n_local; ++i) {
+            DeviceGuard guard(g->devices[i]);
+            if (stage[i]) cudaFree(stage[i]);
+        }
+        if (rc != CYP_OK) return rc;
+    } else {
+        G_NCCL(g_nccl.GroupStart());
+        for (size_t a = 0; a < arrays[0].size(); ++a)
+            for (int i = 0; i < g->n_local; ++i)
+                G_NCCL(g_nccl.Broadcast(arrays[i][a].first, arrays[i][a].first, arrays[i][a].second, ncclChar, root_rank, g->comms[i], g->streams[i]));
+        G_NCCL(g_nccl.GroupEnd());
+        rc = sync_streams(g);
+        if (rc != CYP_OK) return rc;
+    }
     if (ms_broadcast) *ms_broadcast = static_cast<float>(now_ms() - t1);
     return CYP_OK;
 }
