@@ -204,6 +204,8 @@ GraphWire graph_wire(const cyp_graph *g);
 int graph_alloc_like(const GraphWire &w, int device, cyp_graph **out);
 // (pointer, bytes) of every device array of the graph, in an order that only depends on the wire fields
 void graph_device_arrays(const cyp_graph *g, std::vector<std::pair<void *, size_t>> *out);
+// moves every device array of the graph into a fresh allocation (device copy), frees the old one
+int graph_rehome(cyp_graph *g);
 // graph.cu: builds d_q16 and d_edge (the arrays of the step kernels other than walk_v2.cu) if they do not exist yet.
 // Synchronous, default stream; call before launching one of those kernels.
 int ensure_edge_records(const cyp_graph *g);

@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <type_traits>
 #include <unordered_map>
 #include <vector>
 
@@ -415,6 +416,45 @@ void graph_device_arrays(const cyp_graph *g, std::vector<std::pair<void *, size_
 }
 
 static void graph_free(cyp_graph *g);
+
+// Moves every device array of the graph into a fresh allocation (device copy) and frees the old one.
+int graph_rehome(cyp_graph *g) {
+    DeviceGuard guard(g->device);
+    auto move = [&](auto **p, size_t bytes) -> cudaError_t {
+        if (!*p || bytes == 0) return cudaSuccess;
+        void *fresh = nullptr;
+        cudaError_t e = dev_alloc(&fresh, bytes);
+        if (e != cudaSuccess) return e;
+        e = cudaMemcpyAsync(fresh, *p, bytes, cudaMemcpyDeviceToDevice, nullptr);
+        if (e != cudaSuccess) { dev_free(fresh); return e; }
+        dev_free(*p);
+        *p = reinterpret_cast<std::remove_reference_t<decltype(*p)>>(fresh);
+        return cudaSuccess;
+    };
+    const size_t cdf_elem = (g->cdf_mode == CYP_CDF_EXACT) ? 8 : 4;
+    const size_t padded = static_cast<size_t>(g->padded), n = static_cast<size_t>(g->n);
+    cudaError_t e = move(&g->d_row, sizeof(RowInfo) * n);
+    if (e == cudaSuccess) e = move(&g->d_cdf, cdf_elem * padded);
+    if (e == cudaSuccess) e = move(&g->d_col, sizeof(int32_t) * padded);
+    if (e == cudaSuccess) e = move(&g->d_val, sizeof(double) * padded);
+    if (e == cudaSuccess) e = move(&g->d_row_ptr, sizeof(int64_t) * (n + 1));
+    if (e == cudaSuccess && g->v2_ok) {
+        // the fused rows may sit at an offset inside their allocation (developer switch): the copy starts at the rows
+        unsigned char *fresh = nullptr;
+        e = dev_alloc(&fresh, static_cast<size_t>(g->rows2_bytes));
+        if (e == cudaSuccess) e = cudaMemcpyAsync(fresh, g->d_rows2, static_cast<size_t>(g->rows2_bytes), cudaMemcpyDeviceToDevice, nullptr);
+        if (e == cudaSuccess) { dev_free(g->d_rows2_base); g->d_rows2_base = g->d_rows2 = fresh; }
+        if (e == cudaSuccess) e = move(&g->d_edge4, sizeof(uint32_t) * 4 * static_cast<size_t>(g->v2_edge_units + 1));
+        if (e == cudaSuccess) e = move(&g->d_word, sizeof(uint32_t) * n);
+    }
+    if (e == cudaSuccess && g->d_edge) {
+        e = move(&g->d_q16, sizeof(uint16_t) * padded);
+        if (e == cudaSuccess) e = move(&g->d_edge, sizeof(EdgeRec) * padded);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
+    if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? CYP_E_NOMEM : CYP_E_CUDA, std::string("graph_rehome: ") + cudaGetErrorString(e));
+    return CYP_OK;
+}
 
 int graph_alloc_like(const GraphWire &w, int device, cyp_graph **out) {
     *out = nullptr;

@@ -234,7 +234,8 @@ int group_finish_create(cyp_group *g) {
         // (profiles/r01_multi_gpu_probe.md).  So: every collective the group uses, in a small and a large size.
         const char *warm = getenv("CYP_GROUP_WARM");
         const bool full = !(warm && warm[0] == '0');
-        const size_t big = full ? (8u << 20) : 8;             // bytes per rank of the large all-gather
+        size_t big = full ? (8u << 20) : 8;                   // bytes per rank of the large all-gather
+        if (full && warm && atoi(warm) > 1) big = static_cast<size_t>(atoi(warm)) << 20;       // developer switch: MB per rank
         std::vector<void *> bufs(g->n_local, nullptr);
         for (int i = 0; i < g->n_local; ++i) {
             DeviceGuard guard(g->devices[i]);
@@ -505,6 +506,14 @@ extern "C" int cyp_group_graph_create(cyp_group *g, int64_t n_cells, int64_t nnz
         G_NCCL(g_nccl.GroupEnd());
         rc = sync_streams(g);
         if (rc != CYP_OK) return rc;
+    }
+    if (const char *rh = getenv("CYP_BCAST_REHOME")) {
+        if (rh[0] == '1' || rh[0] == '2')
+            for (int i = 0; i < g->n_local; ++i) {
+                if (i == root_local && rh[0] == '1') continue;
+                rc = graph_rehome(g->graphs[i]);
+                if (rc != CYP_OK) return rc;
+            }
     }
     if (ms_broadcast) *ms_broadcast = static_cast<float>(now_ms() - t1);
     return CYP_OK;

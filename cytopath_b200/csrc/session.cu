@@ -67,7 +67,7 @@ struct PredSlotFlagged {       // list position i: the table slot of its key is 
     const uint8_t *keep;       // by original item
     int64_t own_begin, own_end;
     __device__ bool operator()(int64_t i) const {
-        if (!slot_flag[slot_of[i]]) return false;
+        if (slot_of[i] == ~0ull || !slot_flag[slot_of[i]]) return false;
         const int64_t o = ids ? ids[i] : i;
         return !(o >= own_begin && o < own_end && keep[o] == 0);       // verified duplicates are gone for good
     }
@@ -200,10 +200,10 @@ struct DedupTable {
 // the salted re-hash of the replayed rows, stride 2).  Positions ascend with the walker id, so the lowest position
 // with a key is its first occurrence.
 __global__ void __launch_bounds__(kThreads)
-dedup_insert_kernel(int64_t n_list, const uint64_t *__restrict__ hash, int hash_stride, uint64_t lo_mask, uint64_t hi_mask,
+dedup_insert_kernel(int64_t first, int64_t count, const uint64_t *__restrict__ hash, int hash_stride, uint64_t lo_mask, uint64_t hi_mask,
                     DedupTable t, uint64_t *__restrict__ slot_of) {
-    const int64_t k = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
-    if (k >= n_list) return;
+    const int64_t k = first + static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
+    if (k >= first + count) return;
     const uint64_t lo = (hash[static_cast<int64_t>(hash_stride) * k] & lo_mask) | 1ull;          // never 0
     const uint64_t hi = (hash[static_cast<int64_t>(hash_stride) * k + 1] & hi_mask) | 1ull;
     uint64_t idx = fmix(lo ^ (hi * 0x9E3779B97F4A7C15ull)) & t.mask;
@@ -216,6 +216,29 @@ dedup_insert_kernel(int64_t n_list, const uint64_t *__restrict__ hash, int hash_
                 slot_of[k] = idx;
                 return;
             }
+        }
+        idx = (idx + 1) & t.mask;
+    }
+}
+
+// Positions [0, count) that are NOT in the table's owner range (records of lower ranks): a position whose key is in the table
+// competes for it (atomicMin) and remembers the slot; the others get no slot.  Read-only but for the matches, and the table
+// only holds this rank's keys, so it stays cache resident: a rank does not insert the records of all ranks to find its own losers.
+__global__ void __launch_bounds__(kThreads)
+dedup_probe_kernel(int64_t count, const uint64_t *__restrict__ hash, int hash_stride, uint64_t lo_mask, uint64_t hi_mask, DedupTable t,
+                   uint64_t *__restrict__ slot_of) {
+    const int64_t k = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
+    if (k >= count) return;
+    const uint64_t lo = (hash[static_cast<int64_t>(hash_stride) * k] & lo_mask) | 1ull;
+    const uint64_t hi = (hash[static_cast<int64_t>(hash_stride) * k + 1] & hi_mask) | 1ull;
+    uint64_t idx = fmix(lo ^ (hi * 0x9E3779B97F4A7C15ull)) & t.mask;
+    while (true) {
+        const uint64_t kl = t.key_lo[idx];
+        if (kl == 0ull) { slot_of[k] = ~0ull; return; }
+        if (kl == lo && t.key_hi[idx] == hi) {
+            atomicMin(reinterpret_cast<unsigned long long *>(t.min_pos + idx), static_cast<unsigned long long>(k));
+            slot_of[k] = idx;
+            return;
         }
         idx = (idx + 1) & t.mask;
     }
@@ -275,7 +298,7 @@ mark_slots_kernel(int64_t n_list, const int64_t *__restrict__ ids, int64_t own_b
     const int64_t k = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
     if (k >= n_list) return;
     const int64_t o = ids ? ids[k] : k;
-    if (o >= own_begin && o < own_end && keep[o] == 2) slot_flag[slot_of[k]] = 1;
+    if (o >= own_begin && o < own_end && keep[o] == 2 && slot_of[k] != ~0ull) slot_flag[slot_of[k]] = 1;
 }
 
 // out[k] = ids ? ids[sel[k]] : sel[k]  (list positions -> original items)
@@ -605,10 +628,21 @@ static int session_dedup(cyp_session *s, Scratch &sc, int64_t n, const uint64_t 
         Scratch ps;                                   // per pass
         DedupTable tab{};
         uint64_t *d_slot_of = nullptr;
-        int rc = alloc_table(n_list, ps, &tab, st);
+        // first pass over records gathered from several ranks: the table holds this rank's keys, the records of the lower ranks
+        // only probe it (those of the higher ranks cannot win against an own record at all)
+        const bool probe = passes == 0 && d_ids == nullptr && (own_begin > 0 || own_end < n_list);
+        int rc = alloc_table(probe ? own_end - own_begin : n_list, ps, &tab, st);
         if (rc != CYP_OK) return rc;
         S_CUDA(ps.alloc(&d_slot_of, n_list));
-        dedup_insert_kernel<<<blocks_for(n_list, kThreads), kThreads, 0, st>>>(n_list, d_hash, hash_stride, lo_mask, hi_mask, tab, d_slot_of);
+        if (probe) {
+            S_CUDA(cudaMemsetAsync(d_slot_of, 0xFF, sizeof(uint64_t) * n_list, st));
+            dedup_insert_kernel<<<blocks_for(own_end - own_begin, kThreads), kThreads, 0, st>>>(own_begin, own_end - own_begin, d_hash, hash_stride, lo_mask,
+                                                                                                hi_mask, tab, d_slot_of);
+            if (own_begin > 0)
+                dedup_probe_kernel<<<blocks_for(own_begin, kThreads), kThreads, 0, st>>>(own_begin, d_hash, hash_stride, lo_mask, hi_mask, tab, d_slot_of);
+        } else {
+            dedup_insert_kernel<<<blocks_for(n_list, kThreads), kThreads, 0, st>>>(0, n_list, d_hash, hash_stride, lo_mask, hi_mask, tab, d_slot_of);
+        }
         dedup_classify_kernel<<<blocks_for(n_list, kThreads), kThreads, 0, st>>>(n_list, d_ids, own_begin, own_end, passes, tab, d_slot_of,
                                                                                  d_keep, d_winner);
         S_CUDA(cudaGetLastError());
