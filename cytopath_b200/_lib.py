@@ -22,7 +22,7 @@ E_NOCROSSING = -4
 
 EXPORTS = [
     "cyp_version", "cyp_last_error", "cyp_device_count", "cyp_release_cached_memory",
-    "cyp_graph_create", "cyp_graph_create_f32", "cyp_graph_row_sum_range", "cyp_graph_destroy", "cyp_graph_info", "cyp_graph_layout", "cyp_graph_fetch_fused", "cyp_graph_fetch_cdf", "cyp_graph_build_ms",
+    "cyp_graph_create", "cyp_graph_create_f32", "cyp_graph_row_sum_range", "cyp_graph_destroy", "cyp_graph_info", "cyp_graph_layout", "cyp_graph_fetch_fused", "cyp_graph_fetch_cdf", "cyp_graph_build_ms", "cyp_graph_placement",
     "cyp_power_iteration", "cyp_walk", "cyp_walk_device", "cyp_walk_variant_name", "cyp_transition_scores",
     "cyp_session_create", "cyp_session_destroy", "cyp_session_round", "cyp_session_rows",
     "cyp_session_fetch_index", "cyp_session_fetch_rows", "cyp_session_slot_counts", "cyp_session_round_records",
@@ -110,6 +110,7 @@ def load():
     L.cyp_graph_fetch_fused.argtypes = [vp, vp, vp, vp]
     L.cyp_graph_fetch_cdf.argtypes = [vp, vp]
     L.cyp_graph_build_ms.argtypes = [vp, P(ctypes.c_float)]
+    L.cyp_graph_placement.argtypes = [vp, P(ctypes.c_float), P(ctypes.c_float), P(ci)]
     L.cyp_power_iteration.argtypes = [ci, i64, i64, vp, vp, vp, vp, vp, i32, vp, vp, vp]
     L.cyp_walk.argtypes = [vp, vp, i64, i64, i64, i64, i32, u64, u32, vp, vp, P(i64)]
     L.cyp_walk_device.argtypes = [vp, vp, i64, i64, i64, i64, i32, u64, u32, vp, vp, vp, ci, vp]
@@ -314,6 +315,12 @@ class Graph:
         lo, hi = ctypes.c_double(), ctypes.c_double()
         check(load().cyp_graph_row_sum_range(self._h, ctypes.byref(lo), ctypes.byref(hi)))
         return lo.value, hi.value
+
+    def placement(self) -> dict:
+        """Probe times of the placement calibration (0: the graph is small, not calibrated) and the number of moves."""
+        a, b, m = ctypes.c_float(), ctypes.c_float(), ctypes.c_int()
+        check(load().cyp_graph_placement(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(m)))
+        return {"probe_ms_before": a.value, "probe_ms_after": b.value, "moves": m.value}
 
     def build_ms(self) -> float:
         ms = ctypes.c_float()

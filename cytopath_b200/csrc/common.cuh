@@ -172,6 +172,8 @@ struct cyp_graph {
     int64_t v2_edge_units = 0;
     uint32_t *d_word = nullptr;          // [n] row word of every cell (the roots start from it)
     mutable uint64_t labels2_owner = 0;  // id of the session whose label codes are in the fused rows' headers
+    float placement_ms_before = 0.f, placement_ms_after = 0.f;     // probe times of calibrate_placement (0: not calibrated)
+    int placement_moves = 0;
 };
 
 namespace cyp {
@@ -206,6 +208,8 @@ int graph_alloc_like(const GraphWire &w, int device, cyp_graph **out);
 void graph_device_arrays(const cyp_graph *g, std::vector<std::pair<void *, size_t>> *out);
 // moves every device array of the graph into a fresh allocation (device copy), frees the old one
 int graph_rehome(cyp_graph *g);
+// placement.cu: times a short walk on the current placement of the fused rows and on two fresh allocations, keeps the fastest
+int calibrate_placement(cyp_graph *g, float *ms_before, float *ms_after, int *moves);
 // graph.cu: builds d_q16 and d_edge (the arrays of the step kernels other than walk_v2.cu) if they do not exist yet.
 // Synchronous, default stream; call before launching one of those kernels.
 int ensure_edge_records(const cyp_graph *g);

@@ -748,6 +748,13 @@ static int graph_create_impl(int device, int64_t n_cells, int64_t nnz, const int
             return rc2;
         }
     }
+    {   // graphs above half the L2: pick the better of three placements of the fused rows (placement.cu)
+        const int rc3 = calibrate_placement(g, &g->placement_ms_before, &g->placement_ms_after, &g->placement_moves);
+        if (rc3 != CYP_OK) {
+            graph_free(g);
+            return rc3;
+        }
+    }
     *out = g;
     return CYP_OK;
 }
@@ -803,6 +810,14 @@ extern "C" int cyp_graph_fetch_fused(const cyp_graph *g, uint8_t *h_rows, uint32
     CYP_CUDA(cudaMemcpy(h_rows, g->d_rows2, static_cast<size_t>(g->v2_sectors) * 32, cudaMemcpyDeviceToHost));
     CYP_CUDA(cudaMemcpy(h_words, g->d_word, sizeof(uint32_t) * g->n, cudaMemcpyDeviceToHost));
     CYP_CUDA(cudaMemcpy(h_targets, g->d_edge4, sizeof(uint32_t) * 4 * static_cast<size_t>(g->v2_edge_units), cudaMemcpyDeviceToHost));
+    return CYP_OK;
+}
+
+extern "C" int cyp_graph_placement(const cyp_graph *g, float *probe_ms_before, float *probe_ms_after, int *moves) {
+    CYP_REQUIRE(g != nullptr, "cyp_graph_placement: NULL graph");
+    if (probe_ms_before) *probe_ms_before = g->placement_ms_before;
+    if (probe_ms_after) *probe_ms_after = g->placement_ms_after;
+    if (moves) *moves = g->placement_moves;
     return CYP_OK;
 }
 

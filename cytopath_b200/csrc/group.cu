@@ -467,38 +467,7 @@ extern "C" int cyp_group_graph_create(cyp_group *g, int64_t n_cells, int64_t nnz
     if (rc != CYP_OK) return rc;
     std::vector<std::vector<std::pair<void *, size_t>>> arrays(g->n_local);
     for (int i = 0; i < g->n_local; ++i) graph_device_arrays(g->graphs[i], &arrays[i]);
-    const char *stage_env = getenv("CYP_BCAST_STAGE");
-    if (stage_env && stage_env[0] == '1') {
-        // developer switch: receivers take every array through one scratch buffer + a device copy, so that NCCL never touches the
-        // graph's own allocations
-        size_t max_bytes = 0;
-        for (auto &a : arrays[0]) max_bytes = std::max(max_bytes, a.second);
-        std::vector<void *> stage(g->n_local, nullptr);
-        for (int i = 0; i < g->n_local; ++i) {
-            if (i == root_local) continue;
-            DeviceGuard guard(g->devices[i]);
-            G_CUDA(cudaMalloc(&stage[i], max_bytes));
-        }
-        for (size_t a = 0; a < arrays[0].size(); ++a) {
-            G_NCCL(g_nccl.GroupStart());
-            for (int i = 0; i < g->n_local; ++i) {
-                void *buf = i == root_local ? arrays[i][a].first : stage[i];
-                G_NCCL(g_nccl.Broadcast(buf, buf, arrays[i][a].second, ncclChar, root_rank, g->comms[i], g->streams[i]));
-            }
-            G_NCCL(g_nccl.GroupEnd());
-            for (int i = 0; i < g->n_local; ++i) {
-                if (i == root_local) continue;
-                DeviceGuard guard(g->devices[i]);
-                G_CUDA(cudaMemcpyAsync(arrays[i][a].first, stage[i], arrays[i][a].second, cudaMemcpyDeviceToDevice, g->streams[i]));
-            }
-        }
-        rc = sync_streams(g);
-        for (int i = 0; i < g->n_local; ++i) {
-            DeviceGuard guard(g->devices[i]);
-            if (stage[i]) cudaFree(stage[i]);
-        }
-        if (rc != CYP_OK) return rc;
-    } else {
+    {
         G_NCCL(g_nccl.GroupStart());
         for (size_t a = 0; a < arrays[0].size(); ++a)
             for (int i = 0; i < g->n_local; ++i)
@@ -507,14 +476,13 @@ extern "C" int cyp_group_graph_create(cyp_group *g, int64_t n_cells, int64_t nnz
         rc = sync_streams(g);
         if (rc != CYP_OK) return rc;
     }
-    if (const char *rh = getenv("CYP_BCAST_REHOME")) {
-        if (rh[0] == '1' || rh[0] == '2')
-            for (int i = 0; i < g->n_local; ++i) {
-                if (i == root_local && rh[0] == '1') continue;
-                rc = graph_rehome(g->graphs[i]);
-                if (rc != CYP_OK) return rc;
-            }
-    }
+    // the received arrays landed wherever the allocator put them: same placement calibration as after a local build
+    rc = for_each_local(g, [&](int i) -> int {
+        if (i == root_local) return CYP_OK;
+        cyp_graph *gr = g->graphs[i];
+        return calibrate_placement(gr, &gr->placement_ms_before, &gr->placement_ms_after, &gr->placement_moves);
+    });
+    if (rc != CYP_OK) return rc;
     if (ms_broadcast) *ms_broadcast = static_cast<float>(now_ms() - t1);
     return CYP_OK;
 }

@@ -1,0 +1,113 @@
+// Placement calibration of the fused rows.
+//
+// Where the fused rows (and the target words) land in physical memory decides which L2 slices / HBM channels serve the hot
+// rows of the graph, and the busiest slice bounds the step kernel: the same binary on the same graph runs K2 in one of two
+// modes, ~9.45 ms or ~11.3 ms per launch at C4 (profiles/r02_scale_probe.md: 8 ranks of one box, identical arrays; a fresh
+// allocation of the same bytes flips the mode at random, ~70 % good).  So after a graph above half the L2 has been built (or
+// received over NVLink) the library times a short plain-mode walk from pseudo-random roots on the current placement and on
+// two fresh allocations of the same arrays, and keeps the fastest.  ~0.4 ms per probe, ~0.1 ms per copy of 128 MB.
+#include <cstdio>
+#include <cstdlib>
+
+#include "walk.cuh"
+
+namespace cyp {
+
+namespace {
+
+__global__ void __launch_bounds__(256) probe_roots_kernel(int64_t n_roots, int64_t n_cells, int32_t *__restrict__ roots) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+    if (i < n_roots) roots[i] = static_cast<int32_t>((static_cast<uint64_t>(i) * 0x9E3779B97F4A7C15ull >> 20) % static_cast<uint64_t>(n_cells));
+}
+
+}  // namespace
+
+int calibrate_placement(cyp_graph *g, float *ms_before, float *ms_after, int *moves) {
+    if (ms_before) *ms_before = 0.f;
+    if (ms_after) *ms_after = 0.f;
+    if (moves) *moves = 0;
+    if (!g->v2_ok || !walk_auto_is_v2(g) || g->rows2_bytes < (64ll << 20)) return CYP_OK;
+    if (const char *e = getenv("CYP_NO_CALIBRATE")) if (e[0] == '1') return CYP_OK;
+    DeviceGuard guard(g->device);
+    const int sms = current_sm_count();
+    if (sms <= 0) return CYP_OK;
+    const int64_t n_roots = 4096, W = static_cast<int64_t>(sms) * 1280;
+    const int32_t nt = 128;
+    int32_t *d_roots = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaError_t e = dev_alloc(&d_roots, sizeof(int32_t) * n_roots);
+    if (e == cudaSuccess) e = cudaEventCreate(&ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&ev1);
+    auto cleanup = [&]() {
+        dev_free(d_roots);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+    };
+    if (e != cudaSuccess) { cleanup(); return fail(CYP_E_CUDA, std::string("calibrate_placement: ") + cudaGetErrorString(e)); }
+    probe_roots_kernel<<<static_cast<unsigned>((n_roots + 255) / 256), 256>>>(n_roots, g->n, d_roots);
+    WalkParams p{};
+    p.rows = g->d_row; p.cdf = g->d_cdf; p.edge = g->d_edge;
+    p.roots = d_roots; p.sims_per_root = (W + n_roots - 1) / n_roots;
+    p.walker_begin = 0; p.n_walkers = W; p.nt = nt; p.round = 0xC0FFEEu; p.seed = 0x5EEDull;
+    p.uniforms = nullptr; p.out_seq = nullptr; p.ld = nt + 1; p.nocross = nullptr;      // plain mode without a trajectory buffer: gathers only
+    auto probe = [&](float *ms) -> int {
+        float best = 1e30f;
+        for (int rep = 0; rep < 2; ++rep) {                      // the first launch of a process also loads the kernel
+            cudaEventRecord(ev0, nullptr);
+            const int rc = launch_walk(g, p, kModePlain, 0, nullptr);
+            if (rc != CYP_OK) return rc;
+            cudaEventRecord(ev1, nullptr);
+            if (cudaEventSynchronize(ev1) != cudaSuccess) return fail(CYP_E_CUDA, "calibrate_placement: probe failed");
+            float t = 0.f;
+            cudaEventElapsedTime(&t, ev0, ev1);
+            if (t < best) best = t;
+        }
+        *ms = best;
+        return CYP_OK;
+    };
+    float best = 0.f;
+    int rc = probe(&best);
+    if (rc != CYP_OK) { cleanup(); return rc; }
+    if (ms_before) *ms_before = best;
+    const size_t edge_bytes = sizeof(uint32_t) * 4 * static_cast<size_t>(g->v2_edge_units + 1);
+    int moved = 0;
+    for (int trial = 0; trial < 2; ++trial) {
+        unsigned char *rows_new = nullptr;
+        uint32_t *edge_new = nullptr;
+        e = dev_alloc(&rows_new, static_cast<size_t>(g->rows2_bytes));
+        if (e == cudaSuccess) e = dev_alloc(&edge_new, edge_bytes);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(rows_new, g->d_rows2, static_cast<size_t>(g->rows2_bytes), cudaMemcpyDeviceToDevice, nullptr);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(edge_new, g->d_edge4, edge_bytes, cudaMemcpyDeviceToDevice, nullptr);
+        if (e != cudaSuccess) {                                   // out of memory: keep what we have
+            cudaGetLastError();
+            dev_free(rows_new); dev_free(edge_new);
+            break;
+        }
+        unsigned char *rows_old_base = g->d_rows2_base, *rows_old = g->d_rows2;
+        uint32_t *edge_old = g->d_edge4;
+        g->d_rows2_base = g->d_rows2 = rows_new;
+        g->d_edge4 = edge_new;
+        float t = 0.f;
+        rc = probe(&t);
+        if (rc == CYP_OK && t < 0.97f * best) {                   // a better placement: the old arrays go
+            best = t;
+            ++moved;
+            dev_free(rows_old_base);
+            dev_free(edge_old);
+        } else {                                                  // not better: back to the old arrays
+            g->d_rows2_base = rows_old_base; g->d_rows2 = rows_old; g->d_edge4 = edge_old;
+            cudaStreamSynchronize(nullptr);
+            dev_free(rows_new);
+            dev_free(edge_new);
+            if (rc != CYP_OK) { cleanup(); return rc; }
+        }
+    }
+    if (ms_after) *ms_after = best;
+    if (moves) *moves = moved;
+    static const bool trace = getenv("CYP_TRACE") != nullptr;
+    if (trace) fprintf(stderr, "[cyp trace] placement: device %d probe %.3f -> %.3f ms (%d moves)\n", g->device, ms_before ? *ms_before : 0.f, best, moved);
+    cleanup();
+    return CYP_OK;
+}
+
+}  // namespace cyp
