@@ -380,8 +380,14 @@ find_walker_kernel(int64_t n, const uint64_t *__restrict__ rec, uint64_t first_w
 
 __global__ void __launch_bounds__(kThreads)
 slot_histogram_kernel(int64_t n, const int32_t *__restrict__ slot, unsigned long long *__restrict__ counts) {
+    // walkers pile up on few end points: one atomic per distinct slot of a warp, not per row (a hot counter serialises)
     const int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
-    if (i < n) atomicAdd(counts + slot[i], 1ull);
+    const bool in = i < n;
+    const unsigned active = __ballot_sync(0xffffffffu, in);
+    if (!in) return;
+    const int32_t s = slot[i];
+    const unsigned same = __match_any_sync(active, s);
+    if ((threadIdx.x & 31) == __ffs(same) - 1) atomicAdd(counts + s, static_cast<unsigned long long>(__popc(same)));
 }
 
 // the label code lives in byte 6 of every fused row block's header (walk_v2.cuh reads it with the header)
