@@ -174,6 +174,7 @@ struct cyp_graph {
     mutable uint64_t labels2_owner = 0;  // id of the session whose label codes are in the fused rows' headers
     float placement_ms_before = 0.f, placement_ms_after = 0.f;     // probe times of calibrate_placement (0: not calibrated)
     int placement_moves = 0;
+    mutable int placement_state = 0;     // 0: the first large walk calibrates the placement of the fused rows (placement.cu); 1: done
 };
 
 namespace cyp {
@@ -208,11 +209,7 @@ int graph_alloc_like(const GraphWire &w, int device, cyp_graph **out);
 void graph_device_arrays(const cyp_graph *g, std::vector<std::pair<void *, size_t>> *out);
 // moves every device array of the graph into a fresh allocation (device copy), frees the old one
 int graph_rehome(cyp_graph *g);
-// graph.cu: cyp_graph_create without the placement calibration (a group calibrates all its ranks together, after the broadcast)
-int graph_create_uncalibrated(int device, int64_t n_cells, int64_t nnz, const int64_t *h_row_ptr, const int32_t *h_col, const void *h_val,
-                              bool val_f32, int cdf_mode, cyp_graph **out);
-// placement.cu: times a short walk on the current placement of the fused rows and on two fresh allocations, keeps the fastest
-int calibrate_placement(cyp_graph *g, float *ms_before, float *ms_after, int *moves);
+
 // graph.cu: builds d_q16 and d_edge (the arrays of the step kernels other than walk_v2.cu) if they do not exist yet.
 // Synchronous, default stream; call before launching one of those kernels.
 int ensure_edge_records(const cyp_graph *g);

@@ -545,7 +545,7 @@ static void graph_free(cyp_graph *g) {
 // host lays out the rows meanwhile; K1 and K1b of a chunk start as soon as the chunk has landed, so at atlas scale
 // (628 MB of CSR over PCIe) the kernels and the host work hide behind the upload.
 static int graph_create_impl(int device, int64_t n_cells, int64_t nnz, const int64_t *h_row_ptr, const int32_t *h_col,
-                             const void *h_val, bool val_f32, int cdf_mode, cyp_graph **out, bool calibrate = true) {
+                             const void *h_val, bool val_f32, int cdf_mode, cyp_graph **out) {
     CYP_REQUIRE(out != nullptr, "cyp_graph_create: out is NULL");
     *out = nullptr;
     CYP_REQUIRE(n_cells > 0 && nnz > 0, "cyp_graph_create: empty matrix");
@@ -748,23 +748,9 @@ static int graph_create_impl(int device, int64_t n_cells, int64_t nnz, const int
             return rc2;
         }
     }
-    if (calibrate) {   // graphs above half the L2: pick the better of three placements of the fused rows (placement.cu)
-        const int rc3 = calibrate_placement(g, &g->placement_ms_before, &g->placement_ms_after, &g->placement_moves);
-        if (rc3 != CYP_OK) {
-            graph_free(g);
-            return rc3;
-        }
-    }
     *out = g;
     return CYP_OK;
 }
-
-namespace cyp {
-int graph_create_uncalibrated(int device, int64_t n_cells, int64_t nnz, const int64_t *h_row_ptr, const int32_t *h_col, const void *h_val,
-                              bool val_f32, int cdf_mode, cyp_graph **out) {
-    return graph_create_impl(device, n_cells, nnz, h_row_ptr, h_col, h_val, val_f32, cdf_mode, out, false);
-}
-}  // namespace cyp
 
 extern "C" int cyp_graph_create(int device, int64_t n_cells, int64_t nnz, const int64_t *h_row_ptr,
                                 const int32_t *h_col, const double *h_val, int cdf_mode, cyp_graph **out) {

@@ -416,10 +416,8 @@ extern "C" int cyp_group_graph_create(cyp_group *g, int64_t n_cells, int64_t nnz
     const bool have_root = root_local >= 0 && root_local < g->n_local;
     const double t0 = now_ms();
     if (have_root) {
-        // a group of several ranks calibrates the placement of the fused rows on all of them together, after the broadcast
-        const int rc = g->world > 1 ? graph_create_uncalibrated(g->devices[root_local], n_cells, nnz, h_row_ptr, h_col, h_val, val_is_f32 != 0, cdf_mode, &g->graphs[root_local])
-                       : val_is_f32 ? cyp_graph_create_f32(g->devices[root_local], n_cells, nnz, h_row_ptr, h_col, static_cast<const float *>(h_val), cdf_mode, &g->graphs[root_local])
-                                    : cyp_graph_create(g->devices[root_local], n_cells, nnz, h_row_ptr, h_col, static_cast<const double *>(h_val), cdf_mode, &g->graphs[root_local]);
+        const int rc = val_is_f32 ? cyp_graph_create_f32(g->devices[root_local], n_cells, nnz, h_row_ptr, h_col, static_cast<const float *>(h_val), cdf_mode, &g->graphs[root_local])
+                                  : cyp_graph_create(g->devices[root_local], n_cells, nnz, h_row_ptr, h_col, static_cast<const double *>(h_val), cdf_mode, &g->graphs[root_local]);
         if (rc != CYP_OK && g->world == 1) return rc;
         // with other ranks waiting in the broadcast a failure must reach them too: n = -1 in the wire header
         if (rc != CYP_OK) g->graphs[root_local] = nullptr;
@@ -478,12 +476,6 @@ extern "C" int cyp_group_graph_create(cyp_group *g, int64_t n_cells, int64_t nnz
         rc = sync_streams(g);
         if (rc != CYP_OK) return rc;
     }
-    // the arrays landed wherever the allocator put them: every rank calibrates the placement of its fused rows now
-    rc = for_each_local(g, [&](int i) -> int {
-        cyp_graph *gr = g->graphs[i];
-        return calibrate_placement(gr, &gr->placement_ms_before, &gr->placement_ms_after, &gr->placement_moves);
-    });
-    if (rc != CYP_OK) return rc;
     if (ms_broadcast) *ms_broadcast = static_cast<float>(now_ms() - t1);
     return CYP_OK;
 }

@@ -3,9 +3,11 @@
 // Where the fused rows (and the target words) land in physical memory decides which L2 slices / HBM channels serve the hot
 // rows of the graph, and the busiest slice bounds the step kernel: the same binary on the same graph runs K2 in one of two
 // modes, ~9.45 ms or ~11.3 ms per launch at C4 (profiles/r02_scale_probe.md: 8 ranks of one box, identical arrays; a fresh
-// allocation of the same bytes flips the mode at random, ~70 % good).  So after a graph above half the L2 has been built (or
-// received over NVLink) the library times a short plain-mode walk from pseudo-random roots on the current placement and on
-// two fresh allocations of the same arrays, and keeps the fastest.  ~0.2 ms per probe, ~0.1 ms per copy of 336 MB.
+// allocation of the same bytes flips the mode at random, ~70 % good).  So the FIRST large walk on a graph above half the L2
+// is preceded by a calibration: a short plain-mode walk of the caller's own walkers (one wave of CTAs, the first 64 steps)
+// is timed on the current placement and on three fresh allocations of the rows + target words, and the fastest is kept.
+// ~0.2 ms per probe, ~0.1 ms per copy of 336 MB, once per graph.
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -14,16 +16,7 @@
 
 namespace cyp {
 
-namespace {
-
-__global__ void __launch_bounds__(256) probe_roots_kernel(int64_t n_roots, int64_t n_cells, int32_t *__restrict__ roots) {
-    const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
-    if (i < n_roots) roots[i] = static_cast<int32_t>((static_cast<uint64_t>(i) * 0x9E3779B97F4A7C15ull >> 20) % static_cast<uint64_t>(n_cells));
-}
-
-}  // namespace
-
-int calibrate_placement(cyp_graph *g, float *ms_before, float *ms_after, int *moves) {
+int calibrate_placement(cyp_graph *g, const WalkParams &like, float *ms_before, float *ms_after, int *moves) {
     if (ms_before) *ms_before = 0.f;
     if (ms_after) *ms_after = 0.f;
     if (moves) *moves = 0;
@@ -32,25 +25,21 @@ int calibrate_placement(cyp_graph *g, float *ms_before, float *ms_after, int *mo
     DeviceGuard guard(g->device);
     const int sms = current_sm_count();
     if (sms <= 0) return CYP_OK;
-    const int64_t n_roots = 4096, W = static_cast<int64_t>(sms) * 1280;
-    const int32_t nt = 64;
-    int32_t *d_roots = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    cudaError_t e = dev_alloc(&d_roots, sizeof(int32_t) * n_roots);
-    if (e == cudaSuccess) e = cudaEventCreate(&ev0);
+    cudaError_t e = cudaEventCreate(&ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&ev1);
     auto cleanup = [&]() {
-        dev_free(d_roots);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
     };
     if (e != cudaSuccess) { cleanup(); return fail(CYP_E_CUDA, std::string("calibrate_placement: ") + cudaGetErrorString(e)); }
-    probe_roots_kernel<<<static_cast<unsigned>((n_roots + 255) / 256), 256>>>(n_roots, g->n, d_roots);
-    WalkParams p{};
-    p.rows = g->d_row; p.cdf = g->d_cdf; p.edge = g->d_edge;
-    p.roots = d_roots; p.sims_per_root = (W + n_roots - 1) / n_roots;
-    p.walker_begin = 0; p.n_walkers = W; p.nt = nt; p.round = 0xC0FFEEu; p.seed = 0x5EEDull;
-    p.uniforms = nullptr; p.out_seq = nullptr; p.ld = nt + 1; p.nocross = nullptr;      // plain mode without a trajectory buffer: gathers only
+    // the probe: the caller's own walkers (same roots, same stream of uniforms), one full wave of CTAs, the first 64 steps --
+    // where the walkers still sit on few rows and the placement matters most; plain mode without a trajectory buffer
+    WalkParams p = like;
+    p.n_walkers = std::min<int64_t>(like.n_walkers, static_cast<int64_t>(sms) * 1280);
+    p.nt = std::min<int32_t>(like.nt, 64);
+    p.uniforms = nullptr; p.replay = nullptr; p.out_seq = nullptr; p.ld = p.nt + 1; p.nocross = nullptr;
+    p.out_slot = nullptr; p.out_hash = nullptr;
     auto probe = [&](float *ms) -> int {
         static std::atomic<bool> loaded{false};                   // the first launch of a process also loads the kernel: one extra launch, once
         float best = 1e30f;
@@ -73,7 +62,7 @@ int calibrate_placement(cyp_graph *g, float *ms_before, float *ms_after, int *mo
     if (ms_before) *ms_before = best;
     const size_t edge_bytes = sizeof(uint32_t) * 4 * static_cast<size_t>(g->v2_edge_units + 1);
     int moved = 0;
-    for (int trial = 0; trial < 2; ++trial) {
+    for (int trial = 0; trial < 3; ++trial) {
         unsigned char *rows_new = nullptr;
         uint32_t *edge_new = nullptr;
         e = dev_alloc(&rows_new, static_cast<size_t>(g->rows2_bytes));
@@ -91,7 +80,7 @@ int calibrate_placement(cyp_graph *g, float *ms_before, float *ms_after, int *mo
         g->d_edge4 = edge_new;
         float t = 0.f;
         rc = probe(&t);
-        if (rc == CYP_OK && t < 0.97f * best) {                   // a better placement: the old arrays go
+        if (rc == CYP_OK && t < 0.98f * best) {                   // a better placement: the old arrays go
             best = t;
             ++moved;
             dev_free(rows_old_base);
@@ -108,6 +97,7 @@ int calibrate_placement(cyp_graph *g, float *ms_before, float *ms_after, int *mo
     if (moves) *moves = moved;
     static const bool trace = getenv("CYP_TRACE") != nullptr;
     if (trace) fprintf(stderr, "[cyp trace] placement: device %d probe %.3f -> %.3f ms (%d moves)\n", g->device, ms_before ? *ms_before : 0.f, best, moved);
+    g->placement_ms_before = ms_before ? *ms_before : 0.f;
     cleanup();
     return CYP_OK;
 }

@@ -121,6 +121,10 @@ struct WalkerDigest {
 // Chooses lanes/unroll from the mean row length so that one chunk covers a typical row.
 WalkVariant pick_walk_variant(const cyp_graph *g, int variant);
 
+// placement.cu: times a short walk of the caller's walkers on the current placement of the fused rows and on three fresh
+// allocations, keeps the fastest (once per graph, before its first large walk)
+int calibrate_placement(cyp_graph *g, const WalkParams &like, float *ms_before, float *ms_after, int *moves);
+
 // Enqueues K2 on `stream`.  Returns a CYP_* code.
 int launch_walk(const cyp_graph *g, const WalkParams &p, WalkMode mode, int variant, cudaStream_t stream);
 

@@ -85,9 +85,9 @@ int cyp_graph_layout(const cyp_graph *g, int *fused, int64_t *row_block_bytes, i
  * padded to 4 words).  Fails with CYP_E_INVALID when the graph has no fused rows. */
 int cyp_graph_fetch_fused(const cyp_graph *g, uint8_t *h_rows, uint32_t *h_words, uint32_t *h_targets);
 /* Placement calibration (graphs whose fused rows exceed half the L2): where the rows land in physical memory decides which
- * L2 slices serve the hot rows, and the same kernel runs 20 % apart on identical arrays; the library times a short walk on
- * the placement it got and on two fresh allocations and keeps the fastest.  Probe times before / after (0: not calibrated)
- * and how often the arrays were moved. */
+ * L2 slices serve the hot rows, and the same kernel runs 20 % apart on identical arrays; before the first large walk on such
+ * a graph the library times a short walk of the caller's own walkers on the placement it got and on three fresh allocations
+ * and keeps the fastest.  Probe times before / after (0: not calibrated yet) and how often the arrays were moved. */
 int cyp_graph_placement(const cyp_graph *g, float *probe_ms_before, float *probe_ms_after, int *moves);
 /* Milliseconds the K1 prefix-sum kernel took when the graph was created (CUDA events). */
 int cyp_graph_build_ms(const cyp_graph *g, float *ms);
