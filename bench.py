@@ -335,13 +335,13 @@ def run_b200(args, w):
     sims_per_root = -(-total // n_roots)
     w0 = rank * W
 
-    # ---- resident state: graph (K1 on rank 0 + NVLink broadcast), roots, trajectory buffer
-    Cp, _pins = pinned_csr(C) if rank == 0 else (None, None)
-    if os.environ.get("BENCH_EACH_RANK_UPLOADS"):             # probe: every rank builds its own graph from the host CSR (round 1's way)
-        graph = _lib.Graph(C, mode, local_rank)
-    else:
-        gstat = group.create_graph(Cp, mode, 0, shape=(C.shape[0], C.nnz))
-        graph = group.graph
+    # ---- resident state: graph, roots, trajectory buffer.  Every rank holds the host CSR (as every torchrun process of a
+    # real run holds the AnnData): each uploads 1/world of it from pinned memory, an all-gather over NVLink completes it,
+    # every device runs K1.  BENCH_ROOT_UPLOAD=1: rank 0 uploads everything and broadcasts the built arrays instead.
+    sharded = world > 1 and not os.environ.get("BENCH_ROOT_UPLOAD")
+    Cp, _pins = pinned_csr(C) if (rank == 0 or sharded) else (None, None)
+    gstat = group.create_graph(Cp, mode, 0, shape=(C.shape[0], C.nnz), sharded=sharded)
+    graph = group.graph
     info = graph.info()
     kernel_name = graph.variant_name(args.variant)
     d_roots = torch.tensor(roots, dtype=torch.int32, device=dev)
@@ -453,8 +453,8 @@ def run_b200(args, w):
                                   "how": "cyp_gather_ceiling: 8 independent 128-byte random gathers in flight per 8 lanes, same footprint, same run"}
         roof["gather_ceiling_frac"] = (W * nt / (ms_launch * 1e-3)) / ceil_g
 
-    # ---- e2e through the C ABI with HOST buffers, every step: the CSR from pinned host memory on rank 0 -> K1 -> NVLink
-    # broadcast of the built arrays -> per-device session -> one sampling round (K2 + K3, all-gather of the 24-byte
+    # ---- e2e through the C ABI with HOST buffers, every step: the CSR from pinned host memory (each rank its 1/world slice)
+    # -> NVLink all-gather -> K1 on every device -> per-device session -> one sampling round (K2 + K3, all-gather of the 24-byte
     # records, cross-rank first-occurrence prune, all-gather of the index) -> final selection (replay of the picked
     # walkers split over the ranks, all-gather of the int32 sequences) -> rows + scores on the host
     trunc = np.array([c[:8] for c in g.clusters], dtype="U8")
@@ -476,7 +476,7 @@ def run_b200(args, w):
 
     def e2e_step(i, grp, root_csr, per_rank_walkers):
         t0 = time.perf_counter()
-        gs = grp.create_graph(root_csr, mode, 0, shape=(C.shape[0], C.nnz))
+        gs = grp.create_graph(root_csr, mode, 0, shape=(C.shape[0], C.nnz), sharded=sharded and grp.world > 1)
         t0 = lap("graph_create", t0)
         grp.create_session(roots, cell_code, len(code_names), 2, end_slot, len(end_cells), max_steps, True, args.seed)
         t0 = lap("session_create", t0)
@@ -508,7 +508,8 @@ def run_b200(args, w):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = total * nt * e2e_steps / float(t.item())
-    h2d = (C.indptr.shape[0] * 8 + C.nnz * 12) + (roots.nbytes + cell_code.nbytes + end_slot.nbytes) * world       # the CSR once (rank 0), the session arrays per rank
+    # whole job: the column / value arrays once (one slice per rank), the row offsets and the session arrays on every rank
+    h2d = C.nnz * 12 + (C.indptr.shape[0] * 8 * (world if sharded else 1)) + (roots.nbytes + cell_code.nbytes + end_slot.nbytes) * world
     digest_n = group.digest()
 
     # ---- parity self-check of the multi-GPU path: the global index of kept sequences of the last e2e round must be the one
@@ -528,9 +529,18 @@ def run_b200(args, w):
             solo.close()
             e2e_ms.clear(); e2e_ms.update(e2e_keep); last.clear(); last.update(last_keep)
         r, s_ = last["round"], last["select"]
-        multi = {"collectives": "ncclBroadcast(graph arrays) + per round ncclAllGather(stats), ncclAllGather(24-byte records), ncclAllGather(walker, slot) + "
+        gl = last["graph"]
+        if gl.get("sharded"):
+            graph_part = {"graph": "every rank uploads 1/%d of the CSR, ncclAllGather completes it, K1 on every device" % world,
+                          "graph_upload_ms": gl["ms_upload"], "graph_gather_ms": gl["ms_gather"],
+                          "graph_gather_bytes_per_rank": int(C.nnz * 12 * (world - 1) // world)}
+        else:
+            graph_part = {"graph": "rank 0 uploads the CSR and runs K1, ncclBroadcast of the built arrays",
+                          "graph_broadcast_ms": gl["ms_broadcast"], "graph_broadcast_bytes": int(info["device_bytes"])}
+        multi = {"collectives": ("ncclAllGather(CSR slices)" if gl.get("sharded") else "ncclBroadcast(graph arrays)") +
+                                " + per round ncclAllGather(stats), ncclAllGather(24-byte records), ncclAllGather(walker, slot) + "
                                 "ncclAllGather(selected int32 sequences)",
-                 "graph_broadcast_ms": last["graph"]["ms_broadcast"], "graph_broadcast_bytes": int(info["device_bytes"]),
+                 **graph_part,
                  "round_exchange_bytes_per_rank": int(r["exchange_bytes"]), "round_exchange_ms": r["ms_exchange"], "round_local_ms": r["ms_local"],
                  "select_gather_bytes": int(s_.get("gather_bytes", 0)), "select_gather_ms": s_.get("ms_gather"),
                  "kept_global_last_round": int(r["n_kept"]), "replayed_last_round": int(r["n_replayed"]),
@@ -572,7 +582,7 @@ def run_b200(args, w):
                "rounds": len(b["rounds"]), "max_steps": int(ad.uns["run_info"]["simulation_steps"]),
                "rows_out": int(ad.uns["samples"]["cell_sequences"].shape[0]),
                "host_ms": {k: round(v, 1) for k, v in b["timing"].get("host_ms", {}).items()},
-               "ms": {"graph_build": b["timing"]["graph"]["ms_build"], "graph_broadcast": b["timing"]["graph"]["ms_broadcast"],
+               "ms": {**{"graph_" + k[3:]: v for k, v in b["timing"]["graph"].items() if k.startswith("ms_")},
                       "rounds_local": sum(r["ms_local"] for r in b["rounds"]), "rounds_exchange": sum(r["ms_exchange"] for r in b["rounds"]),
                       "k2": sum(r["ms_walk"] for r in b["rounds"]), "k3": sum(r["ms_filter"] for r in b["rounds"]),
                       "select": sum(v for k, v in b["select"].items() if k.startswith("ms_"))},
@@ -586,14 +596,18 @@ def run_b200(args, w):
         "vs_baseline": None, "dtype": "f64" if mode == _lib.CDF_EXACT else "f32", "data": "synthetic",
         "config": base_config(w, args, int(C.nnz)),
         "kernel": kernel_name, "global_walkers": total,
-        "parallelism": "walkers sharded by id over %d GPU(s), graph built on rank 0 and broadcast over NVLink" % world,
+        "parallelism": ("walkers sharded by id over %d GPU(s); " % world) + (
+            "CSR uploaded in slices (1/%d per rank), all-gathered over NVLink, K1 on every device" % world if sharded else
+            "graph built on rank 0" + (" and broadcast over NVLink" if world > 1 else "")),
         "l2": "no flush: the step kernel walks %.2f GB of row blocks + target words and writes %.2f GB of trajectories per step, both above the 126 MB L2" % (
             (lay["row_block_bytes"] + lay["target_word_bytes"]) / 1e9, W * max_steps * 4 / 1e9),
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": "walker-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(last["d2h"]) * world,
                 "steps": e2e_steps, "kept_rows_last_step": int(st["n_kept"]), "ms_walk": st["ms_walk"], "ms_filter": st["ms_filter"],
                 "host_ms_per_step": {k: round(v / e2e_steps, 2) for k, v in e2e_ms.items()},
-                "what": "cyp_group_graph_create (pinned host CSR on rank 0 + K1 + NVLink broadcast), cyp_group_session_create, cyp_group_round "
+                "what": ("cyp_group_graph_create_sharded (every rank: its slice of the pinned host CSR + NVLink all-gather + K1)" if sharded else
+                         "cyp_group_graph_create (pinned host CSR on rank 0 + K1" + (" + NVLink broadcast)" if world > 1 else ")")) +
+                        ", cyp_group_session_create, cyp_group_round "
                         "(K2 + K3 + NCCL exchange), cyp_group_select of %d sequences (replay + all-gather) with scores, to the host" % n_fetch},
         "gpu_launches": args.steps,
         "roofline": roof,

@@ -29,7 +29,7 @@ EXPORTS = [
     "cyp_session_round_prune", "cyp_session_set_hash_bits", "cyp_session_set_chunk_walkers",
     "cyp_hausdorff_matrix", "cyp_directionality_scores", "cyp_graph_power_iteration",
     "cyp_group_create_local", "cyp_group_unique_id", "cyp_group_create_rank", "cyp_group_destroy", "cyp_group_release", "cyp_group_info",
-    "cyp_group_graph", "cyp_group_session", "cyp_group_graph_create", "cyp_group_session_create", "cyp_group_round",
+    "cyp_group_graph", "cyp_group_session", "cyp_group_graph_create", "cyp_group_graph_create_sharded", "cyp_group_session_create", "cyp_group_round",
     "cyp_group_rows", "cyp_group_fetch_index", "cyp_group_digest", "cyp_group_select", "cyp_group_set_chunk_walkers",
     "cyp_group_broadcast_bytes", "cyp_gather_ceiling",
 ]
@@ -142,6 +142,7 @@ def load():
     L.cyp_group_session.argtypes = [vp, ci]
     L.cyp_group_session.restype = vp
     L.cyp_group_graph_create.argtypes = [vp, i64, i64, vp, vp, vp, ci, ci, ci, P(ctypes.c_float), P(ctypes.c_float)]
+    L.cyp_group_graph_create_sharded.argtypes = [vp, i64, i64, vp, vp, vp, ci, ci, P(ctypes.c_float), P(ctypes.c_float), P(ctypes.c_float)]
     L.cyp_group_session_create.argtypes = [vp, vp, i64, vp, i32, i32, vp, i32, i32, ci, u64]
     L.cyp_group_round.argtypes = [vp, u32, i64, vp, P(GroupRoundStats)]
     L.cyp_group_rows.argtypes = [vp, P(i64)]
@@ -525,11 +526,29 @@ class Group:
     def rank(self) -> int:
         return self.first_rank
 
-    def create_graph(self, C, cdf_mode: int, root_rank: int = 0, shape=None) -> dict:
+    def create_graph(self, C, cdf_mode: int, root_rank: int = 0, shape=None, sharded: bool = False) -> dict:
         """K1 on `root_rank` from its canonical CSR `C`, then a broadcast of the device arrays.  Processes that do not
-        host the root rank may pass C=None with shape=(n_cells, nnz)."""
+        host the root rank may pass C=None with shape=(n_cells, nnz).
+        sharded=True (EVERY rank passes the same C): each rank uploads 1/world of the matrix, an all-gather over NVLink
+        completes it and every device builds the graph itself (cyp_group_graph_create_sharded)."""
         L = load()
         bms, xms = ctypes.c_float(), ctypes.c_float()
+        if sharded and self.world > 1:
+            if C is None:
+                raise ValueError("create_graph(sharded=True): every rank passes the matrix")
+            indptr = np.ascontiguousarray(C.indptr, dtype=np.int64)
+            indices = np.ascontiguousarray(C.indices, dtype=np.int32)
+            f32 = C.data.dtype == np.float32
+            data = np.ascontiguousarray(C.data, dtype=np.float32 if f32 else np.float64)
+            n, nnz = int(C.shape[0]), int(data.shape[0])
+            tms = ctypes.c_float()
+            check(L.cyp_group_graph_create_sharded(self._h, n, nnz, ptr(indptr), ptr(indices), ptr(data), int(f32), cdf_mode,
+                                                   ctypes.byref(bms), ctypes.byref(xms), ctypes.byref(tms)))
+            h = L.cyp_group_graph(self._h, 0)
+            dev = ctypes.c_int()
+            check(L.cyp_graph_info(h, None, None, None, None, ctypes.byref(dev), None))
+            self.graph = Graph.view(h, n, nnz, cdf_mode, dev.value)
+            return {"ms_upload": bms.value, "ms_gather": xms.value, "ms_total": tms.value, "sharded": True}
         if C is not None:
             indptr = np.ascontiguousarray(C.indptr, dtype=np.int64)
             indices = np.ascontiguousarray(C.indices, dtype=np.int32)
@@ -563,6 +582,16 @@ class Group:
 
     def session_handle(self, local_index: int = 0):
         return load().cyp_group_session(self._h, local_index)
+
+    def graph_view(self, local_index: int = 0) -> Graph:
+        """The graph of the i-th local device (owned by the group)."""
+        L = load()
+        h = L.cyp_group_graph(self._h, local_index)
+        if not h:
+            raise CytopathB200Error(-1, "the group has no graph on local device %d" % local_index)
+        dev = ctypes.c_int()
+        check(L.cyp_graph_info(h, None, None, None, None, ctypes.byref(dev), None))
+        return Graph.view(h, self.graph.n, self.graph.nnz, self.graph.cdf_mode, dev.value)
 
     def round(self, round_idx: int, sims_per_root: int, want_slot_counts: bool = True):
         """One sampling round over the whole group.  Returns (stats dict, per-slot counts of the sequences it added)."""

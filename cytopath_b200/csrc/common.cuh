@@ -178,19 +178,44 @@ struct cyp_graph {
 };
 
 namespace cyp {
+// K0 (layout.cu): the row layout on the device -- padded row offsets, fused-row words, target bases -- from the uploaded
+// CSR row offsets; the host only reads this summary.  Two candidates of "extra inline sectors per row" are measured at once.
+struct RowLayoutSummary {
+    int64_t units16;                             // sum of ceil(len / kRowAlign): the padded arrays hold units16 * kRowAlign elements
+    int64_t sectors[2];                          // total sectors of the fused rows, per candidate
+    int64_t units4;                              // sum of ceil(len / 4): 4-word units of the target array
+    int64_t hist[2][kV2MaxSectors + 1];          // rows per block size (saturating), per candidate
+    int32_t max_len;
+    int32_t max_sectors[2];
+    int32_t bad;                                 // a row length below 0 or above 2^30
+};
+struct RowLayoutScratch {
+    int64_t n = 0;
+    int extra[2] = {0, 0};
+    int64_t *d_scan = nullptr;                   // 4 x (n + 1): exclusive sums of units16, sectors[0], sectors[1], units4
+    void *d_tmp = nullptr;
+    size_t tmp_bytes = 0;
+    RowLayoutSummary *d_sum = nullptr;
+};
+cudaError_t layout_measure(int64_t n, int align_elems, const int64_t *d_row_ptr, int extra0, int extra1, RowLayoutScratch *s,
+                           cudaStream_t stream, RowLayoutSummary *h_out);
+cudaError_t layout_write(const RowLayoutScratch *s, const int64_t *d_row_ptr, int which, RowInfo *d_row, uint32_t *d_word, uint32_t *d_ebase,
+                         cudaStream_t stream);
+void layout_release(RowLayoutScratch *s);
 // K1b (rows_v2.cu): the fused rows, built from K1's output chunk by chunk; v2_finish sets g->v2_ok.
 struct V2Build {
     bool planned = false;
-    std::vector<uint32_t> word, ebase;       // per cell: row word; start of its targets in edge4 (units of 4 words)
+    int which = 0;                           // the candidate of RowLayoutSummary the plan took
     int64_t sectors = 0, units = 0;
     int max_sectors = 0, slot_sectors = 0, extra = 0, uniform = 0;
     size_t rows_bytes = 0;
-    uint32_t *d_ebase = nullptr;
+    uint32_t *d_ebase = nullptr;             // per cell: start of its targets in edge4 (units of 4 words)
     int *d_bad = nullptr;
 };
-bool v2_plan(const cyp_graph *g, const int64_t *h_row_ptr, V2Build *b);
+// the two candidates of extra inline sectors layout_measure should look at for this graph (CYP_V2_EXTRA pins both)
+void v2_candidates(int *extra0, int *extra1);
+bool v2_plan(const cyp_graph *g, const RowLayoutSummary &rows, const int extra[2], V2Build *b);
 cudaError_t v2_alloc(cyp_graph *g, V2Build *b);
-cudaError_t v2_upload(cyp_graph *g, V2Build *b, cudaStream_t stream);
 cudaError_t v2_launch(cyp_graph *g, V2Build *b, int64_t row_begin, int64_t row_end, cudaStream_t stream);
 cudaError_t v2_finish(cyp_graph *g, V2Build *b, bool codes_ok);
 void v2_release(cyp_graph *g, V2Build *b);
@@ -207,8 +232,15 @@ GraphWire graph_wire(const cyp_graph *g);
 int graph_alloc_like(const GraphWire &w, int device, cyp_graph **out);
 // (pointer, bytes) of every device array of the graph, in an order that only depends on the wire fields
 void graph_device_arrays(const cyp_graph *g, std::vector<std::pair<void *, size_t>> *out);
-// moves every device array of the graph into a fresh allocation (device copy), frees the old one
-int graph_rehome(cyp_graph *g);
+// The raw column / value arrays of a CSR that are already on the device (or on their way there: `ready` fires on the
+// stream that fills them).  What the group's sharded upload hands to the graph build, which takes ownership of both arrays.
+struct RawCsr {
+    int32_t *d_col = nullptr;
+    void *d_val = nullptr;          // float64 or float32
+    cudaEvent_t ready = nullptr;
+};
+// cyp_graph_create with the column / value arrays taken from `raw` instead of the host; h_row_ptr is still a host array
+int graph_create_raw(int device, int64_t n_cells, int64_t nnz, const int64_t *h_row_ptr, bool val_f32, int cdf_mode, const RawCsr &raw, cyp_graph **out);
 
 // graph.cu: builds d_q16 and d_edge (the arrays of the step kernels other than walk_v2.cu) if they do not exist yet.
 // Synchronous, default stream; call before launching one of those kernels.

@@ -417,45 +417,6 @@ void graph_device_arrays(const cyp_graph *g, std::vector<std::pair<void *, size_
 
 static void graph_free(cyp_graph *g);
 
-// Moves every device array of the graph into a fresh allocation (device copy) and frees the old one.
-int graph_rehome(cyp_graph *g) {
-    DeviceGuard guard(g->device);
-    auto move = [&](auto **p, size_t bytes) -> cudaError_t {
-        if (!*p || bytes == 0) return cudaSuccess;
-        void *fresh = nullptr;
-        cudaError_t e = dev_alloc(&fresh, bytes);
-        if (e != cudaSuccess) return e;
-        e = cudaMemcpyAsync(fresh, *p, bytes, cudaMemcpyDeviceToDevice, nullptr);
-        if (e != cudaSuccess) { dev_free(fresh); return e; }
-        dev_free(*p);
-        *p = reinterpret_cast<std::remove_reference_t<decltype(*p)>>(fresh);
-        return cudaSuccess;
-    };
-    const size_t cdf_elem = (g->cdf_mode == CYP_CDF_EXACT) ? 8 : 4;
-    const size_t padded = static_cast<size_t>(g->padded), n = static_cast<size_t>(g->n);
-    cudaError_t e = move(&g->d_row, sizeof(RowInfo) * n);
-    if (e == cudaSuccess) e = move(&g->d_cdf, cdf_elem * padded);
-    if (e == cudaSuccess) e = move(&g->d_col, sizeof(int32_t) * padded);
-    if (e == cudaSuccess) e = move(&g->d_val, sizeof(double) * padded);
-    if (e == cudaSuccess) e = move(&g->d_row_ptr, sizeof(int64_t) * (n + 1));
-    if (e == cudaSuccess && g->v2_ok) {
-        // the fused rows may sit at an offset inside their allocation (developer switch): the copy starts at the rows
-        unsigned char *fresh = nullptr;
-        e = dev_alloc(&fresh, static_cast<size_t>(g->rows2_bytes));
-        if (e == cudaSuccess) e = cudaMemcpyAsync(fresh, g->d_rows2, static_cast<size_t>(g->rows2_bytes), cudaMemcpyDeviceToDevice, nullptr);
-        if (e == cudaSuccess) { dev_free(g->d_rows2_base); g->d_rows2_base = g->d_rows2 = fresh; }
-        if (e == cudaSuccess) e = move(&g->d_edge4, sizeof(uint32_t) * 4 * static_cast<size_t>(g->v2_edge_units + 1));
-        if (e == cudaSuccess) e = move(&g->d_word, sizeof(uint32_t) * n);
-    }
-    if (e == cudaSuccess && g->d_edge) {
-        e = move(&g->d_q16, sizeof(uint16_t) * padded);
-        if (e == cudaSuccess) e = move(&g->d_edge, sizeof(EdgeRec) * padded);
-    }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
-    if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? CYP_E_NOMEM : CYP_E_CUDA, std::string("graph_rehome: ") + cudaGetErrorString(e));
-    return CYP_OK;
-}
-
 int graph_alloc_like(const GraphWire &w, int device, cyp_graph **out) {
     *out = nullptr;
     DeviceGuard guard(device);
@@ -541,16 +502,20 @@ static void graph_free(cyp_graph *g) {
 }
 }  // namespace cyp
 
-// cyp_graph_create: upload + K1 + K1b as a pipeline.  The CSR arrays travel in chunks of rows on a copy stream; the
-// host lays out the rows meanwhile; K1 and K1b of a chunk start as soon as the chunk has landed, so at atlas scale
-// (628 MB of CSR over PCIe) the kernels and the host work hide behind the upload.
+// cyp_graph_create: upload + K0 + K1 + K1b as a pipeline.  The CSR arrays travel in chunks of rows on a copy stream, the
+// row offsets first; K0 (layout.cu) lays out the rows on the device as soon as the offsets have landed; K1 and K1b of a
+// chunk start as soon as the chunk has, so at atlas scale (628 MB of CSR over PCIe) the kernels hide behind the upload.
 static int graph_create_impl(int device, int64_t n_cells, int64_t nnz, const int64_t *h_row_ptr, const int32_t *h_col,
-                             const void *h_val, bool val_f32, int cdf_mode, cyp_graph **out) {
+                             const void *h_val, bool val_f32, int cdf_mode, const RawCsr *raw, cyp_graph **out) {
+    struct RawGuard {                                            // `raw` is ours whatever happens: freed here until the build adopts it
+        const RawCsr *raw; int device; bool adopted;
+        ~RawGuard() { if (raw && !adopted) { DeviceGuard guard(device); dev_free(raw->d_col); dev_free(raw->d_val); } }
+    } raw_guard{raw, device, false};
     CYP_REQUIRE(out != nullptr, "cyp_graph_create: out is NULL");
     *out = nullptr;
     CYP_REQUIRE(n_cells > 0 && nnz > 0, "cyp_graph_create: empty matrix");
     CYP_REQUIRE(n_cells < (1ll << 31), "cyp_graph_create: cell ids must fit int32 (the reference stores int32, :38)");
-    CYP_REQUIRE(h_row_ptr && h_col && h_val, "cyp_graph_create: NULL CSR array");
+    CYP_REQUIRE(h_row_ptr && (raw ? (raw->d_col && raw->d_val) : (h_col && h_val)), "cyp_graph_create: NULL CSR array");
     CYP_REQUIRE(cdf_mode == CYP_CDF_REFERENCE || cdf_mode == CYP_CDF_EXACT, "cyp_graph_create: bad cdf_mode");
     CYP_REQUIRE(h_row_ptr[0] == 0 && h_row_ptr[n_cells] == nnz, "cyp_graph_create: row_ptr does not span nnz");
     int ndev = 0;
@@ -576,11 +541,13 @@ static int graph_create_impl(int device, int64_t n_cells, int64_t nnz, const int
     cudaStream_t s_copy = nullptr, s_aux = nullptr, s_comp = nullptr;
     cudaEvent_t ev_alloc = nullptr, ev_small = nullptr, ev_chunk[kMaxChunks] = {}, ev_t[kMaxChunks][2] = {};
     V2Build v2;
+    RowLayoutScratch layout;
     auto release_tmp = [&]() {
         if (s_copy) cudaStreamSynchronize(s_copy);
         if (s_aux) cudaStreamSynchronize(s_aux);
         if (s_comp) cudaStreamSynchronize(s_comp);
         dev_free(d_raw_col); dev_free(d_raw_val); dev_free(d_flag); dev_free(d_block_min); dev_free(d_block_max);
+        layout_release(&layout);
         d_raw_col = nullptr; d_raw_val = nullptr; d_flag = nullptr; d_block_min = d_block_max = nullptr;
         if (ev_alloc) cudaEventDestroy(ev_alloc);
         if (ev_small) cudaEventDestroy(ev_small);
@@ -607,7 +574,8 @@ static int graph_create_impl(int device, int64_t n_cells, int64_t nnz, const int
                                               std::string(#expr) + ": " + cudaGetErrorString(_e));    \
     } while (0)
 
-    // ---- 1. raw CSR on its way: chunks of rows (multiples of kK1Threads rows, so K1's CTAs never straddle a chunk)
+    // ---- 1. raw CSR on its way: the row offsets first, then chunks of rows (multiples of kK1Threads rows, so K1's CTAs
+    // never straddle a chunk)
     const int n_chunks = nnz < (4 << 20) ? 1 : kMaxChunks;
     int64_t chunk_rows = (n_cells + n_chunks - 1) / n_chunks;
     chunk_rows = (chunk_rows + kK1Threads - 1) / kK1Threads * kK1Threads;
@@ -617,43 +585,46 @@ static int graph_create_impl(int device, int64_t n_cells, int64_t nnz, const int
     G_CUDA(cudaEventCreateWithFlags(&ev_alloc, cudaEventDisableTiming));
     G_CUDA(cudaEventCreateWithFlags(&ev_small, cudaEventDisableTiming));
     G_CUDA(dev_alloc(&g->d_row_ptr, sizeof(int64_t) * (n_cells + 1)));
-    G_CUDA(dev_alloc(&d_raw_col, sizeof(int32_t) * nnz));
-    G_CUDA(dev_alloc(&d_raw_val, val_elem * nnz));
+    if (raw) {                                                   // already on the device: ours from here on
+        d_raw_col = raw->d_col;
+        d_raw_val = raw->d_val;
+        raw_guard.adopted = true;
+    } else {
+        G_CUDA(dev_alloc(&d_raw_col, sizeof(int32_t) * nnz));
+        G_CUDA(dev_alloc(&d_raw_val, val_elem * nnz));
+    }
     G_CUDA(cudaEventRecord(ev_alloc, nullptr));                  // device memory comes from the default stream's pool
     G_CUDA(cudaStreamWaitEvent(s_copy, ev_alloc, 0));
     G_CUDA(cudaMemcpyAsync(g->d_row_ptr, h_row_ptr, sizeof(int64_t) * (n_cells + 1), cudaMemcpyHostToDevice, s_copy));
+    G_CUDA(cudaEventRecord(ev_small, s_copy));
+    G_CUDA(cudaStreamWaitEvent(s_aux, ev_small, 0));             // K0 runs behind the row offsets, beside the chunks
     int used_chunks = 0;
     for (int c = 0; c < n_chunks; ++c) {
         const int64_t rb = std::min<int64_t>(static_cast<int64_t>(c) * chunk_rows, n_cells), re = std::min<int64_t>(rb + chunk_rows, n_cells);
         if (rb >= re) break;
         const int64_t a = h_row_ptr[rb], b = h_row_ptr[re];
         if (!(a >= 0 && b >= a && b <= nnz)) return cleanup(CYP_E_INVALID, "cyp_graph_create: row_ptr not monotone");
-        if (b > a) {
+        if (b > a && !raw) {
             G_CUDA(cudaMemcpyAsync(d_raw_col + a, h_col + a, sizeof(int32_t) * (b - a), cudaMemcpyHostToDevice, s_copy));
             G_CUDA(cudaMemcpyAsync(static_cast<char *>(d_raw_val) + val_elem * a, static_cast<const char *>(h_val) + val_elem * a, val_elem * (b - a),
                                    cudaMemcpyHostToDevice, s_copy));
         }
         G_CUDA(cudaEventCreateWithFlags(&ev_chunk[c], cudaEventDisableTiming));
-        G_CUDA(cudaEventRecord(ev_chunk[c], s_copy));
+        G_CUDA(cudaEventRecord(ev_chunk[c], s_copy));             // (with `raw`: the row offsets only)
         used_chunks = c + 1;
     }
-    // ---- 2. host, while the copies run: padded row offsets and the fused-row layout (O(n))
-    std::vector<RowInfo> rows(static_cast<size_t>(n_cells));
-    int64_t units = 0;
-    int32_t max_len = 0;
-    for (int64_t r = 0; r < n_cells; ++r) {
-        const int64_t len = h_row_ptr[r + 1] - h_row_ptr[r];
-        if (len < 0 || len > (1ll << 30)) return cleanup(CYP_E_INVALID, "cyp_graph_create: row_ptr not monotone");
-        rows[r].off_units = static_cast<uint32_t>(units);
-        rows[r].len = static_cast<uint32_t>(len);
-        units += (len + A - 1) / A;
-        if (len > max_len) max_len = static_cast<int32_t>(len);
-    }
+    // ---- 2. K0, while the copies run: the row layout on the device (layout.cu); the host reads the totals
+    int extra[2];
+    v2_candidates(&extra[0], &extra[1]);
+    RowLayoutSummary shape{};
+    G_CUDA(layout_measure(n_cells, A, g->d_row_ptr, extra[0], extra[1], &layout, s_aux, &shape));
+    if (shape.bad) return cleanup(CYP_E_INVALID, "cyp_graph_create: row_ptr not monotone");
+    const int64_t units = shape.units16;
     if (units >= (1ll << 32)) return cleanup(CYP_E_INVALID, "cyp_graph_create: matrix too large for 32-bit row units");
     g->padded = units * A + 4 * A;                     // slack so vector loads of a last partial chunk stay in bounds
-    g->max_len = max_len;
+    g->max_len = shape.max_len;
     g->mean_len = static_cast<double>(nnz) / static_cast<double>(n_cells);
-    const bool want_v2 = v2_plan(g, h_row_ptr, &v2);
+    const bool want_v2 = v2_plan(g, shape, extra, &v2);
 
     // ---- 3. the other device arrays (default stream)
     G_CUDA(dev_alloc(&g->d_row, sizeof(RowInfo) * n_cells));
@@ -673,10 +644,9 @@ static int graph_create_impl(int device, int64_t n_cells, int64_t nnz, const int
     if (want_v2) G_CUDA(v2_alloc(g, &v2));
     G_CUDA(cudaEventRecord(ev_alloc, nullptr));                  // device memory comes from the default stream's pool
 
-    // the small host-made tables travel on their own stream (pageable: the call blocks until they are staged)
+    // RowInfo, row words and target bases of every row: written on the device from K0's prefix sums
     G_CUDA(cudaStreamWaitEvent(s_aux, ev_alloc, 0));
-    G_CUDA(cudaMemcpyAsync(g->d_row, rows.data(), sizeof(RowInfo) * n_cells, cudaMemcpyHostToDevice, s_aux));
-    if (want_v2) G_CUDA(v2_upload(g, &v2, s_aux));
+    G_CUDA(layout_write(&layout, g->d_row_ptr, v2.which, g->d_row, want_v2 ? g->d_word : nullptr, want_v2 ? v2.d_ebase : nullptr, s_aux));
     G_CUDA(cudaEventRecord(ev_small, s_aux));
 
     // ---- 4. K1 (+ K1b) per chunk
@@ -687,6 +657,7 @@ static int graph_create_impl(int device, int64_t n_cells, int64_t nnz, const int
     const int smem_bytes = smem_elems * static_cast<int>(sizeof(double));
     G_CUDA(cudaStreamWaitEvent(s_comp, ev_alloc, 0));
     G_CUDA(cudaStreamWaitEvent(s_comp, ev_small, 0));
+    if (raw && raw->ready) G_CUDA(cudaStreamWaitEvent(s_comp, raw->ready, 0));
 #define K1_LAUNCH(CDFT, VALT)                                                                                               \
     do {                                                                                                                    \
         G_CUDA(cudaFuncSetAttribute(build_cdf_kernel<CDFT, VALT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); \
@@ -754,12 +725,17 @@ static int graph_create_impl(int device, int64_t n_cells, int64_t nnz, const int
 
 extern "C" int cyp_graph_create(int device, int64_t n_cells, int64_t nnz, const int64_t *h_row_ptr,
                                 const int32_t *h_col, const double *h_val, int cdf_mode, cyp_graph **out) {
-    return graph_create_impl(device, n_cells, nnz, h_row_ptr, h_col, h_val, false, cdf_mode, out);
+    return graph_create_impl(device, n_cells, nnz, h_row_ptr, h_col, h_val, false, cdf_mode, nullptr, out);
 }
 
 extern "C" int cyp_graph_create_f32(int device, int64_t n_cells, int64_t nnz, const int64_t *h_row_ptr,
                                     const int32_t *h_col, const float *h_val, int cdf_mode, cyp_graph **out) {
-    return graph_create_impl(device, n_cells, nnz, h_row_ptr, h_col, h_val, true, cdf_mode, out);
+    return graph_create_impl(device, n_cells, nnz, h_row_ptr, h_col, h_val, true, cdf_mode, nullptr, out);
+}
+
+int cyp::graph_create_raw(int device, int64_t n_cells, int64_t nnz, const int64_t *h_row_ptr, bool val_f32, int cdf_mode, const RawCsr &raw,
+                          cyp_graph **out) {
+    return graph_create_impl(device, n_cells, nnz, h_row_ptr, nullptr, nullptr, val_f32, cdf_mode, &raw, out);
 }
 
 extern "C" int cyp_graph_row_sum_range(const cyp_graph *g, double *min_sum, double *max_sum) {

@@ -480,6 +480,147 @@ extern "C" int cyp_group_graph_create(cyp_group *g, int64_t n_cells, int64_t nnz
     return CYP_OK;
 }
 
+// The same graph, when EVERY rank holds the host CSR (torchrun: each process has the AnnData; one process with N devices:
+// the one host copy): each rank uploads 1/world of the column and value arrays over its own PCIe link, an in-place
+// ncclAllGather over NVLink completes them on every device, and every device runs K1 / K1b itself (3 ms at 1M cells).
+// The upload, the longest part of building a graph, shrinks with the number of GPUs; the 1.6 GB of built arrays never travel.
+extern "C" int cyp_group_graph_create_sharded(cyp_group *g, int64_t n_cells, int64_t nnz, const int64_t *h_row_ptr, const int32_t *h_col,
+                                              const void *h_val, int val_is_f32, int cdf_mode, float *ms_upload, float *ms_gather,
+                                              float *ms_total) {
+    CYP_REQUIRE(g != nullptr, "cyp_group_graph_create_sharded: NULL group");
+    CYP_REQUIRE(n_cells > 0 && nnz > 0 && h_row_ptr && h_col && h_val, "cyp_group_graph_create_sharded: every rank passes the CSR");
+    if (ms_upload) *ms_upload = 0.f;
+    if (ms_gather) *ms_gather = 0.f;
+    if (ms_total) *ms_total = 0.f;
+    const double t0 = now_ms();
+    if (g->world == 1) {
+        const int rc = cyp_group_graph_create(g, n_cells, nnz, h_row_ptr, h_col, h_val, val_is_f32, cdf_mode, 0, ms_total, nullptr);
+        if (ms_upload && ms_total) *ms_upload = *ms_total;
+        return rc;
+    }
+    for (int i = 0; i < g->n_local; ++i) {
+        if (g->sessions[i]) { cyp_session_destroy(g->sessions[i]); g->sessions[i] = nullptr; }
+        if (g->graphs[i]) { cyp_graph_destroy(g->graphs[i]); g->graphs[i] = nullptr; }
+    }
+    const int W = g->world;
+    const size_t val_elem = val_is_f32 ? sizeof(float) : sizeof(double);
+    // ---- 1. do all ranks hold the same matrix?  (a mismatch would otherwise hang the all-gather or build different graphs)
+    {
+        constexpr int kWords = 4;
+        uint64_t h = 0x243F6A8885A308D3ull;
+        auto fold = [&](uint64_t x) { h = (h ^ x) * 0x9E3779B97F4A7C15ull; h ^= h >> 29; };
+        for (int k = 0; k < 64; ++k) {
+            const int64_t r = (n_cells * k) / 64, e = (nnz * k) / 64;
+            fold(static_cast<uint64_t>(h_row_ptr[r]));
+            fold(static_cast<uint64_t>(static_cast<uint32_t>(h_col[e])));
+            uint64_t bits = 0;
+            memcpy(&bits, static_cast<const char *>(h_val) + val_elem * e, val_elem);
+            fold(bits);
+        }
+        fold(static_cast<uint64_t>(h_row_ptr[n_cells]));
+        const int64_t mine[kWords] = {n_cells, nnz, static_cast<int64_t>((val_is_f32 ? 256 : 0) | cdf_mode), static_cast<int64_t>(h)};
+        std::vector<void *> d_chk(g->n_local, nullptr);
+        struct FreeBufs { cyp_group *g; std::vector<void *> &a; ~FreeBufs() { for (int i = 0; i < g->n_local; ++i) { DeviceGuard guard(g->devices[i]); dev_free(a[i]); } } } free_bufs{g, d_chk};
+        for (int i = 0; i < g->n_local; ++i) {
+            DeviceGuard guard(g->devices[i]);
+            G_CUDA(dev_alloc(&d_chk[i], sizeof(int64_t) * kWords * W));
+            G_CUDA(cudaMemcpy(static_cast<int64_t *>(d_chk[i]) + static_cast<size_t>(g->first_rank + i) * kWords, mine, sizeof(mine), cudaMemcpyHostToDevice));
+        }
+        int rc = all_gather_inplace(g, d_chk, kWords, ncclInt64, sizeof(int64_t));
+        if (rc == CYP_OK) rc = sync_streams(g);
+        if (rc != CYP_OK) return rc;
+        std::vector<int64_t> all(static_cast<size_t>(kWords) * W);
+        {
+            DeviceGuard guard(g->devices[0]);
+            G_CUDA(cudaMemcpy(all.data(), d_chk[0], sizeof(int64_t) * kWords * W, cudaMemcpyDeviceToHost));
+        }
+        for (int r = 0; r < W; ++r)
+            if (memcmp(all.data() + static_cast<size_t>(r) * kWords, all.data(), sizeof(mine)) != 0)
+                return fail(CYP_E_INVALID, "cyp_group_graph_create_sharded: rank " + std::to_string(r) +
+                                               " passed a different matrix (or cdf_mode) than rank 0: every rank must pass the same CSR");
+    }
+    // ---- 2. every rank uploads its slice; in-place all-gather over NVLink
+    const int64_t per = (((nnz + W - 1) / W) + 3) & ~int64_t(3);     // elements per rank; slices stay 16-byte aligned
+    std::vector<RawCsr> raw(g->n_local);
+    std::vector<cudaEvent_t> ev(g->n_local * 3, nullptr);            // per device: start, uploaded, gathered
+    auto drop_events = [&]() {
+        for (int i = 0; i < g->n_local; ++i) {
+            DeviceGuard guard(g->devices[i]);
+            for (int k = 0; k < 3; ++k) if (ev[3 * i + k]) cudaEventDestroy(ev[3 * i + k]);
+            if (raw[i].ready) cudaEventDestroy(raw[i].ready);
+        }
+    };
+    auto drop_raw = [&]() {
+        for (int i = 0; i < g->n_local; ++i) {
+            DeviceGuard guard(g->devices[i]);
+            cudaStreamSynchronize(g->streams[i]);
+            dev_free(raw[i].d_col); dev_free(raw[i].d_val);
+            raw[i].d_col = nullptr; raw[i].d_val = nullptr;
+        }
+    };
+    int rc = for_each_local(g, [&](int i) -> int {
+        DeviceGuard guard(g->devices[i]);
+        const int r = g->first_rank + i;
+        cudaStream_t st = g->streams[i];
+        for (int k = 0; k < 3; ++k) G_CUDA(cudaEventCreate(&ev[3 * i + k]));
+        G_CUDA(cudaEventCreateWithFlags(&raw[i].ready, cudaEventDisableTiming));
+        G_CUDA(dev_alloc(&raw[i].d_col, sizeof(int32_t) * per * W));
+        G_CUDA(dev_alloc(&raw[i].d_val, val_elem * per * W));
+        G_CUDA(cudaEventRecord(raw[i].ready, nullptr));              // device memory comes from the default stream's pool
+        G_CUDA(cudaStreamWaitEvent(st, raw[i].ready, 0));
+        G_CUDA(cudaEventRecord(ev[3 * i], st));
+        const int64_t a = std::min<int64_t>(per * r, nnz), b = std::min<int64_t>(a + per, nnz);
+        if (b > a) {
+            G_CUDA(cudaMemcpyAsync(raw[i].d_col + a, h_col + a, sizeof(int32_t) * (b - a), cudaMemcpyHostToDevice, st));
+            G_CUDA(cudaMemcpyAsync(static_cast<char *>(raw[i].d_val) + val_elem * a, static_cast<const char *>(h_val) + val_elem * a,
+                                   val_elem * (b - a), cudaMemcpyHostToDevice, st));
+        }
+        G_CUDA(cudaEventRecord(ev[3 * i + 1], st));
+        return CYP_OK;
+    });
+    if (rc == CYP_OK) {
+        std::vector<void *> cols(g->n_local), vals(g->n_local);
+        for (int i = 0; i < g->n_local; ++i) { cols[i] = raw[i].d_col; vals[i] = raw[i].d_val; }
+        rc = all_gather_inplace(g, cols, static_cast<size_t>(per), ncclInt32, sizeof(int32_t));
+        if (rc == CYP_OK) rc = all_gather_inplace(g, vals, static_cast<size_t>(per) * (val_elem / 4), ncclInt32, sizeof(int32_t));
+    }
+    if (rc == CYP_OK)
+        for (int i = 0; i < g->n_local && rc == CYP_OK; ++i) {
+            DeviceGuard guard(g->devices[i]);
+            cudaError_t e = cudaEventRecord(ev[3 * i + 2], g->streams[i]);
+            if (e == cudaSuccess) e = cudaEventRecord(raw[i].ready, g->streams[i]);
+            if (e != cudaSuccess) rc = fail(CYP_E_CUDA, std::string("cyp_group_graph_create_sharded: ") + cudaGetErrorString(e));
+        }
+    if (rc != CYP_OK) {
+        const std::string keep = cyp_last_error();
+        drop_raw();
+        drop_events();
+        return fail(rc, keep);
+    }
+    // ---- 3. every device builds its graph (the host lays out the rows while the slices travel)
+    rc = for_each_local(g, [&](int i) -> int {
+        RawCsr mine = raw[i];
+        raw[i].d_col = nullptr; raw[i].d_val = nullptr;              // the build owns them now, also when it fails
+        return graph_create_raw(g->devices[i], n_cells, nnz, h_row_ptr, val_is_f32 != 0, cdf_mode, mine, &g->graphs[i]);
+    });
+    if (rc == CYP_OK) {
+        DeviceGuard guard(g->devices[0]);
+        float a = 0.f, b = 0.f;
+        if (cudaEventElapsedTime(&a, ev[0], ev[1]) == cudaSuccess && ms_upload) *ms_upload = a;
+        if (cudaEventElapsedTime(&b, ev[1], ev[2]) == cudaSuccess && ms_gather) *ms_gather = b;
+    }
+    const std::string keep = rc == CYP_OK ? std::string() : std::string(cyp_last_error());
+    drop_raw();
+    drop_events();
+    if (rc != CYP_OK) {
+        for (int i = 0; i < g->n_local; ++i)
+            if (g->graphs[i]) { cyp_graph_destroy(g->graphs[i]); g->graphs[i] = nullptr; }
+        return fail(rc, keep);
+    }
+    if (ms_total) *ms_total = static_cast<float>(now_ms() - t0);
+    return CYP_OK;
+}
+
 extern "C" int cyp_group_session_create(cyp_group *g, const int32_t *h_root_cells, int64_t n_roots, const int32_t *h_cell_code,
                                         int32_t n_codes, int32_t min_clusters, const int32_t *h_end_slot_of_cell, int32_t n_end_slots,
                                         int32_t max_steps, int unique, uint64_t seed) {

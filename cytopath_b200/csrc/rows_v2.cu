@@ -12,7 +12,6 @@
 // The kernel is one warp per row: codes from the CDF K1 wrote (bit-equal to matrix_prep, :11-31), targets
 // translated to row words, the m most probable entries selected by m warp-argmax rounds.
 #include <cstdlib>
-#include <vector>
 
 #include "common.cuh"
 
@@ -107,40 +106,30 @@ build_rows_v2_kernel(int64_t row_begin, int64_t row_end, int64_t n_cells, const 
 
 // ---- host side: cyp_graph_create drives these (graph.cu), chunk by chunk behind the CSR upload ----
 
-// Host-only layout of the fused rows.  Returns false when the layout does not apply to this matrix.
-bool v2_plan(const cyp_graph *g, const int64_t *h_row_ptr, V2Build *b) {
+// The fused-row plan from the device-side row layout (layout.cu).  Returns false when the layout does not apply.
+void v2_candidates(int *extra0, int *extra1) {
+    // Extra sectors of inlined targets per row.  More inlining means fewer second gathers but more bytes per step:
+    // on B200 it pays while the fused rows stay L2 resident (C3, 100k cells: 87 vs 79 G walker-steps/s) and costs
+    // at atlas scale, where DRAM bytes per step are what counts (C4: 51 vs 57 G).  CYP_V2_EXTRA overrides.
+    *extra0 = 0;
+    *extra1 = 1;
+    if (const char *e = getenv("CYP_V2_EXTRA")) {
+        const int x = atoi(e);
+        if (x >= 0) *extra0 = *extra1 = x;
+    }
+}
+
+bool v2_plan(const cyp_graph *g, const RowLayoutSummary &rows, const int extra[2], V2Build *b) {
     b->planned = false;
     if (g->max_len > 65535) return false;
     if (const char *off = getenv("CYP_NO_V2")) if (off[0] == '1') return false;
     const int64_t n = g->n;
-    // Extra sectors of inlined targets per row.  More inlining means fewer second gathers but more bytes per step:
-    // on B200 it pays while the fused rows stay L2 resident (C3, 100k cells: 87 vs 79 G walker-steps/s) and costs
-    // at atlas scale, where DRAM bytes per step are what counts (C4: 51 vs 57 G).  CYP_V2_EXTRA overrides.
-    int extra = -1;
-    if (const char *e = getenv("CYP_V2_EXTRA")) extra = atoi(e);
-    if (extra < 0) {
-        int64_t sectors0 = 0;
-        for (int64_t r = 0; r < n; ++r) sectors0 += (v2_used_bytes(static_cast<int>(h_row_ptr[r + 1] - h_row_ptr[r])) + 31) / 32;
-        extra = ((sectors0 + n) * 32 <= (32ll << 20)) ? 1 : 0;
-    }
-    b->word.resize(static_cast<size_t>(n));
-    b->ebase.resize(static_cast<size_t>(n));
-    int64_t sectors = 0, units = 0;
-    int max_sectors = 0;
-    int64_t hist[kV2MaxSectors + 1] = {0};
-    for (int64_t r = 0; r < n; ++r) {
-        const int len = static_cast<int>(h_row_ptr[r + 1] - h_row_ptr[r]);
-        const int nsect = v2_block_sectors(len, extra);
-        if (sectors > static_cast<int64_t>(kWordOffMask) - nsect - kV2MaxSectors || units >= (1ll << 32) - 1) return false;
-        // the word's sector field saturates: a longer block is never copied whole (slots hold <= 8 sectors), the step
-        // kernel searches it in HBM and takes its length from the header
-        b->word[r] = (static_cast<uint32_t>(nsect < kV2MaxSectors ? nsect : kV2MaxSectors) << kWordOffBits) | static_cast<uint32_t>(sectors);
-        b->ebase[r] = static_cast<uint32_t>(units);
-        sectors += nsect;
-        units += (len + 3) / 4;
-        if (nsect > max_sectors) max_sectors = nsect;
-        ++hist[nsect < kV2MaxSectors ? nsect : kV2MaxSectors];
-    }
+    // one extra sector per row while the fused rows then still fit 32 MB (L2 resident), else none
+    const int which = (extra[0] == extra[1]) ? 0 : (((rows.sectors[0] + n) * 32 <= (32ll << 20)) ? 1 : 0);
+    const int64_t sectors = rows.sectors[which], units = rows.units4;
+    if (sectors > static_cast<int64_t>(kWordOffMask) - kV2MaxSectors || units >= (1ll << 32) - 1) return false;
+    const int max_sectors = rows.max_sectors[which];
+    const int64_t *hist = rows.hist[which];
     // slot of the step kernel: the smallest power of two (1..8 sectors) that holds 97 % of the rows; the few longer
     // rows of a ragged graph are then searched in global memory instead of making every slot as large as the longest
     int slot = max_sectors;
@@ -155,7 +144,8 @@ bool v2_plan(const cyp_graph *g, const int64_t *h_row_ptr, V2Build *b) {
         for (int k = 0; k < slot && k <= kV2MaxSectors; ++k) shorter += hist[k];
         b->uniform = shorter * 10 <= n ? 1 : 0;
     }
-    b->extra = extra;
+    b->which = which;
+    b->extra = extra[which];
     b->sectors = sectors;
     b->units = units;
     b->max_sectors = max_sectors;
@@ -190,12 +180,6 @@ cudaError_t v2_alloc(cyp_graph *g, V2Build *b) {
     if (e == cudaSuccess) e = cudaMemsetAsync(b->d_bad, 0, sizeof(int), nullptr);
     if (e == cudaSuccess) e = cudaMemsetAsync(g->d_rows2, 0, b->rows_bytes, nullptr);
     if (e == cudaSuccess) e = cudaMemsetAsync(g->d_edge4, 0, sizeof(uint32_t) * 4 * static_cast<size_t>(b->units + 1), nullptr);   // row padding
-    return e;
-}
-
-cudaError_t v2_upload(cyp_graph *g, V2Build *b, cudaStream_t stream) {
-    cudaError_t e = cudaMemcpyAsync(g->d_word, b->word.data(), sizeof(uint32_t) * g->n, cudaMemcpyHostToDevice, stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(b->d_ebase, b->ebase.data(), sizeof(uint32_t) * g->n, cudaMemcpyHostToDevice, stream);
     return e;
 }
 

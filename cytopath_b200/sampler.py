@@ -160,11 +160,11 @@ def sampling(data, auto_adjust=True, matrix_key="T_forward", cluster_key="louvai
                                        C.indices, C.indptr), shape=C.shape)
             C.eliminate_zeros()
             pristine = False
-        # a1 (K1): upload + CDF build on the group's first rank, broadcast of the device arrays to the others.  The
-        # row sums of the normalisation check (:181-187) come back from the same kernel, so the host never walks
-        # the 50M-entry value array.
+        # a1 (K1): every rank of the group holds the matrix, so each uploads 1/world of it, an all-gather over NVLink
+        # completes it and every device builds the CDF itself.  The row sums of the normalisation check (:181-187)
+        # come back from the same kernel, so the host never walks the 50M-entry value array.
         t_csr = time.perf_counter()
-        timing = {"graph": group.create_graph(C, _CDF_MODES[cdf_mode])}
+        timing = {"graph": group.create_graph(C, _CDF_MODES[cdf_mode], sharded=True)}
         timing["host_ms"] = {"open_group": 1e3 * (t_group - t_start), "canonical_csr": 1e3 * (t_csr - t_group),
                              "create_graph": 1e3 * (time.perf_counter() - t_csr)}
         if not normalize:

@@ -217,6 +217,15 @@ cyp_session *cyp_group_session(const cyp_group *g, int local_index);
  * of one host upload per GPU.  ms_build / ms_broadcast (may be NULL): host wall time of the two phases. */
 int cyp_group_graph_create(cyp_group *g, int64_t n_cells, int64_t nnz, const int64_t *h_row_ptr, const int32_t *h_col,
                            const void *h_val, int val_is_f32, int cdf_mode, int root_rank, float *ms_build, float *ms_broadcast);
+/* a1 for a group when EVERY rank holds the host CSR (each torchrun process has the AnnData; a single process with N
+ * devices has the one host copy): every rank uploads 1/world of the column and value arrays over its own PCIe link, an
+ * in-place ncclAllGather over NVLink completes them on every device, and each device runs K1 / K1b itself -- the host
+ * upload, the longest part of a graph build, shrinks with the number of GPUs.  The ranks first compare (n_cells, nnz,
+ * dtype, cdf_mode, a sampled checksum of the three arrays): CYP_E_INVALID on every rank if they differ.
+ * ms_upload / ms_gather: device time of the first local device's own upload / of the all-gather; ms_total: host wall. */
+int cyp_group_graph_create_sharded(cyp_group *g, int64_t n_cells, int64_t nnz, const int64_t *h_row_ptr, const int32_t *h_col,
+                                   const void *h_val, int val_is_f32, int cdf_mode, float *ms_upload, float *ms_gather,
+                                   float *ms_total);
 /* cyp_session_create on every local device (same arguments on all ranks). */
 int cyp_group_session_create(cyp_group *g, const int32_t *h_root_cells, int64_t n_roots, const int32_t *h_cell_code,
                              int32_t n_codes, int32_t min_clusters, const int32_t *h_end_slot_of_cell, int32_t n_end_slots,

@@ -130,7 +130,7 @@ class Group:
         self.td.all_gather_object(out, obj)
         return out
 
-    def create_graph(self, C, cdf_mode, root_rank=0, shape=None):
+    def create_graph(self, C, cdf_mode, root_rank=0, shape=None, sharded=False):
         self.graph = Graph(C, cdf_mode)
         return {}
 

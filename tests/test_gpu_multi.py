@@ -99,6 +99,85 @@ def test_group_index_is_independent_of_the_device_count_even_with_colliding_hash
     np.testing.assert_array_equal(w1[r1 == 1], cand)
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("cdf_mode", [_lib.CDF_REFERENCE, _lib.CDF_EXACT])
+def test_sharded_upload_builds_the_graph_the_root_rank_builds(dtype, cdf_mode):
+    """cyp_group_graph_create_sharded (each device uploads half of the CSR, all-gather, K1 on both) == cyp_group_graph_create
+    (device 0 uploads everything, broadcast of the built arrays) == the single-device graph: CDF, fused rows, row sums.
+    nnz is odd, so the slices are ragged and the last one is padded."""
+    need_two()
+    C = sp.canonical_csr(synth.branching_graph(n=3001, k=7, n_branches=3, seed=11, workers=1, scale=2.0, noise=0.05).T)
+    C = C.astype(dtype)
+    if C.nnz % 2 == 0:                                  # drop one entry: an odd nnz
+        C = C.tolil(); r = int(np.argmax(np.diff(C.tocsr().indptr))); C[r, C.rows[r][0]] = 0; C = sp.canonical_csr(C.tocsr()).astype(dtype)
+    assert C.nnz % 2 == 1
+    solo = _lib.Graph(C, cdf_mode, 0)
+    want = (solo.cdf(), solo.fused(), solo.row_sum_range(), solo.layout())
+    solo.close()
+    for sharded in (True, False):
+        grp = _lib.Group(devices=[0, 1])
+        st = grp.create_graph(C, cdf_mode, sharded=sharded)
+        assert bool(st.get("sharded")) == sharded
+        for i in (0, 1):
+            gv = grp.graph_view(i)
+            assert gv.info()["device"] == i
+            np.testing.assert_array_equal(gv.cdf(), want[0])
+            for a, b in zip(gv.fused(), want[1]):
+                np.testing.assert_array_equal(a, b)
+            assert gv.row_sum_range() == want[2] and gv.layout() == want[3]
+        grp.close()
+
+
+def test_sharded_upload_rejects_an_invalid_matrix_on_every_device():
+    need_two()
+    C = sp.canonical_csr(synth.branching_graph(n=500, k=5, n_branches=2, seed=2, workers=1, scale=2.0, noise=0.05).T)
+    bad = C.copy()
+    bad.indices = bad.indices.copy()
+    bad.indices[bad.nnz - 3] = C.shape[0] + 5           # a column out of range, in the second device's slice
+    grp = _lib.Group(devices=[0, 1])
+    with pytest.raises(_lib.CytopathB200Error, match="column index out of range"):
+        grp.create_graph(bad, _lib.CDF_REFERENCE, sharded=True)
+    grp.create_graph(C, _lib.CDF_REFERENCE, sharded=True)    # the group is still usable
+    grp.close()
+
+
+MISMATCH_WORKER = r"""
+import os, sys
+import numpy as np
+sys.path.insert(0, {root!r})
+import torch, torch.distributed as dist
+torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+from cytopath_b200 import _lib, synth
+from oracle import sampler_port as sp
+C = sp.canonical_csr(synth.branching_graph(n=400, k=5, n_branches=2, seed=2, workers=1, scale=2.0, noise=0.05).T)
+if dist.get_rank() == 1:
+    C = C.copy(); C.data = C.data.copy(); C.data[0] *= 0.5          # one value differs on rank 1
+grp = _lib.open_group(device=int(os.environ["LOCAL_RANK"]), dist=True)
+try:
+    grp.create_graph(C, _lib.CDF_REFERENCE, sharded=True)
+    msg = "no error"
+except _lib.CytopathB200Error as exc:
+    msg = str(exc)
+open({out!r} + ".%d.txt" % dist.get_rank(), "w").write(msg)
+dist.barrier()
+dist.destroy_process_group()
+"""
+
+
+def test_sharded_upload_refuses_ranks_with_different_matrices(tmp_path):
+    need_two()
+    script = tmp_path / "worker.py"
+    out = str(tmp_path / "out")
+    script.write_text(MISMATCH_WORKER.format(root=ROOT, out=out))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29543", str(script)],
+                       capture_output=True, text=True, env=dict(os.environ, TQDM_DISABLE="1"), timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    for rank in (0, 1):
+        assert "passed a different matrix" in open(out + ".%d.txt" % rank).read()
+
+
 WORKER = r"""
 import contextlib, io, os, sys, warnings
 import numpy as np
