@@ -174,7 +174,7 @@ struct cyp_graph {
     mutable uint64_t labels2_owner = 0;  // id of the session whose label codes are in the fused rows' headers
     float placement_ms_before = 0.f, placement_ms_after = 0.f;     // probe times of calibrate_placement (0: not calibrated)
     int placement_moves = 0;
-    mutable int placement_state = 0;     // 0: the first large walk calibrates the placement of the fused rows (placement.cu); 1: done
+    mutable int placement_state = 0;     // large walks seen so far (saturating at 2): the second one calibrates the placement of the fused rows (placement.cu)
 };
 
 namespace cyp {

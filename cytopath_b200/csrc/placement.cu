@@ -3,8 +3,8 @@
 // Where the fused rows (and the target words) land in physical memory decides which L2 slices / HBM channels serve the hot
 // rows of the graph, and the busiest slice bounds the step kernel: the same binary on the same graph runs K2 in one of two
 // modes, ~9.45 ms or ~11.3 ms per launch at C4 (profiles/r02_scale_probe.md: 8 ranks of one box, identical arrays; a fresh
-// allocation of the same bytes flips the mode at random, ~70 % good).  So the FIRST large walk on a graph above half the L2
-// is preceded by a calibration: a short plain-mode walk of the caller's own walkers (one wave of CTAs, the first 64 steps)
+// allocation of the same bytes flips the mode at random, ~70 % good).  So the SECOND large walk on a graph above half the L2
+// (a graph that is walked once does not pay for it) is preceded by a calibration: a short plain-mode walk of the caller's own walkers (one wave of CTAs, the first 64 steps)
 // is timed on the current placement and on three fresh allocations of the rows + target words, and the fastest is kept.
 // ~0.2 ms per probe, ~0.1 ms per copy of 336 MB, once per graph.
 #include <algorithm>

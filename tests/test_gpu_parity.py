@@ -661,6 +661,14 @@ def test_full_size_c4_properties():
         starts = roots[np.arange(a, b) // sims]
         want = cwalk.walk(C, cdf, starts, nt, seed=1234, walker_begin=a)
         np.testing.assert_array_equal(outs[0][a:b].cpu().numpy(), want)
+    # the second large walk with the default kernel calibrates the placement of the fused rows (csrc/placement.cu: probes
+    # on fresh allocations, possibly moving the arrays): same trajectories before and after
+    assert g.placement()["probe_ms_before"] == 0.0
+    again = torch.empty((W, nt + 1), dtype=torch.int32, device="cuda")
+    _lib.check(L.cyp_walk_device(g.handle, d_roots.data_ptr(), len(roots), sims, 0, W, nt, 1234, 0, None, again.data_ptr(), None, 0, sptr))
+    torch.cuda.synchronize()
+    assert g.placement()["probe_ms_before"] > 0.0
+    assert torch.equal(again, outs[0])
     g.close()
 
 
