@@ -22,7 +22,7 @@ E_NOCROSSING = -4
 
 EXPORTS = [
     "cyp_version", "cyp_last_error", "cyp_device_count", "cyp_release_cached_memory",
-    "cyp_graph_create", "cyp_graph_create_f32", "cyp_graph_row_sum_range", "cyp_graph_destroy", "cyp_graph_info", "cyp_graph_layout", "cyp_graph_fetch_fused", "cyp_graph_fetch_cdf", "cyp_graph_build_ms", "cyp_graph_placement",
+    "cyp_graph_create", "cyp_graph_create_f32", "cyp_graph_row_sum_range", "cyp_graph_canonical", "cyp_graph_destroy", "cyp_graph_info", "cyp_graph_layout", "cyp_graph_fetch_fused", "cyp_graph_fetch_cdf", "cyp_graph_build_ms", "cyp_graph_placement",
     "cyp_power_iteration", "cyp_walk", "cyp_walk_device", "cyp_walk_variant_name", "cyp_transition_scores",
     "cyp_session_create", "cyp_session_destroy", "cyp_session_round", "cyp_session_rows",
     "cyp_session_fetch_index", "cyp_session_fetch_rows", "cyp_session_slot_counts", "cyp_session_round_records",
@@ -104,6 +104,7 @@ def load():
     L.cyp_graph_create.argtypes = [ci, i64, i64, vp, vp, vp, ci, P(vp)]
     L.cyp_graph_create_f32.argtypes = [ci, i64, i64, vp, vp, vp, ci, P(vp)]
     L.cyp_graph_row_sum_range.argtypes = [vp, P(ctypes.c_double), P(ctypes.c_double)]
+    L.cyp_graph_canonical.argtypes = [vp, P(ci), P(ci)]
     L.cyp_graph_destroy.argtypes = [vp]
     L.cyp_graph_info.argtypes = [vp, P(i64), P(i64), P(i32), P(ci), P(ci), P(i64)]
     L.cyp_graph_layout.argtypes = [vp, P(ci), P(i64), P(i64), P(i32)]
@@ -316,6 +317,12 @@ class Graph:
         lo, hi = ctypes.c_double(), ctypes.c_double()
         check(load().cyp_graph_row_sum_range(self._h, ctypes.byref(lo), ctypes.byref(hi)))
         return lo.value, hi.value
+
+    def canonical(self) -> bool:
+        """Did K1 find the CSR canonical (every row's columns strictly increasing, no explicit zero)?"""
+        a, b = ctypes.c_int(), ctypes.c_int()
+        check(load().cyp_graph_canonical(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return bool(a.value and b.value)
 
     def placement(self) -> dict:
         """Probe times of the placement calibration (0: the graph is small, not calibrated) and the number of moves."""

@@ -146,6 +146,7 @@ struct cyp_graph {
     int align_elems = cyp::kRowAlign;
     int q16_ok = 0;            // the 16-bit CDF codes are usable (all CDF values in range, CDF non-decreasing)
     int monotone = 1;          // every probability >= 0, so each row's CDF is non-decreasing (binary search is exact)
+    int noncanonical = 0;      // what K1 saw in the CSR it was given: bit 0 a row's columns are not strictly increasing, bit 1 an explicit zero
     cyp::RowInfo *d_row = nullptr;   // [n]
     void *d_cdf = nullptr;           // float or double [padded]
     uint16_t *d_q16 = nullptr;       // [padded] 16-bit CDF codes (see walk_tma.cu)
@@ -222,7 +223,7 @@ void v2_release(cyp_graph *g, V2Build *b);
 // graph.cu, for the multi-device layer (group.cu): a graph built on one device is replicated by broadcasting its
 // device arrays over NVLink instead of uploading the CSR from the host once per GPU.
 struct GraphWire {                 // the host-side fields of a cyp_graph, as they travel to the other ranks
-    int32_t cdf_mode, max_len, q16_ok, monotone, v2_ok, v2_max_sectors, v2_slot_sectors, v2_uniform, has_edge_records, pad_;
+    int32_t cdf_mode, max_len, q16_ok, monotone, v2_ok, v2_max_sectors, v2_slot_sectors, v2_uniform, has_edge_records, noncanonical;
     int64_t n, nnz, padded, v2_sectors, v2_edge_units, rows2_bytes;
     double mean_len, row_sum_min, row_sum_max;
     float build_ms, pad2_;

@@ -221,13 +221,15 @@ build_cdf_kernel(int64_t row_begin, int64_t n, const int64_t *__restrict__ row_p
     const int64_t dst0 = s_dst[0], dcnt = s_dst[nrows] - dst0;
     double row_sum = 0.0;                              // this thread's row: last CDF value before narrowing
     if (cnt <= smem_elems) {
-        bool neg = false;
+        bool neg = false, zero = false;
         for (int64_t i = threadIdx.x; i < cnt; i += kK1Threads) {
             const double v = static_cast<double>(raw_val[src0 + i]);      // float32 input widens exactly
             neg |= v < 0.0;
+            zero |= v == 0.0;
             s_val[i] = v;
         }
         if (neg) atomicOr(negative_flag, 1);
+        if (zero) atomicOr(negative_flag, 16);                            // an explicit zero: the CSR is not canonical
         __syncthreads();
         if (threadIdx.x < nrows) {
             const int64_t a = s_src[threadIdx.x] - src0, b = s_src[threadIdx.x + 1] - src0;
@@ -251,6 +253,7 @@ build_cdf_kernel(int64_t row_begin, int64_t n, const int64_t *__restrict__ row_p
                 const int64_t q = s_src[lo] + j;
                 const int32_t c = raw_col[q];
                 if (c < 0 || c >= n) atomicOr(negative_flag, 4);          // not a cell: the create call fails
+                if (j > 0 && raw_col[q - 1] >= c) atomicOr(negative_flag, 8);      // columns not strictly increasing: not canonical
                 cdf[dst0 + p] = finish_cdf<CdfT>(s_val[q - src0]);
                 const uint16_t code = cdf_code<CdfT>(s_val[q - src0], negative_flag);     // also checks the code range
                 col[dst0 + p] = c;
@@ -278,9 +281,11 @@ build_cdf_kernel(int64_t row_begin, int64_t n, const int64_t *__restrict__ row_p
         for (int64_t j = 0; j < len; ++j) {
             const double v = static_cast<double>(raw_val[a + j]);
             if (v < 0.0) atomicOr(negative_flag, 1);
+            if (v == 0.0) atomicOr(negative_flag, 16);
             acc = __dadd_rn(acc, v);
             const int32_t c = raw_col[a + j];
             if (c < 0 || c >= n) atomicOr(negative_flag, 4);
+            if (j > 0 && raw_col[a + j - 1] >= c) atomicOr(negative_flag, 8);
             cdf[dst + j] = finish_cdf<CdfT>(acc);
             const uint16_t code = cdf_code<CdfT>(acc, negative_flag);
             col[dst + j] = c;
@@ -388,6 +393,7 @@ GraphWire graph_wire(const cyp_graph *g) {
     w.cdf_mode = g->cdf_mode; w.max_len = g->max_len; w.q16_ok = g->q16_ok; w.monotone = g->monotone;
     w.v2_ok = g->v2_ok; w.v2_max_sectors = g->v2_max_sectors; w.v2_slot_sectors = g->v2_slot_sectors; w.v2_uniform = g->v2_uniform;
     w.has_edge_records = g->d_edge != nullptr ? 1 : 0;
+    w.noncanonical = g->noncanonical;
     w.n = g->n; w.nnz = g->nnz; w.padded = g->padded; w.v2_sectors = g->v2_sectors; w.v2_edge_units = g->v2_edge_units;
     w.rows2_bytes = g->rows2_bytes;
     w.mean_len = g->mean_len; w.row_sum_min = g->row_sum_min; w.row_sum_max = g->row_sum_max;
@@ -423,7 +429,7 @@ int graph_alloc_like(const GraphWire &w, int device, cyp_graph **out) {
     cyp_graph *g = new cyp_graph();
     g->device = device;
     g->cdf_mode = w.cdf_mode; g->n = w.n; g->nnz = w.nnz; g->padded = w.padded; g->max_len = w.max_len; g->mean_len = w.mean_len;
-    g->q16_ok = w.q16_ok; g->monotone = w.monotone; g->build_ms = w.build_ms;
+    g->q16_ok = w.q16_ok; g->monotone = w.monotone; g->build_ms = w.build_ms; g->noncanonical = w.noncanonical;
     g->row_sum_min = w.row_sum_min; g->row_sum_max = w.row_sum_max;
     g->v2_ok = w.v2_ok; g->v2_max_sectors = w.v2_max_sectors; g->v2_slot_sectors = w.v2_slot_sectors; g->v2_uniform = w.v2_uniform;
     g->v2_sectors = w.v2_sectors; g->v2_edge_units = w.v2_edge_units; g->rows2_bytes = w.rows2_bytes;
@@ -695,7 +701,8 @@ static int graph_create_impl(int device, int64_t n_cells, int64_t nnz, const int
     G_CUDA(cudaMemcpy(&negative, d_flag, sizeof(int), cudaMemcpyDeviceToHost));
     if (negative & 4) return cleanup(CYP_E_INVALID, "cyp_graph_create: column index out of range [0, n_cells)");
     g->monotone = (negative & 1) ? 0 : 1;
-    g->q16_ok = (negative == 0) ? 1 : 0;
+    g->q16_ok = (negative & 3) == 0 ? 1 : 0;
+    g->noncanonical = (negative >> 3) & 3;
     {
         std::vector<double> bmin(total_blocks), bmax(total_blocks);
         G_CUDA(cudaMemcpy(bmin.data(), d_block_min, sizeof(double) * total_blocks, cudaMemcpyDeviceToHost));
@@ -759,6 +766,13 @@ extern "C" int cyp_graph_info(const cyp_graph *g, int64_t *n_cells, int64_t *nnz
     if (cdf_mode) *cdf_mode = g->cdf_mode;
     if (device) *device = g->device;
     if (device_bytes) *device_bytes = g->device_bytes;
+    return CYP_OK;
+}
+
+extern "C" int cyp_graph_canonical(const cyp_graph *g, int *columns_strictly_increasing, int *no_explicit_zeros) {
+    CYP_REQUIRE(g != nullptr, "cyp_graph_canonical: NULL graph");
+    if (columns_strictly_increasing) *columns_strictly_increasing = (g->noncanonical & 1) ? 0 : 1;
+    if (no_explicit_zeros) *no_explicit_zeros = (g->noncanonical & 2) ? 0 : 1;
     return CYP_OK;
 }
 

@@ -151,7 +151,10 @@ def sampling(data, auto_adjust=True, matrix_key="T_forward", cluster_key="louvai
     group = _group if _group is not None else backend.open_group(device=device, devices=devices, dist=dist)
     try:
         t_group = time.perf_counter()
-        C = _canonical_csr(M)
+        # A float CSR is taken as it is: K1 reads every entry anyway and reports whether the matrix was canonical
+        # (cyp_graph_canonical), so the host does not walk 50M entries to find out what is almost always true.
+        trusted = (not normalize and sparse.issparse(M) and M.format == "csr" and M.dtype in (np.float32, np.float64))
+        C = M if trusted else _canonical_csr(M)
         pristine = C is M                 # the stored matrix IS what is sampled from: K4 can reuse the graph's copy
         if normalize:                                                          # :176-180
             row_sums = _row_sums(C)
@@ -165,6 +168,11 @@ def sampling(data, auto_adjust=True, matrix_key="T_forward", cluster_key="louvai
         # come back from the same kernel, so the host never walks the 50M-entry value array.
         t_csr = time.perf_counter()
         timing = {"graph": group.create_graph(C, _CDF_MODES[cdf_mode], sharded=True)}
+        if trusted and not group.graph.canonical():       # unsorted or duplicate columns, or explicit zeros: the rare slow path
+            C = _canonical_csr(M)
+            pristine = C is M
+            timing["graph"] = group.create_graph(C, _CDF_MODES[cdf_mode], sharded=True)
+            timing["graph"]["rebuilt_from_canonical_form"] = True
         timing["host_ms"] = {"open_group": 1e3 * (t_group - t_start), "canonical_csr": 1e3 * (t_csr - t_group),
                              "create_graph": 1e3 * (time.perf_counter() - t_csr)}
         if not normalize:

@@ -71,6 +71,11 @@ int cyp_graph_create_f32(int device, int64_t n_cells, int64_t nnz, const int64_t
 /* Smallest and largest row sum (float64, entries added left to right): the caller applies the
  * reference's normalisation check `1 - 1e-3 <= sum <= 1 + 1e-3` (:182-187) to them. */
 int cyp_graph_row_sum_range(const cyp_graph *g, double *min_sum, double *max_sum);
+/* What K1 saw in the CSR it was given: are every row's columns strictly increasing (sorted, no duplicates), and is there
+ * no explicit zero?  The reference samples from the canonical form (it densifies and re-sparsifies, :168-170, :14); a
+ * caller that holds a CSR of unknown form builds the graph from it as it is and only canonicalises (and rebuilds) when
+ * one of the two comes back 0 -- the check costs the host nothing. */
+int cyp_graph_canonical(const cyp_graph *g, int *columns_strictly_increasing, int *no_explicit_zeros);
 int cyp_graph_destroy(cyp_graph *g);
 int cyp_graph_info(const cyp_graph *g, int64_t *n_cells, int64_t *nnz, int32_t *max_row_nnz,
                    int *cdf_mode, int *device, int64_t *device_bytes);

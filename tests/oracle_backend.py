@@ -21,6 +21,9 @@ class Graph:
     def cdf(self):
         return self._cdf
 
+    def canonical(self):
+        return bool(self.C.has_canonical_format and np.count_nonzero(self.C.data) == self.C.nnz)
+
     def row_sum_range(self):
         r = np.asarray(self.C.sum(axis=1)).ravel()
         return float(r.min()), float(r.max())

@@ -71,6 +71,59 @@ def test_k1_ragged_rows_with_staging_overflow():
         g.close()
 
 
+def test_k1_reports_whether_the_csr_was_canonical():
+    """cyp_graph_canonical: K1 sees every entry, so it tells for free whether every row's columns are strictly increasing
+    and whether an explicit zero is stored -- in the staged path and in the direct path of long rows."""
+    from scipy import sparse
+
+    def variants(C):
+        r = int(np.argmax(np.diff(C.indptr)))                 # a row with at least two entries
+        a = int(C.indptr[r])
+        assert C.indptr[r + 1] - a >= 2
+        yield "canonical", C, True
+        U = C.copy(); U.indices = U.indices.copy(); U.data = U.data.copy()
+        U.indices[[a, a + 1]] = U.indices[[a + 1, a]]; U.data[[a, a + 1]] = U.data[[a + 1, a]]
+        yield "unsorted", U, False
+        D = C.copy(); D.indices = D.indices.copy()
+        D.indices[a + 1] = D.indices[a]
+        yield "duplicate", D, False
+        Z = C.copy(); Z.data = Z.data.copy()
+        Z.data[int(C.indptr[-1]) - 1] = 0.0
+        yield "explicit zero", Z, False
+
+    small = sp.canonical_csr(synth.random_sparse_rows(n=300, max_nnz=12, seed=4, messy=False))
+    rng = np.random.default_rng(5)                            # rows of up to 400 entries: 128 of them overflow K1's staging buffer
+    lens = rng.integers(1, 400, size=700)
+    rows = np.repeat(np.arange(700), lens)
+    cols = np.concatenate([np.sort(rng.choice(700, size=l, replace=False)) for l in lens])
+    big = sp.canonical_csr(sparse.csr_matrix((rng.random(len(cols)) + 1e-3, (rows, cols)), shape=(700, 700)))
+    for C in (small, big, small.astype(np.float32)):
+        for name, M, want in variants(C):
+            g = _lib.Graph(M, _lib.CDF_EXACT)
+            assert g.canonical() == want, name
+            g.close()
+
+
+def test_sampling_canonicalises_a_messy_csr_only_when_k1_says_so():
+    """Unsorted columns, duplicates and explicit zeros (the reference densifies and re-sparsifies, :168-170, :14): sampling()
+    hands the CSR to the graph build as it is, K1 reports it, the host canonicalises and rebuilds -- same result as for the
+    canonical matrix, which is built once."""
+    import pandas as pd
+    from cytopath_b200.sampler import _canonical_csr
+    M = synth.random_sparse_rows(n=150, max_nnz=9, seed=11, messy=True)
+    clusters = np.array(["c%d" % (i % 3) for i in range(150)])
+    out = []
+    for T in (M, _canonical_csr(M)):
+        ad = synth.AnnDataShim(150, pd.DataFrame({"louvain": pd.Categorical(clusters)}), {"T_forward": T})
+        np.random.seed(2)
+        run_quiet(cytopath_b200.sampling, ad, auto_adjust=False, max_steps=8, traj_number=20, sim_number=200, root_cells=[0, 5, 9],
+                  end_points=list(range(100, 150)), min_clusters=1, seed=3)
+        out.append(ad)
+    np.testing.assert_array_equal(out[0].uns["samples"]["cell_sequences"], out[1].uns["samples"]["cell_sequences"])
+    assert out[0].uns["run_info"]["b200"]["timing"]["graph"].get("rebuilt_from_canonical_form") is True
+    assert "rebuilt_from_canonical_form" not in out[1].uns["run_info"]["b200"]["timing"]["graph"]
+
+
 @pytest.mark.parametrize("mode,omode", MODES)
 def test_k1_float32_values_equal_the_widened_matrix(mode, omode):
     """scvelo stores T_forward as float32; the reference widens it with np.float64(toarray()) (:168).
@@ -207,6 +260,25 @@ def test_k4_power_iteration_matches_scipy():
         np.testing.assert_array_equal(state, p)
         np.testing.assert_allclose(got, want, rtol=0, atol=1e-13)
         assert check_convergence_criteria(got, tol=1e-3) == check_convergence_criteria(want, tol=1e-3)
+
+
+def test_k4_hub_columns_and_empty_columns():
+    """SpMV-transpose: columns with thousands of entries overflow the CTA's staging buffer (direct path), empty columns
+    produce 0; the state stays bit-equal to scipy's `p @ T` either way."""
+    T = synth.hub_graph(n=3000, k_typ=(4, 30), hub_share=0.01, k_hub=(2000, 2600), seed=3).T.tocsr()
+    T = sp.canonical_csr(T)
+    keep = np.ones(3000, dtype=bool); keep[[5, 6, 1500, 2999]] = False              # four empty columns
+    T = sp.canonical_csr(T @ __import__("scipy.sparse", fromlist=["diags"]).diags(keep.astype(np.float64)))
+    assert int(np.diff(T.tocsc().indptr).max()) > 1500 and (np.diff(T.tocsc().indptr) == 0).sum() >= 4
+    rng = np.random.default_rng(0)
+    init = rng.random(3000); init /= init.sum()
+    stat = rng.random(3000); stat /= stat.sum()
+    p = init
+    for _ in range(7):
+        p = p @ T
+    got, state = _lib.power_iteration(T, init, stat, 7, return_state=True)
+    np.testing.assert_array_equal(state, p)
+    assert state[5] == 0.0 and state[2999] == 0.0
 
 
 def test_k4_iterate_state_probability_returns_the_reference_history():

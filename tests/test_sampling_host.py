@@ -180,6 +180,28 @@ def test_canonical_csr_equals_densify_resparsify():
     np.testing.assert_array_equal(dense.data, want.data)
 
 
+def test_messy_csr_is_sampled_in_its_canonical_form():
+    """A float CSR goes to the graph build as it is; when K1 reports unsorted / duplicate columns or explicit zeros the
+    host canonicalises it like the reference's densify + re-sparsify (:168-170, :14) and rebuilds: same result as
+    handing over the canonical matrix in the first place."""
+    import pandas as pd
+    from cytopath_b200.synth import AnnDataShim
+    M = synth.random_sparse_rows(n=150, max_nnz=9, seed=11, messy=True)
+    assert not (M.has_canonical_format and np.count_nonzero(M.data) == M.nnz)
+    clusters = np.array(["c%d" % (i % 3) for i in range(150)])
+    out = []
+    for T in (M, _canonical_csr(M)):
+        obs = pd.DataFrame({"louvain": pd.Categorical(clusters)})
+        ad = AnnDataShim(150, obs, {"T_forward": T})
+        np.random.seed(2)
+        run_quiet(cytopath_b200.sampling, ad, auto_adjust=False, max_steps=8, traj_number=20, sim_number=200, root_cells=[0, 5, 9],
+                  end_points=list(range(100, 150)), min_clusters=1, seed=3, _backend=oracle_backend, dist=False)
+        out.append(ad)
+    np.testing.assert_array_equal(out[0].uns["samples"]["cell_sequences"], out[1].uns["samples"]["cell_sequences"])
+    assert out[0].uns["run_info"]["b200"]["timing"]["graph"].get("rebuilt_from_canonical_form") is True
+    assert "rebuilt_from_canonical_form" not in out[1].uns["run_info"]["b200"]["timing"]["graph"]
+
+
 def test_convergence_helpers():
     z = load("convergence_probes")
     for i, want in enumerate(z["result"]):
