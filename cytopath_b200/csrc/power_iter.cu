@@ -20,39 +20,18 @@ namespace cyp {
 
 constexpr int kPiThreads = 256;
 
-// One CTA (kSpThreads threads) per kSpCols consecutive columns.  The CTA's slice of the CSC arrays is contiguous, so the products
-// val[e] * p[row[e]] are formed with coalesced loads (the gathers of p hit the L2: p is 8 bytes per cell) and parked in
-// shared memory; then every thread adds up its own column from there, in increasing row order with separate multiply and
-// add -- the order and rounding of scipy's csc_matvec.  One thread per column reading its 600-byte run straight from HBM
-// (the first version) ran at 25 % of the HBM roofline: 32 lanes, 32 different sectors per load.  Slices that do not fit
-// the staging buffer (hub columns) take that direct path.  Few columns per CTA keep the buffer small (35 KB at k = 50), so
-// that six CTAs share an SM and enough gathers are in flight.
-constexpr int kSpCols = 64;
-constexpr int kSpThreads = 256;
-
-__global__ void __launch_bounds__(kSpThreads)
+// One thread per column, reading its run of the CSC arrays straight from HBM: 0.40 ms per iteration at C4 (612 MB, 23 % of
+// the HBM roofline: 32 lanes touch 32 different sectors per load, the L1 keeps the rest of each sector for the next
+// iterations of the lane).  Tried in round 2 and dropped: one CTA per 64 columns forming the products with coalesced loads
+// into shared memory and adding them up per column from there -- 0.70 ms per iteration (profiles/r02_k2_experiments.md, 6).
+__global__ void __launch_bounds__(kPiThreads)
 spmv_t_kernel(int64_t n, const int64_t *__restrict__ col_ptr, const int32_t *__restrict__ row_idx,
-              const double *__restrict__ val, const double *__restrict__ p, double *__restrict__ p_new, int smem_elems) {
-    extern __shared__ double prod[];
-    const int64_t c0 = static_cast<int64_t>(blockIdx.x) * kSpCols;
-    const int64_t c1 = c0 + kSpCols < n ? c0 + kSpCols : n;
-    const int64_t e0 = col_ptr[c0], e1 = col_ptr[c1];
-    const int64_t j = c0 + threadIdx.x;
-    if (e1 - e0 <= smem_elems) {
-#pragma unroll 4
-        for (int64_t e = e0 + threadIdx.x; e < e1; e += kSpThreads) prod[e - e0] = __dmul_rn(val[e], p[row_idx[e]]);
-        __syncthreads();
-        if (threadIdx.x >= kSpCols || j >= n) return;
-        double acc = 0.0;
-        const int a = static_cast<int>(col_ptr[j] - e0), b = static_cast<int>(col_ptr[j + 1] - e0);
-        for (int e = a; e < b; ++e) acc = __dadd_rn(acc, prod[e]);
-        p_new[j] = acc;
-    } else {
-        if (threadIdx.x >= kSpCols || j >= n) return;
-        double acc = 0.0;
-        for (int64_t e = col_ptr[j]; e < col_ptr[j + 1]; ++e) acc = __dadd_rn(acc, __dmul_rn(val[e], p[row_idx[e]]));
-        p_new[j] = acc;
-    }
+              const double *__restrict__ val, const double *__restrict__ p, double *__restrict__ p_new) {
+    const int64_t j = static_cast<int64_t>(blockIdx.x) * kPiThreads + threadIdx.x;
+    if (j >= n) return;
+    double acc = 0.0;
+    for (int64_t e = col_ptr[j]; e < col_ptr[j + 1]; ++e) acc = __dadd_rn(acc, __dmul_rn(val[e], p[row_idx[e]]));
+    p_new[j] = acc;
 }
 
 // row id and identity permutation of every edge (one thread per row)
@@ -167,16 +146,9 @@ int power_iteration_device(int64_t n_cells, int64_t nnz, const int64_t *d_row_pt
         expand_rows_kernel<<<blocks, kPiThreads>>>(n_cells, d_row_ptr, d_row_of, d_edge);
         step(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_col, d_col_sorted, d_edge, d_perm, static_cast<int>(nnz), 0, key_bits));
         gather_csc_kernel<<<eblocks, kPiThreads>>>(nnz, d_col_sorted, d_perm, d_row_of, d_val, d_row_idx, d_val_t, d_col_ptr, n_cells);
-        // staging buffer of the SpMV: 1.25x a typical slice of kSpCols columns, at most 160 KB
-        int sp_elems = static_cast<int>(1.25 * kSpCols * (static_cast<double>(nnz) / static_cast<double>(n_cells))) + 256;
-        if (sp_elems < 1024) sp_elems = 1024;
-        if (sp_elems > 20 * 1024) sp_elems = 20 * 1024;
-        const int sp_smem = sp_elems * static_cast<int>(sizeof(double));
-        const unsigned sp_blocks = static_cast<unsigned>((n_cells + kSpCols - 1) / kSpCols);
-        step(cudaFuncSetAttribute(spmv_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sp_smem));
         for (int32_t i = 0; i < max_iter; ++i) {
             if (h_history) step(cudaMemcpy(h_history + static_cast<int64_t>(i) * n_cells, d_p, sizeof(double) * n_cells, cudaMemcpyDeviceToHost));   // :71 history[i] = p
-            spmv_t_kernel<<<sp_blocks, kSpThreads, sp_smem>>>(n_cells, d_col_ptr, d_row_idx, d_val_t, d_p, d_q, sp_elems);
+            spmv_t_kernel<<<blocks, kPiThreads>>>(n_cells, d_col_ptr, d_row_idx, d_val_t, d_p, d_q);
             dots_partial_kernel<<<blocks, kPiThreads>>>(n_cells, d_q, d_s, d_partial);
             dots_final_kernel<<<1, kPiThreads>>>(blocks, d_partial, d_eps + i);
             double *t = d_p; d_p = d_q; d_q = t;

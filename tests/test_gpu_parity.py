@@ -263,8 +263,8 @@ def test_k4_power_iteration_matches_scipy():
 
 
 def test_k4_hub_columns_and_empty_columns():
-    """SpMV-transpose: columns with thousands of entries overflow the CTA's staging buffer (direct path), empty columns
-    produce 0; the state stays bit-equal to scipy's `p @ T` either way."""
+    """SpMV-transpose with columns of thousands of entries next to empty ones (which produce 0): the state stays bit-equal
+    to scipy's `p @ T`."""
     T = synth.hub_graph(n=3000, k_typ=(4, 30), hub_share=0.01, k_hub=(2000, 2600), seed=3).T.tocsr()
     T = sp.canonical_csr(T)
     keep = np.ones(3000, dtype=bool); keep[[5, 6, 1500, 2999]] = False              # four empty columns
