@@ -5,8 +5,10 @@
 // replicated.  Because the uniform stream is keyed by (walker, step, round) the result does not depend on the cut,
 // and because a kept sequence is stored as its 16-byte (round, walker, slot) record (session.cu) the ranks exchange
 // records, not rows:
-//   graph      built from the host CSR on ONE rank, then ncclBroadcast of its device arrays (1.6 GB at 1M cells, a few
-//              ms over NVLink) -- not one PCIe upload per GPU;
+//   graph      every rank uploads 1/world of the host CSR over its own PCIe link, ncclAllGather completes it on every
+//              device and each builds the graph itself (cyp_group_graph_create_sharded); or, when only one rank holds the
+//              matrix, built there and ncclBroadcast of its device arrays (1.6 GB at 1M cells, a few ms over NVLink) --
+//              never one full PCIe upload per GPU;
 //   per round  ncclAllGather of every rank's (hash_lo, hash_hi, walker) records -> each rank drops its sequences that
 //              also occur under a lower walker id elsewhere (first occurrence, :330-331; equality is VERIFIED by
 //              replaying both walkers, see session.cu) -> ncclAllGather of the survivors' (walker, slot), so that

@@ -120,7 +120,7 @@ def sampling(data, auto_adjust=True, matrix_key="T_forward", cluster_key="louvai
         CUDA device of a single-GPU run (default 0; LOCAL_RANK under torchrun).
     devices : sequence of int, optional
         Several GPUs driven by THIS process -- a plain function call, no launcher: every round's walkers are cut
-        into one block per device, the graph is built on the first device and broadcast to the others over NVLink,
+        into one block per device, every device uploads its share of the matrix and an all-gather over NVLink completes it,
         the devices exchange 24-byte records of the kept sequences with NCCL all-gathers (the reference's joblib
         fan-out, :306-319).  The result is bit-identical for any number of devices.
     dist : 'auto' | bool
