@@ -610,6 +610,8 @@ def run_b200(args, w):
                         ", cyp_group_session_create, cyp_group_round "
                         "(K2 + K3 + NCCL exchange), cyp_group_select of %d sequences (replay + all-gather) with scores, to the host" % n_fetch},
         "gpu_launches": args.steps,
+        "value_scope": "K2 launches only (communication-free: the path has no collective inside the step loop); the per-round "
+                       "NCCL exchange, the graph upload + all-gather and the selection are timed in e2e / multi_gpu",
         "roofline": roof,
     }
     if multi is not None:
