@@ -1,10 +1,5 @@
-"""Drop-ins for the two helpers that consume the sampler's output first
-(reference cytopath/trajectory_estimation/sample_clustering.py:38-71).
-
-`coordinate_assigner` maps sampled cell sequences to coordinates; `distance_matrix` computes the
-S x S Hausdorff distances that HDBSCAN clusters (:80-84).  In the reference the latter is
-S(S+1)/2 Python-level calls into a numba loop; here it is one CUDA kernel (csrc/hausdorff.cu).
-"""
+"""f2: `coordinate_assigner` / `distance_matrix` of cytopath/trajectory_estimation/sample_clustering.py:38-71, the latter as
+one CUDA kernel (csrc/hausdorff.cu) instead of S(S+1)/2 Python-level calls of a numba loop."""
 from __future__ import annotations
 
 import numpy as np

@@ -1,10 +1,5 @@
-"""`undirected_simulations` — the second caller of the sampler (reference cytopath/utils.py:42-101).
-
-Every (or a random subset of) cell is a root and every cell is an end point, so no walker is
-filtered; the outputs are the sampler's `uns['samples']` (stored as `uns['undirected_samples']`) and
-`obs['log_terminal_state_freq']` = log1p(visits as final state / sim_number).  Same signature and
-side effects as the reference; the sampling itself is `cytopath_b200.sampling` (CUDA).
-"""
+"""f1: `undirected_simulations`, the second caller of the sampler (reference cytopath/utils.py:42-101): every cell (or a random
+subset) is a root, every cell an end point; same signature and side effects, the sampling itself is `cytopath_b200.sampling`."""
 from __future__ import annotations
 
 import numpy as np
