@@ -19,6 +19,7 @@ per-process `np.random.rand` (:43); `num_cores` is accepted and ignored.
 from __future__ import annotations
 
 import math
+import os
 import time
 import warnings
 
@@ -232,7 +233,7 @@ def _sampling_on_graph(adata, copy, group, C, pristine, auto_adjust, matrix_key,
             except Exception:
                 raise ValueError('Root cells must be provided in adata.obs["root_cells"]. Run cytopath.terminal_states')
         else:
-            root_cells = np.asarray(np.where(np.asarray(adata.obs[cluster_key].isin(root_clusters))))[0]
+            root_cells = labels.cells_in(adata.obs[cluster_key], root_clusters)
     adata.uns["run_info"]["root_cells"] = root_cells
     if not end_points:
         if not end_clusters:
@@ -241,11 +242,11 @@ def _sampling_on_graph(adata, copy, group, C, pristine, auto_adjust, matrix_key,
             except Exception:
                 raise ValueError('End points must be provided in adata.obs["end_points"]. Run cytopath.terminal_states')
         else:
-            end_points = np.asarray(np.where(np.asarray(adata.obs[cluster_key].isin(end_clusters))))[0]
+            end_points = labels.cells_in(adata.obs[cluster_key], end_clusters)
     adata.uns["run_info"]["end_points"] = end_points
     end_cells = np.asarray(end_points, dtype=np.int64).reshape(-1)
-    end_point_clusters = labels.of(end_cells) if end_cells.size else np.empty(0, dtype=str)
-    end_clusters_ = np.unique(end_point_clusters)
+    # terminal clusters: the distinct labels of the end points, sorted, and for every end point which of them it has
+    end_clusters_, end_point_cluster = labels.groups_of(end_cells)
     if len(end_clusters_) == 0:
         raise ValueError("Terminal cluster set is empty.")
     roots = np.asarray(root_cells, dtype=np.int64).reshape(-1)
@@ -279,14 +280,14 @@ def _sampling_on_graph(adata, copy, group, C, pristine, auto_adjust, matrix_key,
                          len(slot_cells), max_steps, bool(unique), int(seed))
     t_marks.append(time.perf_counter())
     timing["host_ms"].update(resolve_and_auto_adjust=1e3 * (t_marks[1] - t_marks[0]), labels_and_session=1e3 * (t_marks[2] - t_marks[1]))
-    return _run_rounds(adata, copy, group, roots, end_slot_of_point, end_point_clusters, end_clusters_, trunc,
+    return _run_rounds(adata, copy, group, roots, end_slot_of_point, end_point_cluster, end_clusters_, trunc,
                        max_steps, traj_number, sim_number, min_sim_ratio, rounds_limit, timing, slot_cells, want_rows)
 
 
 class _Labels:
     """The cluster label of every cell as the reference sees it (`adata.obs[cluster_key].astype(str)`, :217) and cut
     to 8 characters (what markov_sim stores, :39,:51), computed per CATEGORY and expanded through the category codes:
-    a million cells cost a few array gathers instead of a million Python string operations."""
+    a million cells cost a few integer gathers instead of a million Python string operations."""
 
     def __init__(self, col):
         self.cats = self.codes = None
@@ -298,34 +299,83 @@ class _Labels:
         except Exception:
             pass
         if self.cats is None:                                    # not categorical after all, or missing values: per cell
-            self.full = np.asarray(col.astype(str).values, dtype=object)
+            self.full = np.array([str(x) for x in col.astype(str).values], dtype=object)    # (a missing value reads 'nan')
+
+    def cells_in(self, col, clusters) -> np.ndarray:
+        """np.where(col.isin(clusters))[0] (:225,:236).  pandas matches `clusters` against the categories and then looks
+        the codes up; with every cell labelled that is one table lookup per cell."""
+        if self.cats is not None:
+            in_cat = np.asarray(col.cat.categories.isin(clusters), dtype=bool)
+            return np.flatnonzero(in_cat[self.codes])
+        return np.asarray(np.where(np.asarray(col.isin(clusters))))[0]
 
     def of(self, cells) -> np.ndarray:
         out = self.cats[self.codes[cells]] if self.cats is not None else self.full[cells]
         return out.astype(str)
 
+    def groups_of(self, cells):
+        """(np.unique(labels of `cells`), index into it for every cell of `cells`)."""
+        if cells.size == 0:
+            return np.empty(0, dtype=str), np.empty(0, dtype=np.int64)
+        if self.cats is None:
+            return np.unique(self.of(cells), return_inverse=True)
+        names, cat_group = np.unique(self.cats.astype(str), return_inverse=True)    # categories may share a str()
+        group = cat_group[self.codes[cells]]
+        present = np.flatnonzero(np.bincount(group, minlength=len(names)))
+        local = np.full(len(names), -1, dtype=np.int64)
+        local[present] = np.arange(len(present))
+        return np.array([str(x) for x in names[present]], dtype=str), local[group]
+
     def truncated(self):
-        """('<U8' label per cell, code of that label per cell, number of codes) -- codes number the distinct truncated
-        labels in sorted order, like np.unique(..., return_inverse=True)."""
+        """(lookup cells -> '<U8' labels, code of that label per cell, number of codes) -- codes number the distinct
+        truncated labels in sorted order, like np.unique(..., return_inverse=True)."""
         if self.cats is not None:
             cut = np.array([c[:8] for c in self.cats], dtype="U8")
             names, cat_code = np.unique(cut, return_inverse=True)
             present = np.zeros(len(names), dtype=bool)
-            present[cat_code[np.unique(self.codes)]] = True       # categories without cells do not count as labels
+            present[cat_code[np.flatnonzero(np.bincount(self.codes, minlength=len(cut)))]] = True   # categories without cells do not count as labels
             renum = np.cumsum(present) - 1
-            return cut[self.codes], renum[cat_code][self.codes].astype(np.int32), int(present.sum())
+            codes = self.codes
+            return (lambda cells, width="U8": _gather_labels(cut, codes, cells, width)), renum[cat_code].astype(np.int32)[codes], int(present.sum())
         trunc = np.array([c[:8] for c in self.full], dtype="U8")
         names, code = np.unique(trunc, return_inverse=True)
-        return trunc, code.astype(np.int32), len(names)
+        return (lambda cells, width="U8": trunc[cells].astype(width)), code.astype(np.int32), len(names)
 
 
-def _run_rounds(adata, copy, group, roots, end_slot_of_point, end_point_clusters, end_clusters_, trunc, max_steps,
+def _gather_labels(cut, codes, cells, width):
+    """cut[codes[cells]].astype(width) -- `cut` holds one '<U8' label per category.  The [sequences, steps] result of a
+    1M-cell run is 250 MB of '<U32' (:312): most of the time goes into touching that memory for the first time, so the
+    rows are gathered as plain uint32 words (no per-element unicode cast, the GIL is released) by a few threads."""
+    cells = np.asarray(cells)
+    n_chars = np.dtype(width).itemsize // 4
+    if n_chars < 8 or cells.ndim == 0:
+        return cut[codes[cells]].astype(width)
+    table = np.zeros((len(cut), n_chars), dtype=np.uint32)
+    table[:, :8] = np.ascontiguousarray(cut).view(np.uint32).reshape(len(cut), 8)
+    flat = cells.reshape(-1)
+    out = np.empty((flat.shape[0], n_chars), dtype=np.uint32)
+    n_threads = min(8, os.cpu_count() or 1) if out.nbytes >= (32 << 20) else 1
+
+    def work(bounds):
+        a, b = bounds
+        np.take(table, codes[flat[a:b]], axis=0, out=out[a:b], mode="clip")      # (codes are category codes: always in range)
+
+    if n_threads == 1:
+        work((0, flat.shape[0]))
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(n_threads) as pool:
+            list(pool.map(work, [(flat.shape[0] * i // n_threads, flat.shape[0] * (i + 1) // n_threads) for i in range(n_threads)]))
+    return out.view(width).reshape(cells.shape)
+
+
+def _run_rounds(adata, copy, group, roots, end_slot_of_point, end_point_cluster, end_clusters_, trunc, max_steps,
                 traj_number, sim_number, min_sim_ratio, rounds_limit, timing, slot_cells, want_rows=True):
     n_roots = len(roots)
     n_slots = int(end_slot_of_point.max()) + 1
     sim_number_ = max(int(sim_number / n_roots), 1)                    # :285
     # per terminal cluster: the end-point slots in the order the reference scans them
-    cluster_slots = [end_slot_of_point[end_point_clusters == name] for name in end_clusters_]
+    cluster_slots = [end_slot_of_point[end_point_cluster == k] for k in range(len(end_clusters_))]
 
     slot_counts = np.zeros(n_slots, dtype=np.int64)                   # kept sequences per end point, all rounds
     t_rounds = time.perf_counter()
@@ -392,7 +442,7 @@ def _run_rounds(adata, copy, group, roots, end_slot_of_point, end_point_clusters
     adata.uns["samples"] = {
         "cell_sequences": cell_sequences,
         "transition_score": scores,
-        "cluster_sequences": trunc[cell_sequences].astype(width),
+        "cluster_sequences": trunc(cell_sequences, width),
     }
     adata.uns["run_info"]["b200"] = {"rounds": stats, "world_size": group.world, "select": sel, "timing": timing,
                                      "kernel": group.graph.variant_name() if hasattr(group.graph, "variant_name") else ""}

@@ -202,6 +202,50 @@ def test_messy_csr_is_sampled_in_its_canonical_form():
     assert "rebuilt_from_canonical_form" not in out[1].uns["run_info"]["b200"]["timing"]["graph"]
 
 
+def test_label_helpers_equal_the_per_cell_formulas():
+    """_Labels works per category and expands through the codes; the results are those of the reference's per-cell
+    expressions (`obs[key].astype(str)`, `isin`, `np.unique`, the U8 store of :39) -- with unused categories, labels
+    longer than 8 characters that collide once cut, categories that share a str(), and missing values (fallback)."""
+    from cytopath_b200.sampler import _Labels
+    rng = np.random.default_rng(0)
+    cats = pd.Index(["stem0", "a_very_long_label_one", "a_very_long_label_two", "b", 1, "1", "zz_unused"], dtype=object)
+    codes = rng.integers(0, len(cats) - 1, size=5000)
+    for with_nan in (False, True):
+        c = codes.copy()
+        if with_nan:
+            c[::97] = -1
+        col = pd.Series(pd.Categorical.from_codes(c, categories=cats))
+        lab = _Labels(col)
+        assert (lab.cats is None) == with_nan
+        strs = np.array([str(x) for x in col.astype(str).values], dtype=str)
+        for wanted in (["b", 1], ["1"], ["nope"], ["stem0", "a_very_long_label_two", "zz_unused"]):
+            np.testing.assert_array_equal(lab.cells_in(col, wanted), np.where(np.asarray(col.isin(wanted)))[0])
+        cells = rng.choice(5000, size=700, replace=True)
+        names, local = lab.groups_of(cells)
+        want_names = np.unique(strs[cells])
+        np.testing.assert_array_equal(names, want_names)
+        assert names.dtype == want_names.dtype
+        np.testing.assert_array_equal(names[local], strs[cells])
+        only_b = np.flatnonzero(strs == "b")[:5]
+        np.testing.assert_array_equal(lab.groups_of(only_b)[0], np.array(["b"]))
+        assert lab.groups_of(np.empty(0, dtype=np.int64))[0].size == 0
+        lookup, code, n_codes = lab.truncated()
+        cut = np.array([x[:8] for x in strs], dtype="U8")
+        want_u, want_code = np.unique(cut, return_inverse=True)
+        np.testing.assert_array_equal(lookup(cells), cut[cells])
+        np.testing.assert_array_equal(lookup(cells.reshape(70, 10)), cut[cells.reshape(70, 10)])
+        np.testing.assert_array_equal(code, want_code)
+        assert code.dtype == np.int32 and n_codes == len(want_u)
+        for width in ("U8", "U32"):
+            got = lookup(cells.reshape(70, 10), width)
+            assert got.dtype == np.dtype(width)
+            np.testing.assert_array_equal(got, cut[cells.reshape(70, 10)].astype(width))
+        big = rng.integers(0, 5000, size=(1500, 200))                 # 38 MB of '<U32': the threaded gather
+        got = lookup(big, "U32")
+        assert got.dtype == np.dtype("U32") and got.shape == big.shape
+        np.testing.assert_array_equal(got, cut[big].astype("U32"))
+
+
 def test_convergence_helpers():
     z = load("convergence_probes")
     for i, want in enumerate(z["result"]):
